@@ -1,0 +1,219 @@
+/* rt3cuda.h — C ABI of the B200-native render core (librt3cuda.so).
+ *
+ * This is the drop-in boundary for RayTracer-3's per-pixel hot path. A host
+ * renderer backend (raytracer-3_b200/host/CudaRenderer.cpp, or a backend a
+ * maintainer adds to the reference tree — see INTEGRATION.md) implements the
+ * reference plug-in interface
+ *     RayTracer::Renderer::prerender(const Tools::Array<ECS::RenderEntity*>&)
+ *     RayTracer::Renderer::render(Camera&) const
+ *     RayTracer::initialize_renderer()
+ * (reference src/lib/renderer/Renderer.hpp:34-63) on top of these calls:
+ *
+ *   reference interface                                   this ABI
+ *   ---------------------------------------------------   --------------------------
+ *   initialize_renderer()        Renderer.hpp:63          rt3_create
+ *   ~Renderer()                  Renderer.hpp:45          rt3_destroy
+ *   Renderer::prerender upload   VulkanRenderer.cpp:266   rt3_scene_upload
+ *   Renderer::render             Renderer.hpp:50,         rt3_render / rt3_render_aov
+ *                                SequentialRenderer.cpp:269-308
+ *   DLOG(fatal, msg)             Main.cpp:305-308         non-zero status + rt3_last_error
+ *
+ * Plain C: pointers and sizes only, no C++ or torch types, no exceptions across
+ * the boundary. All functions return 0 on success, a negative rt3 status on
+ * failure; rt3_last_error() then describes it (thread-local string).
+ * There is no CPU fallback: without a CUDA device rt3_create fails.
+ */
+#ifndef RT3CUDA_H
+#define RT3CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT3_OK 0
+#define RT3_ERR_INVALID (-1)   /* bad argument / inconsistent scene */
+#define RT3_ERR_CUDA (-2)      /* CUDA runtime error (message has the cudaError string) */
+#define RT3_ERR_NO_SCENE (-3)  /* render called before rt3_scene_upload */
+#define RT3_ERR_NO_DEVICE (-4) /* no usable CUDA device */
+
+/* ---- scene -------------------------------------------------------------- */
+
+/* The reference's flattened face record, byte for byte
+ * (GFace, reference src/lib/renderer/Vertex.hpp:39-51; sizeof == 48). */
+typedef struct rt3_face {
+    uint32_t v1, v2, v3; /* indices into the vertex array */
+    uint32_t _pad0;
+    float normal[3];     /* host-computed face normal (Triangle.cpp:48, Object.cpp:193, Sphere.cpp:153) */
+    float _pad1;
+    float color[3];      /* baked flat colour (Sphere.cpp:155, Object.cpp:194) / albedo */
+    float _pad2;
+} rt3_face;
+
+/* The reference's vertex record (glm::vec4, w = 0; SequentialRenderer.hpp:31). */
+typedef struct rt3_vertex {
+    float x, y, z, w;
+} rt3_vertex;
+
+#define RT3_MAT_LAMBERTIAN 0u
+#define RT3_MAT_METAL 1u
+#define RT3_MAT_DIELECTRIC 2u
+
+/* Material record. The reference ECS carries only a colour per entity
+ * (Sphere.hpp:44, Triangle.hpp:34, Object.hpp:37); the material table is the
+ * extension the bounce loop needs (raytracer_v4.glsl:255-283 reserves
+ * obj_material for it). */
+typedef struct rt3_material {
+    uint32_t kind;   /* RT3_MAT_* */
+    float albedo[3]; /* attenuation for Lambertian / metal; ignored for dielectric */
+    float fuzz;      /* metal: radius of the perturbation ball, clamped to [0,1] */
+    float ior;       /* dielectric: index of refraction */
+    float _pad[2];
+} rt3_material;
+
+/* Analytic sphere (raytracer_v4.glsl:43-50 `Sphere`): centre + radius.
+ * A negative radius gives the hollow-glass inward-normal sphere. */
+typedef struct rt3_sphere {
+    float cx, cy, cz, r;
+} rt3_sphere;
+
+/* Everything is copied during rt3_scene_upload; the caller keeps ownership
+ * (the reference deletes its entities right after render, Main.cpp:286-288).
+ * Primitive ids in AOVs: faces are 0..n_faces-1 in array order (the reference's
+ * order, SequentialRenderer.cpp:174-195), spheres follow at n_faces + i
+ * (faces are tested before spheres, raytracer_v4.glsl:227-245). */
+typedef struct rt3_scene {
+    uint32_t n_faces;
+    uint32_t n_vertices;
+    const rt3_face* faces;
+    const rt3_vertex* vertices;
+    const uint32_t* face_material; /* per face index into materials; NULL: Lambertian(face colour) */
+    const uint32_t* face_entity;   /* per face entity id; NULL: 0 */
+
+    uint32_t n_spheres;
+    uint32_t n_materials;
+    const rt3_sphere* spheres;
+    const float* sphere_color;       /* 3 floats per sphere: flat colour in reference mode, albedo when sphere_material is NULL */
+    const uint32_t* sphere_material; /* per sphere index into materials; NULL: Lambertian(sphere colour) */
+    const uint32_t* sphere_entity;   /* per sphere entity id; NULL: 0 */
+    const rt3_material* materials;
+} rt3_scene;
+
+/* ---- camera ------------------------------------------------------------- */
+
+/* The four public vectors of the reference Camera (camera/Camera.hpp:27-34;
+ * GPU mirror GCameraData, VulkanRenderer.hpp:32-37), plus an optional thin
+ * lens (lens_radius == 0: pinhole, lens_u / lens_v ignored). */
+typedef struct rt3_camera {
+    float origin[3];
+    float horizontal[3];
+    float vertical[3];
+    float lower_left_corner[3];
+    float lens_radius;
+    float lens_u[3];
+    float lens_v[3];
+} rt3_camera;
+
+/* ---- render parameters -------------------------------------------------- */
+
+/* RT3_MODE_REFERENCE: the reference's ray caster, in the reference's
+ *   arithmetic order with no FMA contraction: one un-jittered primary ray per
+ *   pixel, brute-force closest hit, flat baked colour or sky gradient
+ *   (SequentialRenderer.cpp:47-109,284-297). spp/max_depth/seed are ignored.
+ *   All rows are rendered (the reference's CPU loop skips the last row,
+ *   SequentialRenderer.cpp:286; its GLSL renders it, raytracer_v3.glsl:193).
+ * RT3_MODE_PATHTRACE: spp jittered samples per pixel, multi-bounce
+ *   Lambertian / metal / dielectric shading up to max_depth segments,
+ *   order-independent fixed-point accumulation, gamma-2 resolve. */
+#define RT3_MODE_REFERENCE 0u
+#define RT3_MODE_PATHTRACE 1u
+
+#define RT3_FLAG_NO_JITTER 0x1u /* pathtrace: sample pixel centres (deterministic primary rays) */
+#define RT3_FLAG_NO_GAMMA 0x2u  /* pathtrace: resolve the linear mean instead of its square root */
+
+typedef struct rt3_params {
+    uint32_t width;
+    uint32_t height;
+    uint32_t mode;      /* RT3_MODE_* */
+    uint32_t spp;       /* samples per pixel (pathtrace), 1..65535 */
+    uint32_t max_depth; /* maximum ray segments per path (pathtrace), >= 1 */
+    uint32_t seed;
+    uint32_t flags;     /* RT3_FLAG_* */
+    /* Row-tile partition (multi-GPU): the image is cut into tiles of tile_rows
+     * rows; this context renders tiles t with t % part_count == part_index.
+     * part_count <= 1 renders everything. Results do not depend on the
+     * partition (per-pixel RNG counters use the global pixel index). */
+    uint32_t tile_rows;
+    uint32_t part_index;
+    uint32_t part_count;
+} rt3_params;
+
+/* Timings and counters of the most recent render on this context. */
+typedef struct rt3_stats {
+    double device_ms;       /* CUDA-event time of the render kernels (+ resolve), on the render stream */
+    double h2d_ms;          /* host->device copies inside rt3_render (camera/params) */
+    double d2h_ms;          /* device->host copy of the frame / AOVs */
+    uint64_t rays;          /* ray segments traced (primary + bounce), counted by the kernel */
+    uint64_t sphere_tests;  /* ray-sphere tests = rays * n_spheres (brute force) */
+    uint64_t face_tests;    /* ray-triangle tests = rays * n_faces */
+    uint32_t kernel_launches;
+    uint32_t rows_rendered; /* rows owned by this partition */
+} rt3_stats;
+
+typedef struct rt3_ctx rt3_ctx;
+
+/* ---- entry points ------------------------------------------------------- */
+
+const char* rt3_last_error(void);
+
+/* Creates a context on CUDA device `device` (>= 0). */
+int rt3_create(rt3_ctx** out, int device);
+int rt3_destroy(rt3_ctx* ctx);
+
+/* Flattens the scene into device SoA arrays (replacing any previous scene). */
+int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* scene);
+
+/* Renders into a HOST frame of width*height packed pixels, reference packing
+ * r<<24 | g<<16 | b<<8 | 0xFF, index y*width + x, row 0 = top
+ * (SequentialRenderer.cpp:297, Frame.hpp:44). With a partition, only the rows
+ * this context owns are written. Blocking, like the reference's render(). */
+int rt3_render(rt3_ctx* ctx, const rt3_camera* camera, const rt3_params* params, uint32_t* host_frame);
+
+/* As rt3_render, and also returns per pixel the closest-hit AOVs of the
+ * primary ray: primitive id (0xFFFFFFFF on a miss), entity id (0xFFFFFFFF on
+ * a miss) and hit distance along the un-normalised primary direction (+inf on
+ * a miss). Any of the three output pointers may be NULL.
+ * Only RT3_MODE_REFERENCE is supported. */
+int rt3_render_aov(rt3_ctx* ctx, const rt3_camera* camera, const rt3_params* params, uint32_t* host_frame,
+                   uint32_t* host_hit_prim, uint32_t* host_hit_entity, float* host_hit_t);
+
+/* Device-resident variant for multi-GPU plumbing: renders this partition's
+ * rows into `device_frame` (a device pointer to width*height uint32, full-frame
+ * indexing) asynchronously on `cuda_stream` (a cudaStream_t; NULL = the
+ * context's own stream). No host copies, no synchronisation. */
+int rt3_render_device(rt3_ctx* ctx, const rt3_camera* camera, const rt3_params* params, uint32_t* device_frame,
+                      void* cuda_stream);
+
+/* Number of rows `part_index` owns under (height, tile_rows, part_count), and
+ * packing/unpacking between full-frame row order and a partition's compact
+ * slab (its owned rows, top to bottom) for the frame-end gather. Both run on
+ * the device, asynchronously on `cuda_stream`. */
+uint32_t rt3_partition_rows(uint32_t height, uint32_t tile_rows, uint32_t part_index, uint32_t part_count);
+int rt3_pack_partition(rt3_ctx* ctx, const uint32_t* device_frame, uint32_t* device_slab, uint32_t width, uint32_t height,
+                       uint32_t tile_rows, uint32_t part_index, uint32_t part_count, void* cuda_stream);
+int rt3_unpack_partition(rt3_ctx* ctx, const uint32_t* device_slab, uint32_t* device_frame, uint32_t width, uint32_t height,
+                         uint32_t tile_rows, uint32_t part_index, uint32_t part_count, void* cuda_stream);
+
+int rt3_get_stats(rt3_ctx* ctx, rt3_stats* out);
+
+/* Achieved FP32 FMA throughput of a dependent-chain-free FFMA micro-kernel on
+ * this context's device, in TFLOP/s (2 FLOP per FMA): the measured
+ * denominator for the roofline fraction. */
+int rt3_measure_fma_peak(rt3_ctx* ctx, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RT3CUDA_H */
