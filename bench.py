@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the per-pixel render path on N B200s (one process per GPU).
+
+Workload (BASELINE.json configs[1]): RTIOW book-1 cover scene (~484 analytic
+spheres, mixed materials, thin lens), 1200x800, 500 spp, depth 50. One "step" is
+one full frame: camera in, packed uint32 framebuffer out.
+
+  value : device-timed (CUDA events on the render stream) whole-job Mrays/s with
+          the scene and frame resident in HBM; rays = ray segments the kernel counted.
+  e2e   : the same frame through the reference-facing C-ABI call rt3_render() with a
+          HOST frame buffer (N=1), or device render + NCCL gather + D2H into pinned
+          host memory on rank 0 (N>1); host<->device copies inside the timed region.
+  --impl reference : the CPU implementation of the same path (the oracle port of the
+          RTIOW semantics -- the reference itself has no bounce loop) on all host threads.
+
+N>1: the frame's row tiles are dealt round-robin to the ranks (no data-path collective
+while rendering); the packed framebuffer is gathered with NCCL at frame end. The frame
+is fixed, so scaling is strong.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, SPP, DEPTH, SEED, TILE_ROWS = 1200, 800, 500, 50, 1, 8
+FLOP_PER_SPHERE_TEST, FLOP_PER_FACE_TEST = 17, 45
+CPU_SAMPLE = dict(width=240, height=160, spp=16)    # bounded sample of the same workload for the CPU legs
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def workload_config():
+    return {"workload": f"RTIOW book-1 cover scene, {W}x{H}, {SPP} spp, depth {DEPTH} (BASELINE configs[1])",
+            "width": W, "height": H, "spp": SPP, "max_depth": DEPTH, "tile_rows": TILE_ROWS,
+            "l2": "256 MiB buffer written between timed steps (L2 flush); scene+accumulators re-read from HBM"}
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons during the timed region (nvidia-smi, 200 ms)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 7 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i] == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows),
+                "power_w_max": max(float(r[2]) for r in rows)}
+
+
+def cpu_port_rate(n_threads, steps=1, warmup=0):
+    """Mrays/s of the oracle port on a bounded sample of the workload (all ray segments counted)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import rt3_b200  # noqa: F401
+    from rt3_b200 import abi, scenes
+    import oraclelib
+    w, h, spp = CPU_SAMPLE["width"], CPU_SAMPLE["height"], CPU_SAMPLE["spp"]
+    scene, cam = scenes.rtiow_cover(w, h)
+    params = abi.make_params(w, h, mode=abi.MODE_PATHTRACE, spp=spp, max_depth=DEPTH, seed=SEED)
+    for _ in range(warmup):
+        oraclelib.oracle_pathtrace(scene, cam, params, n_threads=n_threads)
+    t0 = time.perf_counter()
+    rays = 0
+    for _ in range(steps):
+        _, _, r = oraclelib.oracle_pathtrace(scene, cam, params, n_threads=n_threads)
+        rays += r
+    dt = time.perf_counter() - t0
+    sample = f"same scene and camera at {w}x{h}, {spp} spp, depth {DEPTH}: {rays // max(steps, 1)} ray segments per step"
+    return rays / dt / 1e6, dt / max(steps, 1), sample
+
+
+def reference_native_rate():
+    """The compiled reference's own render loop (oracle/_ref) on its default-scene shape: 1 core, 1 spp, depth 1."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import oraclelib
+        if not oraclelib.have_ref() or not os.path.exists(oraclelib.REF_TEDDY):
+            return None
+        rs = oraclelib.RefScene()
+        rs.add_object(oraclelib.REF_TEDDY, (0, 0, -3), 1.0 / 17.0, (1, 0, 0))
+        rs.add_sphere((-2, 0, -5), 1.0, 8, 8, (0, 0, 1))
+        rs.prerender()
+        w, h = 200, 113
+        _, sec = rs.render(w, h)
+        return {"kind": "reference", "what": f"reference SequentialRenderer::render, Main.cpp default scene (3288 faces), {w}x{h}, 1 spp, depth 1",
+                "cores": 1, "value": w * (h - 1) / sec / 1e6, "unit": "Mrays/s", "seconds": round(sec, 3)}
+    except Exception as e:  # the reference leg is informative only
+        return {"kind": "reference", "error": str(e)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_threads = os.cpu_count() or 1
+    rate, sec_per_step, sample = cpu_port_rate(n_threads, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": rate, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
+        "cpu_baseline": {"value": rate, "unit": "Mrays/s", "cores": n_threads, "kind": "port", "sample": sample,
+                         "note": "the reference has no bounce loop/materials (raytracer_v4.glsl:279); this is the CPU restatement of the same path"},
+        "e2e": {"value": rate, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_native": reference_native_rate(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="rt3", choices=["rt3", "reference"])
+    ap.add_argument("--spp", type=int, default=SPP, help="override samples per pixel (non-default values are not the BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import rt3_b200  # noqa: F401
+    from rt3_b200 import abi, scenes
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the render core has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    spp = args.spp
+    scene, cam = scenes.rtiow_cover(W, H)
+    ctx = abi.Context(local_rank)
+    ctx.upload(scene)
+    params = abi.make_params(W, H, mode=abi.MODE_PATHTRACE, spp=spp, max_depth=DEPTH, seed=SEED,
+                             tile_rows=TILE_ROWS, part_index=rank, part_count=world)
+    lib = ctx.lib
+    stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream: kernels, NCCL and the timing events all go here
+    torch.cuda.set_stream(stream)
+    frame = torch.zeros(H * W, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    my_rows = lib.rt3_partition_rows(H, TILE_ROWS, rank, world)
+    max_rows = max(lib.rt3_partition_rows(H, TILE_ROWS, r, world) for r in range(world))
+    slab = torch.zeros(max_rows * W, dtype=torch.int32, device=dev)
+    gathered = [torch.zeros(max_rows * W, dtype=torch.int32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    host_frame_t = torch.zeros(H * W, dtype=torch.int32).pin_memory()
+    host_frame = host_frame_t.numpy().view(np.uint32).reshape(H, W)
+    launches_per_step = 3  # clear_accum + pathtrace + resolve
+
+    def device_step():
+        """Render this rank's rows; N>1: gather the packed framebuffer onto rank 0 (NCCL) and de-interleave."""
+        ctx.render_device(cam, params, frame.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            ctx.pack_partition(frame.data_ptr(), slab.data_ptr(), W, H, TILE_ROWS, rank, world, stream.cuda_stream)
+            dist.gather(slab, gathered, dst=0)
+            if rank == 0:
+                for r in range(1, world):
+                    ctx.unpack_partition(gathered[r].data_ptr(), frame.data_ptr(), W, H, TILE_ROWS, r, world, stream.cuda_stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 0)):
+        flush.fill_(1)
+        device_step()
+    sync_all()
+    rays_step = torch.tensor([ctx.stats().rays], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(rays_step)
+    rays_per_step = int(rays_step.item())  # deterministic: identical every step
+
+    # ---- timed: device-resident ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    for s in range(args.steps):
+        flush.fill_(s)  # L2 flush, outside the per-step events
+        ev[s][0].record(stream)
+        device_step()
+        ev[s][1].record(stream)
+    sync_all()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    st = ctx.stats()  # last step's dominant-kernel time and counters (this rank)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- timed: end to end with host buffers ----
+    e2e_steps = args.steps
+    sync_all()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        if world == 1:
+            ctx.render(cam, params, out=host_frame)     # rt3_render: blocking, D2H into the pinned host frame
+        else:
+            device_step()
+            if rank == 0:
+                host_frame_t.copy_(frame, non_blocking=True)
+            torch.cuda.synchronize()
+    sync_all()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = rays_per_step * args.steps / (total_ms * 1e-3) / 1e6
+        e2e_value = rays_per_step * e2e_steps / e2e_s / 1e6
+        # roofline of the dominant kernel (pathtrace_kernel), this rank's launch
+        flops = FLOP_PER_SPHERE_TEST * st.sphere_tests + FLOP_PER_FACE_TEST * st.face_tests
+        achieved = flops / (st.trace_kernel_ms * 1e-3) / 1e12 if st.trace_kernel_ms > 0 else 0.0
+        peak = ctx.measure_fma_peak()
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(),
+            "rays_per_step": rays_per_step, "spheres": scene.n_spheres,
+            "clocks": clocks, "gpu_launches": launches_per_step * args.steps + (0 if world == 1 else (1 + (world - 1)) * args.steps),
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": ctypes.sizeof(abi.Camera) + ctypes.sizeof(abi.Params),
+                    "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                    "path": "rt3_render (C ABI), pinned host frame" if world == 1 else "rt3_render_device + NCCL gather + D2H on rank 0"},
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                         "traffic": None, "kernel": "pathtrace_kernel", "kernel_ms": st.trace_kernel_ms,
+                         "algorithmic": f"{FLOP_PER_SPHERE_TEST} FLOP x {st.sphere_tests} ray-sphere tests (rank 0 launch)",
+                         "peak_source": "FFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                         "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS},
+        }
+        if spp != SPP:
+            line["config"]["workload"] += f" [OVERRIDE spp={spp}: not the BASELINE config]"
+            line["config"]["spp"] = spp
+        if world == 1 and not args.no_cpu_baseline:
+            n_threads = os.cpu_count() or 1
+            rate, _, sample = cpu_port_rate(n_threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "Mrays/s", "cores": n_threads, "kind": "port", "sample": sample}
+            line["reference_native"] = reference_native_rate()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -151,7 +151,8 @@ typedef struct rt3_params {
 
 /* Timings and counters of the most recent render on this context. */
 typedef struct rt3_stats {
-    double device_ms;       /* CUDA-event time of the render kernels (+ resolve), on the render stream */
+    double device_ms;       /* CUDA-event time of all render kernels (clear + trace + resolve), on the render stream */
+    double trace_kernel_ms; /* CUDA-event time of the dominant kernel alone (reference_kernel / pathtrace_kernel) */
     double h2d_ms;          /* host->device copies inside rt3_render (camera/params) */
     double d2h_ms;          /* device->host copy of the frame / AOVs */
     uint64_t rays;          /* ray segments traced (primary + bounce), counted by the kernel */

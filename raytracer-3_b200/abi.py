@@ -71,7 +71,7 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [
-        ("device_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+        ("device_ms", C.c_double), ("trace_kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("rays", C.c_uint64), ("sphere_tests", C.c_uint64), ("face_tests", C.c_uint64),
         ("kernel_launches", C.c_uint32), ("rows_rendered", C.c_uint32),
     ]

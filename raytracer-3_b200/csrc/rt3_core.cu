@@ -1,0 +1,586 @@
+/* rt3_core.cu — host side of librt3cuda.so: the C ABI of include/rt3cuda.h.
+ *
+ * Owns one CUDA context per rt3_ctx: the flattened scene in HBM (SoA), the
+ * frame / AOV / accumulator buffers, a stream and the timing events. Scene
+ * upload mirrors what the reference's GPU backend does in prerender
+ * (reference src/lib/renderer/VulkanRenderer.cpp:266-399: flatten once, keep
+ * on the device, reuse across render() calls); render mirrors
+ * VulkanRenderer.cpp:402-557 without its per-call pipeline rebuild.
+ *
+ * Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+ * (see __graft_entry__.build()). There is no CPU path in this library.
+ */
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "rt3_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define RT3_CUDA(call)                                                                                           \
+    do {                                                                                                         \
+        cudaError_t e__ = (call);                                                                                \
+        if (e__ != cudaSuccess) { return fail(RT3_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); } \
+    } while (0)
+
+template <class T> struct DeviceBuffer {
+    T* ptr = nullptr;
+    size_t count = 0;
+    int reserve(size_t n) {
+        if (n <= count) { return RT3_OK; }
+        if (ptr) { cudaFree(ptr); ptr = nullptr; count = 0; }
+        RT3_CUDA(cudaMalloc(&ptr, n * sizeof(T)));
+        count = n;
+        return RT3_OK;
+    }
+    void release() { if (ptr) { cudaFree(ptr); } ptr = nullptr; count = 0; }
+};
+
+}  // namespace
+
+struct rt3_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int rays_per_thread = 2;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_copy = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaStream_t last_stream = nullptr; /* stream of the most recent render */
+    bool stats_pending = false;         /* timings / counters not yet read back */
+    bool copy_timed = false;
+
+    bool has_scene = false;
+    rt3_scene_view view{};
+    DeviceBuffer<float4> bounds, face_n, face_p1, face_p2, face_p3, spheres, prim_color, materials;
+    DeviceBuffer<uint32_t> prim_material, prim_entity;
+
+    DeviceBuffer<uint32_t> frame, aov_prim, aov_entity;
+    DeviceBuffer<float> aov_t;
+    DeviceBuffer<unsigned long long> accum, counters;
+
+    rt3_stats stats{};
+};
+
+namespace {
+
+uint32_t owned_rows(uint32_t height, uint32_t tile_rows, uint32_t part_index, uint32_t part_count) {
+    if (tile_rows == 0) { tile_rows = 1; }
+    if (part_count <= 1) { return height; }
+    uint32_t n_tiles = (height + tile_rows - 1) / tile_rows, rows = 0;
+    for (uint32_t t = part_index; t < n_tiles; t += part_count) {
+        uint32_t first = t * tile_rows;
+        rows += (height - first < tile_rows) ? height - first : tile_rows;
+    }
+    return rows;
+}
+
+int make_kparams(const rt3_params* p, rt3_kparams* k) {
+    if (!p) { return fail(RT3_ERR_INVALID, "params is NULL"); }
+    if (p->width < 2 || p->height < 2) { return fail(RT3_ERR_INVALID, "frame must be at least 2x2 (got %ux%u)", p->width, p->height); }
+    if ((unsigned long long) p->width * p->height > 0xFFFFFFFFull) { return fail(RT3_ERR_INVALID, "frame too large"); }
+    if (p->mode != RT3_MODE_REFERENCE && p->mode != RT3_MODE_PATHTRACE) { return fail(RT3_ERR_INVALID, "unknown mode %u", p->mode); }
+    if (p->mode == RT3_MODE_PATHTRACE && (p->spp < 1 || p->spp > 65535 || p->max_depth < 1)) {
+        return fail(RT3_ERR_INVALID, "pathtrace needs 1 <= spp <= 65535 and max_depth >= 1 (got spp %u, depth %u)", p->spp, p->max_depth);
+    }
+    uint32_t parts = p->part_count ? p->part_count : 1;
+    if (p->part_index >= parts) { return fail(RT3_ERR_INVALID, "part_index %u >= part_count %u", p->part_index, parts); }
+    k->width = p->width; k->height = p->height;
+    k->spp = p->mode == RT3_MODE_PATHTRACE ? p->spp : 1;
+    k->max_depth = p->max_depth; k->seed = p->seed; k->flags = p->flags;
+    k->tile_rows = p->tile_rows ? p->tile_rows : 1;
+    k->part_index = p->part_index; k->part_count = parts;
+    k->owned_rows = owned_rows(p->height, k->tile_rows, p->part_index, parts);
+    k->n_pixels = (unsigned long long) k->owned_rows * p->width;
+    k->n_items = k->n_pixels * k->spp;
+    k->resident = 0;
+    return RT3_OK;
+}
+
+float round_down(double v) {
+    float f = (float) v;
+    if ((double) f > v) { f = std::nextafterf(f, -std::numeric_limits<float>::infinity()); }
+    return f;
+}
+
+/* Prefilter entry for a bounding sphere (double centre c, radius r >= 0). */
+float4 make_bound(const double c[3], double r) {
+    const float never[4] = { 0.0f, 0.0f, 0.0f, std::numeric_limits<float>::infinity() };
+    float4 out = { never[0], never[1], never[2], never[3] };
+    if (!(std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]) && std::isfinite(r))) { return out; }
+    float cf[3] = { (float) c[0], (float) c[1], (float) c[2] };
+    double cc = (double) cf[0] * cf[0] + (double) cf[1] * cf[1] + (double) cf[2] * cf[2];
+    double clen = std::sqrt(cc);
+    /* inflate: relative 2^-10, absolute 2^-16 (|c| + r) (centre rounding, hit-point rounding of the exact tests) */
+    double re = r * (1.0 + 1.0 / 1024.0) + (clen + r) / 65536.0 + 1e-30;
+    double k = cc - re * re - (double) RT3_FILTER_SLACK * (cc + re * re);
+    float kf = round_down(k);
+    if (!std::isfinite(kf)) { return out; }
+    out.x = cf[0]; out.y = cf[1]; out.z = cf[2]; out.w = kf;
+    return out;
+}
+
+/* Smallest sphere through/around a triangle (double precision). */
+void triangle_bound(const double a[3], const double b[3], const double c[3], double centre[3], double* radius) {
+    const double* v[3] = { a, b, c };
+    auto dist = [](const double* p, const double* q) {
+        return std::sqrt((p[0] - q[0]) * (p[0] - q[0]) + (p[1] - q[1]) * (p[1] - q[1]) + (p[2] - q[2]) * (p[2] - q[2]));
+    };
+    /* longest edge first: if the opposite vertex lies inside its diameter sphere, that sphere is minimal */
+    int e0 = 0;
+    double best = -1.0;
+    for (int e = 0; e < 3; e++) { double l = dist(v[e], v[(e + 1) % 3]); if (l > best) { best = l; e0 = e; } }
+    const double *p = v[e0], *q = v[(e0 + 1) % 3], *o = v[(e0 + 2) % 3];
+    double mid[3] = { 0.5 * (p[0] + q[0]), 0.5 * (p[1] + q[1]), 0.5 * (p[2] + q[2]) };
+    if (dist(mid, o) <= 0.5 * best) { memcpy(centre, mid, sizeof mid); *radius = 0.5 * best; return; }
+    /* acute: circumsphere */
+    double ab[3] = { b[0] - a[0], b[1] - a[1], b[2] - a[2] }, ac[3] = { c[0] - a[0], c[1] - a[1], c[2] - a[2] };
+    double n[3] = { ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0] };
+    double n2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    double ab2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2], ac2 = ac[0] * ac[0] + ac[1] * ac[1] + ac[2] * ac[2];
+    if (n2 > 0.0 && std::isfinite(n2)) {
+        /* centre = a + (|ac|^2 (n x ab) + |ab|^2 (ac x n)) / (2 |n|^2) */
+        double nxab[3] = { n[1] * ab[2] - n[2] * ab[1], n[2] * ab[0] - n[0] * ab[2], n[0] * ab[1] - n[1] * ab[0] };
+        double acxn[3] = { ac[1] * n[2] - ac[2] * n[1], ac[2] * n[0] - ac[0] * n[2], ac[0] * n[1] - ac[1] * n[0] };
+        for (int i = 0; i < 3; i++) { centre[i] = a[i] + (ac2 * nxab[i] + ab2 * acxn[i]) / (2.0 * n2); }
+    } else {
+        for (int i = 0; i < 3; i++) { centre[i] = (a[i] + b[i] + c[i]) / 3.0; }
+    }
+    double r = 0.0;
+    for (int i = 0; i < 3; i++) { double l = dist(centre, v[i]); if (l > r) { r = l; } }
+    *radius = r;
+}
+
+template <class T> int upload(DeviceBuffer<T>& buf, const std::vector<T>& host, cudaStream_t stream) {
+    int rc = buf.reserve(host.size() ? host.size() : 1);
+    if (rc != RT3_OK) { return rc; }
+    if (!host.empty()) { RT3_CUDA(cudaMemcpyAsync(buf.ptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, stream)); }
+    return RT3_OK;
+}
+
+size_t render_smem_bytes(const rt3_scene_view& v, bool* resident) {
+    *resident = v.n_prims_padded <= RT3_RESIDENT_PRIMS;
+    size_t tiles = *resident ? (size_t) v.n_prims_padded * 16 : (size_t) 2 * RT3_TILE_PRIMS * 16;
+    return 64 + (tiles ? tiles : 16);
+}
+
+template <class K> int configure(K kernel, size_t smem, int* blocks_per_sm) {
+    RT3_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    if (blocks_per_sm) { RT3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, RT3_CTA_THREADS, smem)); }
+    return RT3_OK;
+}
+
+template <int R>
+int launch_reference(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp, size_t smem, uint32_t* frame, uint32_t* prim,
+                     uint32_t* ent, float* t, cudaStream_t stream) {
+    int rc = configure(reference_kernel<R>, smem, nullptr);
+    if (rc != RT3_OK) { return rc; }
+    unsigned long long per_cta = (unsigned long long) RT3_CTA_THREADS * R;
+    unsigned grid = (unsigned) ((kp.n_pixels + per_cta - 1) / per_cta);
+    reference_kernel<R><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, cam, kp, frame, prim, ent, t, ctx->counters.ptr);
+    RT3_CUDA(cudaGetLastError());
+    return RT3_OK;
+}
+
+template <int R>
+int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp, size_t smem, cudaStream_t stream) {
+    int per_sm = 0;
+    int rc = configure(pathtrace_kernel<R>, smem, &per_sm);
+    if (rc != RT3_OK) { return rc; }
+    if (per_sm < 1) { return fail(RT3_ERR_CUDA, "pathtrace kernel does not fit on an SM (smem %zu)", smem); }
+    /* persistent grid: every SM full, no more CTAs than there are warps' worth of paths */
+    unsigned long long want = (kp.n_items + (unsigned long long) RT3_CTA_THREADS * R - 1) / ((unsigned long long) RT3_CTA_THREADS * R);
+    unsigned grid = (unsigned) ctx->sm_count * (unsigned) per_sm;
+    if (want < grid) { grid = want ? (unsigned) want : 1u; }
+    pathtrace_kernel<R><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, cam, kp, ctx->accum.ptr, ctx->counters.ptr);
+    RT3_CUDA(cudaGetLastError());
+    return RT3_OK;
+}
+
+/* Enqueues one render of this partition into device_frame (full-frame indexing). */
+int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params, const rt3_kparams& kp_in, uint32_t* device_frame,
+                   uint32_t* prim, uint32_t* ent, float* t, cudaStream_t stream) {
+    rt3_kparams kp = kp_in;
+    bool resident = false;
+    size_t smem = render_smem_bytes(ctx->view, &resident);
+    kp.resident = resident ? 1u : 0u;
+    ctx->stats.kernel_launches = 0;
+    ctx->stats.rows_rendered = kp.owned_rows;
+    ctx->last_stream = stream;
+    ctx->stats_pending = true;
+    ctx->copy_timed = false;
+    RT3_CUDA(cudaEventRecord(ctx->ev_begin, stream));
+    RT3_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 2 * sizeof(unsigned long long), stream));
+    int rc = RT3_OK;
+    if (kp.n_pixels == 0) {
+        RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
+        RT3_CUDA(cudaEventRecord(ctx->ev_k1, stream));
+        RT3_CUDA(cudaEventRecord(ctx->ev_end, stream));
+        return RT3_OK;
+    }
+    if (params->mode == RT3_MODE_REFERENCE) {
+        RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
+        switch (ctx->rays_per_thread) {
+            case 1: rc = launch_reference<1>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream); break;
+            case 4: rc = launch_reference<4>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream); break;
+            default: rc = launch_reference<2>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream); break;
+        }
+        if (rc != RT3_OK) { return rc; }
+        RT3_CUDA(cudaEventRecord(ctx->ev_k1, stream));
+        RT3_CUDA(cudaEventRecord(ctx->ev_end, stream));
+        ctx->stats.kernel_launches = 1;
+        return rc;
+    }
+    size_t n_acc = (size_t) kp.width * kp.height * 3;
+    rc = ctx->accum.reserve(n_acc);
+    if (rc != RT3_OK) { return rc; }
+    unsigned clear_grid = (unsigned) ((kp.n_pixels * 3ull + 255ull) / 256ull);
+    clear_accum_kernel<<<clear_grid, 256, 0, stream>>>(kp, ctx->accum.ptr);
+    RT3_CUDA(cudaGetLastError());
+    RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
+    switch (ctx->rays_per_thread) {
+        case 1: rc = launch_pathtrace<1>(ctx, *cam, kp, smem, stream); break;
+        case 4: rc = launch_pathtrace<4>(ctx, *cam, kp, smem, stream); break;
+        default: rc = launch_pathtrace<2>(ctx, *cam, kp, smem, stream); break;
+    }
+    if (rc != RT3_OK) { return rc; }
+    RT3_CUDA(cudaEventRecord(ctx->ev_k1, stream));
+    unsigned resolve_grid = (unsigned) ((kp.n_pixels + 255ull) / 256ull);
+    resolve_kernel<<<resolve_grid, 256, 0, stream>>>(kp, ctx->accum.ptr, device_frame);
+    RT3_CUDA(cudaGetLastError());
+    RT3_CUDA(cudaEventRecord(ctx->ev_end, stream));
+    ctx->stats.kernel_launches = 3;
+    return RT3_OK;
+}
+
+int check_render_args(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params, rt3_kparams* kp) {
+    if (!ctx) { return fail(RT3_ERR_INVALID, "ctx is NULL"); }
+    if (!cam) { return fail(RT3_ERR_INVALID, "camera is NULL"); }
+    if (!ctx->has_scene) { return fail(RT3_ERR_NO_SCENE, "rt3_scene_upload has not been called on this context"); }
+    int rc = make_kparams(params, kp);
+    if (rc != RT3_OK) { return rc; }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    return RT3_OK;
+}
+
+/* Copies the rows this partition owns from the device frame to the host frame. */
+template <class T>
+int copy_owned_rows(const rt3_kparams& kp, const T* dev, T* host, cudaStream_t stream) {
+    if (kp.part_count <= 1) {
+        RT3_CUDA(cudaMemcpyAsync(host, dev, (size_t) kp.width * kp.height * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        return RT3_OK;
+    }
+    uint32_t n_tiles = (kp.height + kp.tile_rows - 1) / kp.tile_rows;
+    for (uint32_t t = kp.part_index; t < n_tiles; t += kp.part_count) {
+        uint32_t first = t * kp.tile_rows;
+        uint32_t rows = (kp.height - first < kp.tile_rows) ? kp.height - first : kp.tile_rows;
+        size_t off = (size_t) first * kp.width;
+        RT3_CUDA(cudaMemcpyAsync(host + off, dev + off, (size_t) rows * kp.width * sizeof(T), cudaMemcpyDeviceToHost, stream));
+    }
+    return RT3_OK;
+}
+
+int render_to_host(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params, uint32_t* host_frame, uint32_t* host_prim,
+                   uint32_t* host_ent, float* host_t, bool want_aov) {
+    rt3_kparams kp;
+    int rc = check_render_args(ctx, cam, params, &kp);
+    if (rc != RT3_OK) { return rc; }
+    if (!host_frame) { return fail(RT3_ERR_INVALID, "host_frame is NULL"); }
+    if (want_aov && params->mode != RT3_MODE_REFERENCE) { return fail(RT3_ERR_INVALID, "AOVs are only produced in RT3_MODE_REFERENCE"); }
+    size_t n = (size_t) kp.width * kp.height;
+    if ((rc = ctx->frame.reserve(n)) != RT3_OK) { return rc; }
+    uint32_t *d_prim = nullptr, *d_ent = nullptr;
+    float* d_t = nullptr;
+    if (want_aov) {
+        if (host_prim) { if ((rc = ctx->aov_prim.reserve(n)) != RT3_OK) { return rc; } d_prim = ctx->aov_prim.ptr; }
+        if (host_ent) { if ((rc = ctx->aov_entity.reserve(n)) != RT3_OK) { return rc; } d_ent = ctx->aov_entity.ptr; }
+        if (host_t) { if ((rc = ctx->aov_t.reserve(n)) != RT3_OK) { return rc; } d_t = ctx->aov_t.ptr; }
+    }
+    rc = enqueue_render(ctx, cam, params, kp, ctx->frame.ptr, d_prim, d_ent, d_t, ctx->stream);
+    if (rc != RT3_OK) { return rc; }
+    if ((rc = copy_owned_rows(kp, ctx->frame.ptr, host_frame, ctx->stream)) != RT3_OK) { return rc; }
+    if (d_prim && (rc = copy_owned_rows(kp, d_prim, host_prim, ctx->stream)) != RT3_OK) { return rc; }
+    if (d_ent && (rc = copy_owned_rows(kp, d_ent, host_ent, ctx->stream)) != RT3_OK) { return rc; }
+    if (d_t && (rc = copy_owned_rows(kp, d_t, host_t, ctx->stream)) != RT3_OK) { return rc; }
+    RT3_CUDA(cudaEventRecord(ctx->ev_copy, ctx->stream));
+    ctx->copy_timed = true;
+    RT3_CUDA(cudaStreamSynchronize(ctx->stream)); /* blocking, like the reference's render() (VulkanRenderer.cpp:497) */
+    return RT3_OK;
+}
+
+/* Reads back the timings and counters of the most recent render (synchronises its stream). */
+int collect_stats(rt3_ctx* ctx) {
+    if (!ctx->stats_pending) { return RT3_OK; }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    RT3_CUDA(cudaStreamSynchronize(ctx->last_stream));
+    unsigned long long counters[2] = { 0, 0 };
+    RT3_CUDA(cudaMemcpy(counters, ctx->counters.ptr, sizeof counters, cudaMemcpyDeviceToHost));
+    float ms = 0.0f, ms_k = 0.0f, ms_copy = 0.0f;
+    RT3_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+    RT3_CUDA(cudaEventElapsedTime(&ms_k, ctx->ev_k0, ctx->ev_k1));
+    if (ctx->copy_timed) { RT3_CUDA(cudaEventElapsedTime(&ms_copy, ctx->ev_end, ctx->ev_copy)); }
+    ctx->stats.device_ms = ms;
+    ctx->stats.trace_kernel_ms = ms_k;
+    ctx->stats.h2d_ms = 0.0;
+    ctx->stats.d2h_ms = ms_copy;
+    ctx->stats.rays = counters[1];
+    ctx->stats.sphere_tests = counters[1] * ctx->view.n_spheres;
+    ctx->stats.face_tests = counters[1] * ctx->view.n_faces;
+    ctx->stats_pending = false;
+    return RT3_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rt3_last_error(void) { return g_error.c_str(); }
+
+int rt3_create(rt3_ctx** out, int device) {
+    if (!out) { return fail(RT3_ERR_INVALID, "out is NULL"); }
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        return fail(RT3_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= n_dev) { return fail(RT3_ERR_INVALID, "device %d out of range (0..%d)", device, n_dev - 1); }
+    RT3_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RT3_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { return fail(RT3_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); }
+    rt3_ctx* ctx = new rt3_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (const char* env = getenv("RT3_RAYS_PER_THREAD")) {
+        int r = atoi(env);
+        if (r == 1 || r == 2 || r == 4) { ctx->rays_per_thread = r; }
+    }
+    cudaError_t err = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_begin); }
+    if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_end); }
+    if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_copy); }
+    if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_k0); }
+    if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_k1); }
+    if (err == cudaSuccess && ctx->counters.reserve(2) != RT3_OK) { err = cudaErrorMemoryAllocation; }
+    if (err != cudaSuccess) {
+        rt3_destroy(ctx);
+        return fail(RT3_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(err));
+    }
+    *out = ctx;
+    return RT3_OK;
+}
+
+int rt3_destroy(rt3_ctx* ctx) {
+    if (!ctx) { return RT3_OK; }
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
+    ctx->bounds.release(); ctx->face_n.release(); ctx->face_p1.release(); ctx->face_p2.release(); ctx->face_p3.release();
+    ctx->spheres.release(); ctx->prim_color.release(); ctx->materials.release(); ctx->prim_material.release(); ctx->prim_entity.release();
+    ctx->frame.release(); ctx->aov_prim.release(); ctx->aov_entity.release(); ctx->aov_t.release(); ctx->accum.release(); ctx->counters.release();
+    if (ctx->ev_begin) { cudaEventDestroy(ctx->ev_begin); }
+    if (ctx->ev_end) { cudaEventDestroy(ctx->ev_end); }
+    if (ctx->ev_copy) { cudaEventDestroy(ctx->ev_copy); }
+    if (ctx->ev_k0) { cudaEventDestroy(ctx->ev_k0); }
+    if (ctx->ev_k1) { cudaEventDestroy(ctx->ev_k1); }
+    if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
+    delete ctx;
+    return RT3_OK;
+}
+
+int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
+    if (!ctx || !s) { return fail(RT3_ERR_INVALID, "ctx or scene is NULL"); }
+    if (s->n_faces && (!s->faces || !s->vertices)) { return fail(RT3_ERR_INVALID, "faces/vertices missing"); }
+    if (s->n_spheres && !s->spheres) { return fail(RT3_ERR_INVALID, "spheres missing"); }
+    if ((s->face_material || s->sphere_material) && s->n_materials && !s->materials) { return fail(RT3_ERR_INVALID, "materials missing"); }
+    if ((unsigned long long) s->n_faces + s->n_spheres > 0x7FFFFFFFull) { return fail(RT3_ERR_INVALID, "too many primitives"); }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    ctx->has_scene = false;
+
+    const uint32_t nf = s->n_faces, ns = s->n_spheres, np = nf + ns;
+    const uint32_t np_pad = (np + RT3_BLOCK_PRIMS - 1) / RT3_BLOCK_PRIMS * RT3_BLOCK_PRIMS;
+    const float inf = std::numeric_limits<float>::infinity();
+    std::vector<float4> bounds(np_pad, make_float4(0.f, 0.f, 0.f, inf));
+    std::vector<float4> fn(nf), p1(nf), p2(nf), p3(nf), sph(ns), color(np), mats((size_t) s->n_materials * 2);
+    std::vector<uint32_t> pmat(np, RT3_NO_HIT), pent(np, 0u);
+
+    for (uint32_t i = 0; i < nf; i++) {
+        const rt3_face& f = s->faces[i];
+        if (f.v1 >= s->n_vertices || f.v2 >= s->n_vertices || f.v3 >= s->n_vertices) {
+            return fail(RT3_ERR_INVALID, "face %u references vertex out of range (%u,%u,%u of %u)", i, f.v1, f.v2, f.v3, s->n_vertices);
+        }
+        const rt3_vertex &a = s->vertices[f.v1], &b = s->vertices[f.v2], &c = s->vertices[f.v3];
+        /* plane offset dot3(n, p1) in the reference's order (SequentialRenderer.cpp:32-33,67); volatile keeps
+         * the host compiler from contracting it */
+        volatile float m0 = f.normal[0] * a.x, m1 = f.normal[1] * a.y, m2 = f.normal[2] * a.z;
+        volatile float s01 = m0 + m1;
+        float pd = s01 + m2;
+        fn[i] = make_float4(f.normal[0], f.normal[1], f.normal[2], pd);
+        p1[i] = make_float4(a.x, a.y, a.z, 0.f);
+        p2[i] = make_float4(b.x, b.y, b.z, 0.f);
+        p3[i] = make_float4(c.x, c.y, c.z, 0.f);
+        double da[3] = { a.x, a.y, a.z }, db[3] = { b.x, b.y, b.z }, dc[3] = { c.x, c.y, c.z }, centre[3], radius;
+        triangle_bound(da, db, dc, centre, &radius);
+        bounds[i] = make_bound(centre, radius);
+        color[i] = make_float4(f.color[0], f.color[1], f.color[2], 0.f);
+        if (s->face_material) {
+            if (s->face_material[i] >= s->n_materials) { return fail(RT3_ERR_INVALID, "face %u: material %u out of range", i, s->face_material[i]); }
+            pmat[i] = s->face_material[i];
+        }
+        if (s->face_entity) { pent[i] = s->face_entity[i]; }
+    }
+    for (uint32_t i = 0; i < ns; i++) {
+        const rt3_sphere& sp = s->spheres[i];
+        sph[i] = make_float4(sp.cx, sp.cy, sp.cz, sp.r);
+        double c[3] = { sp.cx, sp.cy, sp.cz };
+        bounds[nf + i] = make_bound(c, std::fabs((double) sp.r));
+        if (s->sphere_color) { color[nf + i] = make_float4(s->sphere_color[3 * i], s->sphere_color[3 * i + 1], s->sphere_color[3 * i + 2], 0.f); }
+        else { color[nf + i] = make_float4(1.f, 1.f, 1.f, 0.f); }
+        if (s->sphere_material) {
+            if (s->sphere_material[i] >= s->n_materials) { return fail(RT3_ERR_INVALID, "sphere %u: material %u out of range", i, s->sphere_material[i]); }
+            pmat[nf + i] = s->sphere_material[i];
+        }
+        if (s->sphere_entity) { pent[nf + i] = s->sphere_entity[i]; }
+    }
+    for (uint32_t i = 0; i < s->n_materials; i++) {
+        const rt3_material& m = s->materials[i];
+        if (m.kind > RT3_MAT_DIELECTRIC) { return fail(RT3_ERR_INVALID, "material %u: unknown kind %u", i, m.kind); }
+        float kind_bits;
+        memcpy(&kind_bits, &m.kind, sizeof kind_bits);
+        mats[2 * i] = make_float4(kind_bits, m.albedo[0], m.albedo[1], m.albedo[2]);
+        mats[2 * i + 1] = make_float4(m.fuzz, m.ior, 0.f, 0.f);
+    }
+
+    int rc;
+    if ((rc = upload(ctx->bounds, bounds, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->face_n, fn, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->face_p1, p1, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->face_p2, p2, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->face_p3, p3, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->spheres, sph, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->prim_color, color, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->materials, mats, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->prim_material, pmat, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->prim_entity, pent, ctx->stream)) != RT3_OK) { return rc; }
+    RT3_CUDA(cudaStreamSynchronize(ctx->stream)); /* host vectors go out of scope */
+
+    rt3_scene_view& v = ctx->view;
+    v.n_faces = nf; v.n_spheres = ns; v.n_prims = np; v.n_prims_padded = np_pad;
+    v.bounds = ctx->bounds.ptr;
+    v.face_n = ctx->face_n.ptr; v.face_p1 = ctx->face_p1.ptr; v.face_p2 = ctx->face_p2.ptr; v.face_p3 = ctx->face_p3.ptr;
+    v.spheres = ctx->spheres.ptr; v.prim_color = ctx->prim_color.ptr;
+    v.prim_material = ctx->prim_material.ptr; v.prim_entity = ctx->prim_entity.ptr; v.materials = ctx->materials.ptr;
+    ctx->has_scene = true;
+    return RT3_OK;
+}
+
+int rt3_render(rt3_ctx* ctx, const rt3_camera* camera, const rt3_params* params, uint32_t* host_frame) {
+    return render_to_host(ctx, camera, params, host_frame, nullptr, nullptr, nullptr, false);
+}
+
+int rt3_render_aov(rt3_ctx* ctx, const rt3_camera* camera, const rt3_params* params, uint32_t* host_frame, uint32_t* host_hit_prim,
+                   uint32_t* host_hit_entity, float* host_hit_t) {
+    return render_to_host(ctx, camera, params, host_frame, host_hit_prim, host_hit_entity, host_hit_t, true);
+}
+
+int rt3_render_device(rt3_ctx* ctx, const rt3_camera* camera, const rt3_params* params, uint32_t* device_frame, void* cuda_stream) {
+    rt3_kparams kp;
+    int rc = check_render_args(ctx, camera, params, &kp);
+    if (rc != RT3_OK) { return rc; }
+    if (!device_frame) { return fail(RT3_ERR_INVALID, "device_frame is NULL"); }
+    cudaStream_t stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
+    return enqueue_render(ctx, camera, params, kp, device_frame, nullptr, nullptr, nullptr, stream);
+}
+
+uint32_t rt3_partition_rows(uint32_t height, uint32_t tile_rows, uint32_t part_index, uint32_t part_count) {
+    return owned_rows(height, tile_rows, part_index, part_count);
+}
+
+static int partition_kparams(uint32_t width, uint32_t height, uint32_t tile_rows, uint32_t part_index, uint32_t part_count, rt3_kparams* kp) {
+    rt3_params p;
+    memset(&p, 0, sizeof p);
+    p.width = width; p.height = height; p.mode = RT3_MODE_REFERENCE; p.tile_rows = tile_rows; p.part_index = part_index; p.part_count = part_count;
+    return make_kparams(&p, kp);
+}
+
+int rt3_pack_partition(rt3_ctx* ctx, const uint32_t* device_frame, uint32_t* device_slab, uint32_t width, uint32_t height,
+                       uint32_t tile_rows, uint32_t part_index, uint32_t part_count, void* cuda_stream) {
+    if (!ctx || !device_frame || !device_slab) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    rt3_kparams kp;
+    int rc = partition_kparams(width, height, tile_rows, part_index, part_count, &kp);
+    if (rc != RT3_OK) { return rc; }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    if (kp.n_pixels == 0) { return RT3_OK; }
+    cudaStream_t stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
+    pack_partition_kernel<<<(unsigned) ((kp.n_pixels + 255ull) / 256ull), 256, 0, stream>>>(kp, device_frame, device_slab);
+    RT3_CUDA(cudaGetLastError());
+    return RT3_OK;
+}
+
+int rt3_unpack_partition(rt3_ctx* ctx, const uint32_t* device_slab, uint32_t* device_frame, uint32_t width, uint32_t height,
+                         uint32_t tile_rows, uint32_t part_index, uint32_t part_count, void* cuda_stream) {
+    if (!ctx || !device_frame || !device_slab) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    rt3_kparams kp;
+    int rc = partition_kparams(width, height, tile_rows, part_index, part_count, &kp);
+    if (rc != RT3_OK) { return rc; }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    if (kp.n_pixels == 0) { return RT3_OK; }
+    cudaStream_t stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
+    unpack_partition_kernel<<<(unsigned) ((kp.n_pixels + 255ull) / 256ull), 256, 0, stream>>>(kp, device_slab, device_frame);
+    RT3_CUDA(cudaGetLastError());
+    return RT3_OK;
+}
+
+int rt3_get_stats(rt3_ctx* ctx, rt3_stats* out) {
+    if (!ctx || !out) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    int rc = collect_stats(ctx);
+    if (rc != RT3_OK) { return rc; }
+    *out = ctx->stats;
+    return RT3_OK;
+}
+
+int rt3_measure_fma_peak(rt3_ctx* ctx, double* tflops_out) {
+    if (!ctx || !tflops_out) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    int rc0 = collect_stats(ctx);
+    if (rc0 != RT3_OK) { return rc0; }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    const int threads = 256, blocks = ctx->sm_count * 8, iters = 1 << 15;
+    DeviceBuffer<float> out;
+    int rc = out.reserve((size_t) threads * blocks);
+    if (rc != RT3_OK) { return rc; }
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        RT3_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
+        fma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out.ptr, 0.999f, 0.001f, iters);
+        RT3_CUDA(cudaGetLastError());
+        RT3_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
+        RT3_CUDA(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        RT3_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+        double flops = 2.0 * 16.0 * (double) iters * threads * blocks;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) { best = tf; }
+    }
+    out.release();
+    *tflops_out = best;
+    return RT3_OK;
+}
+
+}  // extern "C"

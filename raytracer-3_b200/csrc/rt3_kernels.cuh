@@ -1,0 +1,463 @@
+/* rt3_kernels.cuh — the sm_100a kernels of the render core.
+ *
+ *   reference_kernel   : the reference's ray caster (one un-jittered primary
+ *                        ray per pixel, closest hit, flat colour / sky, AOVs).
+ *   pathtrace_kernel   : persistent multi-bounce path tracer with in-warp path
+ *                        regeneration and fixed-point accumulation.
+ *   resolve_kernel     : mean over samples, gamma, 8-bit pack.
+ *   pack/unpack kernels: frame <-> partition slab for the frame-end gather.
+ *   fma_peak_kernel    : FFMA throughput probe (roofline denominator).
+ *
+ * Both render kernels run the same sweep: per primitive one broadcast LDS.128
+ * of its prefilter sphere from shared memory and nine FP32-pipe instructions
+ * per ray (rt3_device.cuh), exact tests only on the survivors.
+ */
+#pragma once
+
+#include "rt3_device.cuh"
+
+struct rt3_kparams {
+    uint32_t width, height;
+    uint32_t spp, max_depth, seed, flags;
+    uint32_t tile_rows, part_index, part_count;
+    uint32_t owned_rows;          /* rows this partition renders */
+    unsigned long long n_pixels;  /* owned_rows * width */
+    unsigned long long n_items;   /* n_pixels * spp */
+    uint32_t resident;            /* 1: the whole prefilter array is kept in shared memory */
+};
+
+/* Compact owned-row index -> global row (row tiles dealt round-robin to partitions). */
+__device__ __forceinline__ uint32_t owned_row_to_global(const rt3_kparams& P, uint32_t local_row) {
+    uint32_t lt = local_row / P.tile_rows, within = local_row - lt * P.tile_rows;
+    return (lt * P.part_count + P.part_index) * P.tile_rows + within;
+}
+
+/* Shared-memory layout: [mbarriers (64 B)] [prefilter tiles]. */
+struct rt3_smem_view {
+    uint64_t* bars;  /* RT3 streaming: one "tile landed" mbarrier per stage */
+    float4* tiles;   /* resident: n_prims_padded entries; streamed: 2 stages of RT3_TILE_PRIMS */
+};
+
+__device__ __forceinline__ rt3_smem_view smem_view(unsigned char* base) {
+    rt3_smem_view v;
+    v.bars = reinterpret_cast<uint64_t*>(base);
+    v.tiles = reinterpret_cast<float4*>(base + 64);
+    return v;
+}
+
+/* Brings the prefilter array into shared memory once (resident scenes) with one
+ * bulk asynchronous copy per 32 KB, or arms the streaming barriers. */
+__device__ __forceinline__ void scene_prologue(const rt3_scene_view& S, const rt3_smem_view& sm, bool resident) {
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.bars[0], 1);
+        mbar_init(&sm.bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (resident) {
+        if (threadIdx.x == 0 && S.n_prims_padded > 0) {
+            uint32_t bytes = S.n_prims_padded * 16u;
+            mbar_expect_tx(&sm.bars[0], bytes);
+            for (uint32_t off = 0; off < bytes; off += 32768u) {
+                uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+                bulk_copy_g2s(reinterpret_cast<unsigned char*>(sm.tiles) + off, reinterpret_cast<const unsigned char*>(S.bounds) + off, n,
+                              &sm.bars[0]);
+            }
+        }
+        if (S.n_prims_padded > 0) { mbar_wait(&sm.bars[0], 0); }
+    }
+}
+
+/* Closest hit of R rays against the whole scene. For streamed scenes every
+ * thread of the CTA must call this together (tile barriers); `phase` carries
+ * the mbarrier parities across calls. */
+template <int R, bool PATH_MODE>
+__device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_smem_view& sm, bool resident, uint32_t& phase,
+                                            const rt3_vec3 (&o)[R], const rt3_vec3 (&d)[R], const rt3_vec3 (&dn)[R],
+                                            const bool (&live)[R], rt3_hit (&best)[R]) {
+    rt3_ray_filter f[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        f[r] = make_ray_filter(o[r], dn[r]);
+        best[r].t = __int_as_float(0x7f800000);
+        best[r].prim = RT3_NO_HIT;
+    }
+    if (resident) {
+        for (uint32_t base = 0; base < S.n_prims_padded; base += RT3_BLOCK_PRIMS) {
+            sweep_block<R, PATH_MODE>(S, sm.tiles + base, base, f, o, d, live, best);
+        }
+        return;
+    }
+    const uint32_t n_tiles = (S.n_prims_padded + RT3_TILE_PRIMS - 1) / RT3_TILE_PRIMS;
+    if (threadIdx.x == 0) {
+        uint32_t n0 = S.n_prims_padded < RT3_TILE_PRIMS ? S.n_prims_padded : RT3_TILE_PRIMS;
+        mbar_expect_tx(&sm.bars[0], n0 * 16u);
+        bulk_copy_g2s(sm.tiles, S.bounds, n0 * 16u, &sm.bars[0]);
+    }
+    for (uint32_t t = 0; t < n_tiles; t++) {
+        const uint32_t stage = t & 1u;
+        if (threadIdx.x == 0 && t + 1 < n_tiles) {
+            /* stage^1 was last read for tile t-1; the __syncthreads below ordered those reads before this copy */
+            uint32_t first = (t + 1) * RT3_TILE_PRIMS;
+            uint32_t n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
+            mbar_expect_tx(&sm.bars[stage ^ 1u], n * 16u);
+            bulk_copy_g2s(sm.tiles + (stage ^ 1u) * RT3_TILE_PRIMS, S.bounds + first, n * 16u, &sm.bars[stage ^ 1u]);
+        }
+        mbar_wait(&sm.bars[stage], (phase >> stage) & 1u);
+        phase ^= 1u << stage;
+        const uint32_t first = t * RT3_TILE_PRIMS;
+        const uint32_t n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
+        const float4* tile = sm.tiles + stage * RT3_TILE_PRIMS;
+        for (uint32_t base = 0; base < n; base += RT3_BLOCK_PRIMS) {
+            sweep_block<R, PATH_MODE>(S, tile + base, first + base, f, o, d, live, best);
+        }
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------ *
+ * Reference mode: SequentialRenderer.cpp:269-308 (+ AOVs)
+ * ------------------------------------------------------------------------ */
+template <int R>
+__global__ void __launch_bounds__(RT3_CTA_THREADS, 2)
+reference_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, uint32_t* __restrict__ frame, uint32_t* __restrict__ hit_prim,
+                 uint32_t* __restrict__ hit_entity, float* __restrict__ hit_t, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const rt3_smem_view sm = smem_view(smem_raw);
+    const bool resident = P.resident != 0;
+    scene_prologue(S, sm, resident);
+    uint32_t phase = resident ? 1u : 0u;
+
+    const rt3_vec3 origin = v3(cam.origin[0], cam.origin[1], cam.origin[2]);
+    const rt3_vec3 hor = v3(cam.horizontal[0], cam.horizontal[1], cam.horizontal[2]);
+    const rt3_vec3 ver = v3(cam.vertical[0], cam.vertical[1], cam.vertical[2]);
+    const rt3_vec3 llc = v3(cam.lower_left_corner[0], cam.lower_left_corner[1], cam.lower_left_corner[2]);
+
+    rt3_vec3 o[R], d[R], dn[R];
+    bool live[R];
+    rt3_hit best[R];
+    size_t pix[R];
+    const unsigned long long cta_first = (unsigned long long) blockIdx.x * (RT3_CTA_THREADS * R);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        unsigned long long p = cta_first + (unsigned long long) r * RT3_CTA_THREADS + threadIdx.x;
+        live[r] = p < P.n_pixels;
+        if (!live[r]) { p = 0; }
+        uint32_t local_row = (uint32_t) (p / P.width), x = (uint32_t) (p - (unsigned long long) local_row * P.width);
+        uint32_t y = owned_row_to_global(P, local_row);
+        pix[r] = (size_t) y * P.width + x;
+        /* SequentialRenderer.cpp:289-293: the divides are written in double there */
+        float u = (float) ((double) (float) x / ((double) (float) P.width - 1.0));
+        float v = (float) ((double) (float) (P.height - 1 - y) / ((double) (float) P.height - 1.0));
+        o[r] = origin;
+        d[r] = ((llc + u * hor) + v * ver) - origin;
+        dn[r] = normalize3(d[r]);
+    }
+    sweep_scene<R, false>(S, sm, resident, phase, o, d, dn, live, best);
+    unsigned long long rays = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        if (!live[r]) { continue; }
+        rays++;
+        rt3_vec3 col;
+        uint32_t ent = RT3_NO_HIT;
+        if (best[r].prim == RT3_NO_HIT) {
+            /* sky, SequentialRenderer.cpp:105-107 */
+            float len = sqrtf(dot3(d[r], d[r]));
+            float uy = d[r].y / len;
+            float t = (float) (0.5 * ((double) uy + 1.0));
+            float a = 1.0f - t;
+            col = v3(a * 1.0f + t * 0.5f, a * 1.0f + t * 0.7f, a * 1.0f + t * 1.0f);
+        } else {
+            float4 c = __ldg(&S.prim_color[best[r].prim]);
+            col = v3(c.x, c.y, c.z);
+            ent = __ldg(&S.prim_entity[best[r].prim]);
+        }
+        frame[pix[r]] = pack_rgb(col);
+        if (hit_prim) { hit_prim[pix[r]] = best[r].prim; }
+        if (hit_entity) { hit_entity[pix[r]] = ent; }
+        if (hit_t) { hit_t[pix[r]] = best[r].t; }
+    }
+    /* ray count: one atomic per warp */
+    for (int off = 16; off > 0; off >>= 1) { rays += __shfl_down_sync(0xffffffffu, rays, off); }
+    if ((threadIdx.x & 31) == 0 && rays) { atomicAdd(&counters[1], rays); }
+}
+
+/* ------------------------------------------------------------------------ *
+ * Path tracer
+ * ------------------------------------------------------------------------ */
+
+/* Uniform point on the unit sphere: z = 1 - 2 xi1, phi = 2 pi xi2. */
+__device__ __forceinline__ rt3_vec3 unit_vector(float xi1, float xi2) {
+    float z = 1.0f - 2.0f * xi1;
+    float rr = 1.0f - z * z;
+    rr = sqrtf(rr < 0.0f ? 0.0f : rr);
+    float sn, cs;
+    rt3_sincos_2pi(xi2, &sn, &cs);
+    return v3(rr * cs, rr * sn, z);
+}
+
+__device__ __forceinline__ unsigned long long to_fixed(float c) {
+    if (!(c > 0.0f)) { return 0ull; }
+    if (c > 1048576.0f) { c = 1048576.0f; }
+    return (unsigned long long) (c * RT3_ACC_SCALE + 0.5f);
+}
+
+/* Warp-cooperative claim of one path item per requesting lane. `cur`/`end`
+ * are the warp's current chunk (uniform); chunks come from one global counter. */
+__device__ __forceinline__ bool claim_item(bool want, unsigned long long& cur, unsigned long long& end, bool& dry,
+                                           unsigned long long n_items, unsigned long long* next_item, unsigned long long& item) {
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned m = __ballot_sync(0xffffffffu, want);
+    int n = __popc(m);
+    int rank = __popc(m & ((1u << lane) - 1u));
+    bool got = false;
+    while (n > 0 && !dry) {
+        if (cur == end) {
+            unsigned long long c = 0;
+            if (lane == 0) { c = atomicAdd(next_item, (unsigned long long) RT3_ITEM_CHUNK); }
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= n_items) { dry = true; break; }
+            cur = c;
+            end = c + RT3_ITEM_CHUNK < n_items ? c + RT3_ITEM_CHUNK : n_items;
+        }
+        unsigned long long avail = end - cur;
+        int take = (unsigned long long) n < avail ? n : (int) avail;
+        if (want && !got && rank >= 0 && rank < take) { item = cur + (unsigned long long) rank; got = true; }
+        rank -= take;
+        cur += (unsigned long long) take;
+        n -= take;
+    }
+    return got;
+}
+
+template <int R>
+__global__ void __launch_bounds__(RT3_CTA_THREADS, 2)
+pathtrace_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, unsigned long long* __restrict__ accum,
+                 unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const rt3_smem_view sm = smem_view(smem_raw);
+    const bool resident = P.resident != 0;
+    scene_prologue(S, sm, resident);
+    uint32_t phase = resident ? 1u : 0u;
+
+    const rt3_vec3 cam_o = v3(cam.origin[0], cam.origin[1], cam.origin[2]);
+    const rt3_vec3 hor = v3(cam.horizontal[0], cam.horizontal[1], cam.horizontal[2]);
+    const rt3_vec3 ver = v3(cam.vertical[0], cam.vertical[1], cam.vertical[2]);
+    const rt3_vec3 llc = v3(cam.lower_left_corner[0], cam.lower_left_corner[1], cam.lower_left_corner[2]);
+    const float inv_w = (float) P.width - 1.0f, inv_h = (float) P.height - 1.0f;
+
+    rt3_vec3 o[R], d[R], thr[R];
+    uint32_t key[R], bounce[R];
+    size_t pix[R];
+    bool live[R];
+    rt3_hit best[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { live[r] = false; bounce[r] = 0; key[r] = 0; pix[r] = 0; o[r] = d[r] = thr[r] = v3(0.f, 0.f, 0.f); }
+    unsigned long long cur = 0, end = 0, rays = 0;
+    bool dry = false;
+
+    for (;;) {
+        /* (1) regenerate: every free slot starts the next (pixel, sample) item */
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            unsigned long long item = 0;
+            if (claim_item(!live[r], cur, end, dry, P.n_items, &counters[0], item)) {
+                unsigned long long p = item / P.spp;
+                uint32_t sample = (uint32_t) (item - p * P.spp);
+                uint32_t local_row = (uint32_t) (p / P.width), x = (uint32_t) (p - (unsigned long long) local_row * P.width);
+                uint32_t y = owned_row_to_global(P, local_row);
+                uint32_t pixel_index = y * P.width + x;
+                pix[r] = (size_t) pixel_index;
+                uint32_t k = rt3_path_key(pixel_index, sample, P.seed);
+                key[r] = k;
+                float jx = 0.0f, jy = 0.0f;
+                if (!(P.flags & RT3_FLAG_NO_JITTER)) { jx = rt3_draw(k, RT3_DIM_JITTER_X); jy = rt3_draw(k, RT3_DIM_JITTER_Y); }
+                float u = ((float) x + jx) / inv_w;
+                float v = ((float) (P.height - 1 - y) + jy) / inv_h;
+                rt3_vec3 org = cam_o;
+                rt3_vec3 dir = ((llc + u * hor) + v * ver) - org;
+                if (cam.lens_radius > 0.0f) {
+                    float rad = sqrtf(rt3_draw(k, RT3_DIM_LENS_R));
+                    float sn, cs;
+                    rt3_sincos_2pi(rt3_draw(k, RT3_DIM_LENS_PHI), &sn, &cs);
+                    float lx = cam.lens_radius * (rad * cs), ly = cam.lens_radius * (rad * sn);
+                    rt3_vec3 off = lx * v3(cam.lens_u[0], cam.lens_u[1], cam.lens_u[2]) + ly * v3(cam.lens_v[0], cam.lens_v[1], cam.lens_v[2]);
+                    org = org + off;
+                    dir = dir - off;
+                }
+                o[r] = org;
+                d[r] = normalize3(dir);
+                thr[r] = v3(1.0f, 1.0f, 1.0f);
+                bounce[r] = 0;
+                live[r] = true;
+            }
+            any = any || live[r];
+        }
+        if (resident) { if (!__any_sync(0xffffffffu, any)) { break; } }
+        else { if (!__syncthreads_or(any ? 1 : 0)) { break; } }
+
+        /* (2) closest hit of every live ray against the whole scene */
+        sweep_scene<R, true>(S, sm, resident, phase, o, d, d, live, best);
+
+        /* (3) shade: miss -> sky * throughput; hit -> scatter */
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (!live[r]) { continue; }
+            rays++;
+            bool done = false;
+            rt3_vec3 L = v3(0.0f, 0.0f, 0.0f);
+            const rt3_vec3 dr = d[r];
+            if (best[r].prim == RT3_NO_HIT) {
+                float t = 0.5f * (dr.y + 1.0f);
+                float a = 1.0f - t;
+                L = thr[r] * v3(a * 1.0f + t * 0.5f, a * 1.0f + t * 0.7f, a * 1.0f + t * 1.0f);
+                done = true;
+            } else {
+                const uint32_t prim = best[r].prim;
+                rt3_vec3 hp = o[r] + best[r].t * dr;
+                rt3_vec3 outward;
+                if (prim < S.n_faces) {
+                    float4 fn = __ldg(&S.face_n[prim]);
+                    outward = v3(fn.x, fn.y, fn.z);
+                } else {
+                    float4 sp = __ldg(&S.spheres[prim - S.n_faces]);
+                    rt3_vec3 pc = hp - v3(sp.x, sp.y, sp.z);
+                    outward = v3(pc.x / sp.w, pc.y / sp.w, pc.z / sp.w);
+                }
+                const bool front = dot3(dr, outward) < 0.0f;
+                const rt3_vec3 n = front ? outward : -outward;
+                uint32_t kind = RT3_MAT_LAMBERTIAN;
+                rt3_vec3 albedo;
+                float fuzz = 0.0f, ior = 1.0f;
+                const uint32_t mi = __ldg(&S.prim_material[prim]);
+                if (mi == RT3_NO_HIT) {
+                    float4 c = __ldg(&S.prim_color[prim]);
+                    albedo = v3(c.x, c.y, c.z);
+                } else {
+                    float4 m0 = __ldg(&S.materials[2 * mi]), m1 = __ldg(&S.materials[2 * mi + 1]);
+                    kind = __float_as_uint(m0.x);
+                    albedo = v3(m0.y, m0.z, m0.w);
+                    fuzz = m1.x; ior = m1.y;
+                }
+                const uint32_t dim = RT3_DIM_BOUNCE0 + RT3_DIMS_PER_BOUNCE * bounce[r];
+                const uint32_t k = key[r];
+                rt3_vec3 nd;
+                if (kind == RT3_MAT_LAMBERTIAN) {
+                    rt3_vec3 uv = unit_vector(rt3_draw(k, dim + 0), rt3_draw(k, dim + 1));
+                    nd = n + uv;
+                    if (fabsf(nd.x) < 1e-8f && fabsf(nd.y) < 1e-8f && fabsf(nd.z) < 1e-8f) { nd = n; }
+                    thr[r] = thr[r] * albedo;
+                } else if (kind == RT3_MAT_METAL) {
+                    float dnn = dot3(dr, n);
+                    nd = dr - (2.0f * dnn) * n;
+                    float fz = fuzz < 1.0f ? fuzz : 1.0f;
+                    if (fz > 0.0f) {
+                        rt3_vec3 uv = unit_vector(rt3_draw(k, dim + 0), rt3_draw(k, dim + 1));
+                        float a = rt3_draw(k, dim + 2), b = rt3_draw(k, dim + 3), c = rt3_draw(k, dim + 4);
+                        float mx = a < b ? b : a;
+                        mx = mx < c ? c : mx;
+                        nd = nd + (fz * mx) * uv;
+                    }
+                    if (!(dot3(nd, n) > 0.0f)) { done = true; }
+                    thr[r] = thr[r] * albedo;
+                } else {
+                    float ratio = front ? (1.0f / ior) : ior;
+                    float cs = -dot3(dr, n);
+                    cs = cs < 1.0f ? cs : 1.0f;
+                    float s2 = 1.0f - cs * cs;
+                    float sn = sqrtf(s2 < 0.0f ? 0.0f : s2);
+                    bool cannot_refract = ratio * sn > 1.0f;
+                    float r0 = (1.0f - ratio) / (1.0f + ratio);
+                    r0 = r0 * r0;
+                    float w = 1.0f - cs;
+                    float w2 = w * w;
+                    float schlick = r0 + (1.0f - r0) * ((w2 * w2) * w);
+                    if (cannot_refract || schlick > rt3_draw(k, dim + 0)) {
+                        float dnn = dot3(dr, n);
+                        nd = dr - (2.0f * dnn) * n;
+                    } else {
+                        rt3_vec3 perp = ratio * (dr + cs * n);
+                        float kk = 1.0f - dot3(perp, perp);
+                        rt3_vec3 par = (-sqrtf(fabsf(kk))) * n;
+                        nd = perp + par;
+                    }
+                }
+                if (!done) {
+                    o[r] = hp;
+                    d[r] = normalize3(nd);
+                    bounce[r]++;
+                    if (bounce[r] >= P.max_depth) { done = true; } /* depth exhausted: radiance 0 */
+                }
+            }
+            if (done) {
+                unsigned long long qx = to_fixed(L.x), qy = to_fixed(L.y), qz = to_fixed(L.z);
+                unsigned long long* acc = accum + 3 * pix[r];
+                if (qx) { atomicAdd(acc + 0, qx); }
+                if (qy) { atomicAdd(acc + 1, qy); }
+                if (qz) { atomicAdd(acc + 2, qz); }
+                live[r] = false;
+            }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) { rays += __shfl_down_sync(0xffffffffu, rays, off); }
+    if ((threadIdx.x & 31) == 0 && rays) { atomicAdd(&counters[1], rays); }
+}
+
+/* Mean over samples, gamma 2, reference packing (SequentialRenderer.cpp:297). */
+__global__ void resolve_kernel(rt3_kparams P, const unsigned long long* __restrict__ accum, uint32_t* __restrict__ frame) {
+    unsigned long long p = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_pixels) { return; }
+    uint32_t local_row = (uint32_t) (p / P.width), x = (uint32_t) (p - (unsigned long long) local_row * P.width);
+    size_t idx = (size_t) owned_row_to_global(P, local_row) * P.width + x;
+    const bool gamma = !(P.flags & RT3_FLAG_NO_GAMMA);
+    uint32_t ch[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float m = (float) ((double) accum[3 * idx + c] / ((double) P.spp * (double) RT3_ACC_SCALE));
+        if (gamma) { m = sqrtf(m); }
+        ch[c] = unorm8(m);
+    }
+    frame[idx] = (ch[0] << 24) | (ch[1] << 16) | (ch[2] << 8) | 0xFFu;
+}
+
+/* Clears the accumulators of the owned rows. */
+__global__ void clear_accum_kernel(rt3_kparams P, unsigned long long* __restrict__ accum) {
+    unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_pixels * 3ull) { return; }
+    unsigned long long p = i / 3ull;
+    uint32_t c = (uint32_t) (i - p * 3ull);
+    uint32_t local_row = (uint32_t) (p / P.width), x = (uint32_t) (p - (unsigned long long) local_row * P.width);
+    size_t idx = (size_t) owned_row_to_global(P, local_row) * P.width + x;
+    accum[3 * idx + c] = 0ull;
+}
+
+/* frame (full indexing) <-> compact slab of the owned rows. */
+__global__ void pack_partition_kernel(rt3_kparams P, const uint32_t* __restrict__ frame, uint32_t* __restrict__ slab) {
+    unsigned long long p = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_pixels) { return; }
+    uint32_t local_row = (uint32_t) (p / P.width), x = (uint32_t) (p - (unsigned long long) local_row * P.width);
+    slab[p] = frame[(size_t) owned_row_to_global(P, local_row) * P.width + x];
+}
+__global__ void unpack_partition_kernel(rt3_kparams P, const uint32_t* __restrict__ slab, uint32_t* __restrict__ frame) {
+    unsigned long long p = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_pixels) { return; }
+    uint32_t local_row = (uint32_t) (p / P.width), x = (uint32_t) (p - (unsigned long long) local_row * P.width);
+    frame[(size_t) owned_row_to_global(P, local_row) * P.width + x] = slab[p];
+}
+
+/* FFMA throughput probe: 16 independent three-register FMA chains per thread. */
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, float a, float b, int iters) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { acc[i] = (float) (threadIdx.x + i); }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) { acc[i] = __fmaf_rn(acc[i], a, b); }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) { s += acc[i]; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
