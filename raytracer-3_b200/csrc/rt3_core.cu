@@ -70,6 +70,7 @@ struct rt3_ctx {
     rt3_scene_view view{};
     DeviceBuffer<float4> bounds, face_n, face_p1, face_p2, face_p3, spheres, prim_color, materials;
     DeviceBuffer<uint32_t> prim_material, prim_entity;
+    DeviceBuffer<float> prim_radius;
 
     DeviceBuffer<uint32_t> frame, aov_prim, aov_entity;
     DeviceBuffer<float> aov_t;
@@ -174,10 +175,9 @@ template <class T> int upload(DeviceBuffer<T>& buf, const std::vector<T>& host, 
     return RT3_OK;
 }
 
-size_t render_smem_bytes(const rt3_scene_view& v, bool* resident) {
+size_t render_smem_bytes(const rt3_scene_view& v, int rays_per_thread, bool* resident) {
     *resident = v.n_prims_padded <= RT3_RESIDENT_PRIMS;
-    size_t tiles = *resident ? (size_t) v.n_prims_padded * 16 : (size_t) 2 * RT3_TILE_PRIMS * 16;
-    return 64 + (tiles ? tiles : 16);
+    return rt3_smem_bytes(v.n_prims_padded, *resident, rays_per_thread);
 }
 
 template <class K> int configure(K kernel, size_t smem, int* blocks_per_sm) {
@@ -218,7 +218,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
                    uint32_t* prim, uint32_t* ent, float* t, cudaStream_t stream) {
     rt3_kparams kp = kp_in;
     bool resident = false;
-    size_t smem = render_smem_bytes(ctx->view, &resident);
+    size_t smem = render_smem_bytes(ctx->view, ctx->rays_per_thread, &resident);
     kp.resident = resident ? 1u : 0u;
     ctx->stats.kernel_launches = 0;
     ctx->stats.rows_rendered = kp.owned_rows;
@@ -393,7 +393,7 @@ int rt3_destroy(rt3_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
     ctx->bounds.release(); ctx->face_n.release(); ctx->face_p1.release(); ctx->face_p2.release(); ctx->face_p3.release();
-    ctx->spheres.release(); ctx->prim_color.release(); ctx->materials.release(); ctx->prim_material.release(); ctx->prim_entity.release();
+    ctx->spheres.release(); ctx->prim_color.release(); ctx->materials.release(); ctx->prim_material.release(); ctx->prim_entity.release(); ctx->prim_radius.release();
     ctx->frame.release(); ctx->aov_prim.release(); ctx->aov_entity.release(); ctx->aov_t.release(); ctx->accum.release(); ctx->counters.release();
     if (ctx->ev_begin) { cudaEventDestroy(ctx->ev_begin); }
     if (ctx->ev_end) { cudaEventDestroy(ctx->ev_end); }
@@ -420,6 +420,7 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     std::vector<float4> bounds(np_pad, make_float4(0.f, 0.f, 0.f, inf));
     std::vector<float4> fn(nf), p1(nf), p2(nf), p3(nf), sph(ns), color(np), mats((size_t) s->n_materials * 2);
     std::vector<uint32_t> pmat(np, RT3_NO_HIT), pent(np, 0u);
+    std::vector<float> prad(np_pad, 0.0f);
 
     for (uint32_t i = 0; i < nf; i++) {
         const rt3_face& f = s->faces[i];
@@ -449,6 +450,7 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     for (uint32_t i = 0; i < ns; i++) {
         const rt3_sphere& sp = s->spheres[i];
         sph[i] = make_float4(sp.cx, sp.cy, sp.cz, sp.r);
+        prad[nf + i] = sp.r;
         double c[3] = { sp.cx, sp.cy, sp.cz };
         bounds[nf + i] = make_bound(c, std::fabs((double) sp.r));
         if (s->sphere_color) { color[nf + i] = make_float4(s->sphere_color[3 * i], s->sphere_color[3 * i + 1], s->sphere_color[3 * i + 2], 0.f); }
@@ -479,6 +481,7 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     if ((rc = upload(ctx->materials, mats, ctx->stream)) != RT3_OK) { return rc; }
     if ((rc = upload(ctx->prim_material, pmat, ctx->stream)) != RT3_OK) { return rc; }
     if ((rc = upload(ctx->prim_entity, pent, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->prim_radius, prad, ctx->stream)) != RT3_OK) { return rc; }
     RT3_CUDA(cudaStreamSynchronize(ctx->stream)); /* host vectors go out of scope */
 
     rt3_scene_view& v = ctx->view;
@@ -486,7 +489,7 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     v.bounds = ctx->bounds.ptr;
     v.face_n = ctx->face_n.ptr; v.face_p1 = ctx->face_p1.ptr; v.face_p2 = ctx->face_p2.ptr; v.face_p3 = ctx->face_p3.ptr;
     v.spheres = ctx->spheres.ptr; v.prim_color = ctx->prim_color.ptr;
-    v.prim_material = ctx->prim_material.ptr; v.prim_entity = ctx->prim_entity.ptr; v.materials = ctx->materials.ptr;
+    v.prim_material = ctx->prim_material.ptr; v.prim_entity = ctx->prim_entity.ptr; v.prim_radius = ctx->prim_radius.ptr; v.materials = ctx->materials.ptr;
     ctx->has_scene = true;
     return RT3_OK;
 }

@@ -24,8 +24,10 @@
 #define RT3_BLOCK_PRIMS 32      /* primitives per candidate-mask block */
 #define RT3_TILE_PRIMS 2048     /* primitives per streamed shared-memory tile (32 KB) */
 #define RT3_RESIDENT_PRIMS 4096 /* scenes up to this size live in shared memory for the whole kernel (64 KB) */
-#define RT3_CTA_THREADS 256
+#define RT3_CTA_THREADS 128
+#define RT3_CTAS_PER_SM 5       /* register budget: 65536 / (128 * 5) = 102 per thread */
 #define RT3_ITEM_CHUNK 1024u    /* path items a warp claims per global atomic */
+#define RT3_CAND_CAP 16         /* per-ray deferred-candidate list entries (shared memory, 16-bit tile-relative ids) */
 
 /* Relative slack folded into the prefilter (64 ulp of binary32): covers the
  * rounding of the prefilter's own FMA chains plus that of the exact sphere
@@ -78,6 +80,7 @@ struct rt3_scene_view {
     const float4* prim_color;     /* per primitive: flat colour / albedo */
     const uint32_t* prim_material; /* per primitive: index into materials, or RT3_NO_HIT for Lambertian(prim_color) */
     const uint32_t* prim_entity;
+    const float* prim_radius; /* per primitive (padded): sphere radius, 0 for faces */
     const float4* materials; /* 2 float4 per material: (kind bits, albedo rgb), (fuzz, ior, -, -) */
 };
 
@@ -129,8 +132,7 @@ __device__ __forceinline__ void exact_face(const rt3_scene_view& S, uint32_t i, 
 
 /* Exact ray-sphere test, reference mode: WIP hit_sphere, raytracer_v4.glsl:157-178
  * (abc form, near root, t >= 0), un-normalised direction. */
-__device__ __forceinline__ void exact_sphere_v4(const rt3_scene_view& S, uint32_t si, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
-    float4 sp = __ldg(&S.spheres[si]);
+__device__ __forceinline__ void exact_sphere_v4(const rt3_scene_view& S, uint32_t si, float4 sp, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
     rt3_vec3 oc = o - v3(sp.x, sp.y, sp.z);
     float a = dot3(d, d);
     float b = 2.0f * dot3(oc, d);
@@ -144,8 +146,7 @@ __device__ __forceinline__ void exact_sphere_v4(const rt3_scene_view& S, uint32_
 
 /* Exact ray-sphere test, bounce loop: half-b form with a unit direction, near
  * then far root, accepted iff tmin <= t < best. */
-__device__ __forceinline__ void exact_sphere_path(const rt3_scene_view& S, uint32_t si, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
-    float4 sp = __ldg(&S.spheres[si]);
+__device__ __forceinline__ void exact_sphere_path(const rt3_scene_view& S, uint32_t si, float4 sp, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
     rt3_vec3 oc = o - v3(sp.x, sp.y, sp.z);
     float h = dot3(oc, d);
     float c = dot3(oc, oc) - sp.w * sp.w;
@@ -160,24 +161,49 @@ __device__ __forceinline__ void exact_sphere_path(const rt3_scene_view& S, uint3
     best.prim = S.n_faces + si; best.t = t;
 }
 
+/* Exact test of one candidate primitive. `sp` is the sphere record (centre,
+ * radius) when the primitive is a sphere; the caller fetches it from shared
+ * memory when the scene is resident, from global memory otherwise. */
 template <bool PATH_MODE>
-__device__ __forceinline__ void exact_prim(const rt3_scene_view& S, uint32_t prim, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
+__device__ __forceinline__ void exact_prim(const rt3_scene_view& S, uint32_t prim, float4 sp, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
     if (prim < S.n_faces) {
         exact_face(S, prim, o, d, PATH_MODE ? RT3_TMIN : 0.0f, best);
     } else if (prim < S.n_prims) {
-        if (PATH_MODE) { exact_sphere_path(S, prim - S.n_faces, o, d, best); }
-        else { exact_sphere_v4(S, prim - S.n_faces, o, d, best); }
+        if (PATH_MODE) { exact_sphere_path(S, prim - S.n_faces, sp, o, d, best); }
+        else { exact_sphere_v4(S, prim - S.n_faces, sp, o, d, best); }
     }
 }
 
+/* Where the sweep finds its data: the prefilter tile in shared memory, the
+ * per-primitive radii (shared memory for resident scenes, else NULL) and the
+ * per-thread deferred-candidate lists. */
+struct rt3_tile_view {
+    const float4* bounds;   /* shared: prefilter records of this tile */
+    const float* radius;    /* shared: sphere radii of this tile, or NULL (fetch S.spheres from global) */
+    uint16_t* cand;         /* shared: [R][RT3_CAND_CAP][RT3_CTA_THREADS] tile-relative candidate ids */
+    uint32_t first_prim;    /* global id of the tile's first primitive */
+};
+
+template <bool PATH_MODE>
+__device__ __forceinline__ void exact_candidate(const rt3_scene_view& S, const rt3_tile_view& T, uint32_t rel, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
+    const uint32_t prim = T.first_prim + rel;
+    float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (prim >= S.n_faces && prim < S.n_prims) {
+        if (T.radius) { sp = T.bounds[rel]; sp.w = T.radius[rel]; }   /* the prefilter centre of a sphere is its own centre */
+        else { sp = __ldg(&S.spheres[prim - S.n_faces]); }
+    }
+    exact_prim<PATH_MODE>(S, prim, sp, o, d, best);
+}
+
 /* Filters one block of RT3_BLOCK_PRIMS primitives (shared memory, broadcast
- * LDS.128) against R rays and runs the exact test on the survivors, in
- * ascending primitive order so that the strict `t < best` rule keeps the
- * lowest index on ties (SequentialRenderer.cpp:71). */
+ * LDS.128) against R rays. Survivors are appended to the ray's deferred list
+ * (ascending primitive order); when a list is full the exact test runs at
+ * once, which is still in ascending order. */
 template <int R, bool PATH_MODE>
-__device__ __forceinline__ void sweep_block(const rt3_scene_view& S, const float4* __restrict__ blk, uint32_t first_prim,
+__device__ __forceinline__ void sweep_block(const rt3_scene_view& S, const rt3_tile_view& T, uint32_t rel_base,
                                             const rt3_ray_filter (&f)[R], const rt3_vec3 (&o)[R], const rt3_vec3 (&d)[R],
-                                            const bool (&live)[R], rt3_hit (&best)[R]) {
+                                            const bool (&live)[R], uint32_t (&n_cand)[R], rt3_hit (&best)[R]) {
+    const float4* __restrict__ blk = T.bounds + rel_base;
     uint32_t miss[R];
 #pragma unroll
     for (int r = 0; r < R; r++) { miss[r] = 0u; }
@@ -197,8 +223,32 @@ __device__ __forceinline__ void sweep_block(const rt3_scene_view& S, const float
         while (cand) {
             int j = __clz(cand);
             cand &= ~(0x80000000u >> j);
-            exact_prim<PATH_MODE>(S, first_prim + (uint32_t) j, o[r], d[r], best[r]);
+            const uint32_t rel = rel_base + (uint32_t) j;
+            if (n_cand[r] < RT3_CAND_CAP) {
+                T.cand[(r * RT3_CAND_CAP + n_cand[r]) * RT3_CTA_THREADS + threadIdx.x] = (uint16_t) rel;
+                n_cand[r]++;
+            } else {
+                /* list full: drain it first so that the order of exact tests stays ascending */
+                for (uint32_t e = 0; e < RT3_CAND_CAP; e++) {
+                    exact_candidate<PATH_MODE>(S, T, T.cand[(r * RT3_CAND_CAP + e) * RT3_CTA_THREADS + threadIdx.x], o[r], d[r], best[r]);
+                }
+                T.cand[(r * RT3_CAND_CAP) * RT3_CTA_THREADS + threadIdx.x] = (uint16_t) rel;
+                n_cand[r] = 1;
+            }
         }
+    }
+}
+
+/* Runs the exact tests of every deferred candidate of this tile. */
+template <int R, bool PATH_MODE>
+__device__ __forceinline__ void drain_candidates(const rt3_scene_view& S, const rt3_tile_view& T, const rt3_vec3 (&o)[R],
+                                                 const rt3_vec3 (&d)[R], uint32_t (&n_cand)[R], rt3_hit (&best)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        for (uint32_t e = 0; e < n_cand[r]; e++) {
+            exact_candidate<PATH_MODE>(S, T, T.cand[(r * RT3_CAND_CAP + e) * RT3_CTA_THREADS + threadIdx.x], o[r], d[r], best[r]);
+        }
+        n_cand[r] = 0;
     }
 }
 

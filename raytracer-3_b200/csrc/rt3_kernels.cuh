@@ -32,21 +32,36 @@ __device__ __forceinline__ uint32_t owned_row_to_global(const rt3_kparams& P, ui
     return (lt * P.part_count + P.part_index) * P.tile_rows + within;
 }
 
-/* Shared-memory layout: [mbarriers (64 B)] [prefilter tiles]. */
+/* Shared-memory layout: [mbarriers (64 B)] [prefilter tiles] [radii (resident only)] [candidate lists]. */
 struct rt3_smem_view {
-    uint64_t* bars;  /* RT3 streaming: one "tile landed" mbarrier per stage */
-    float4* tiles;   /* resident: n_prims_padded entries; streamed: 2 stages of RT3_TILE_PRIMS */
+    uint64_t* bars;  /* one "tile landed" mbarrier per stage */
+    float4* tiles;   /* resident: n_prims_padded records; streamed: 2 stages of RT3_TILE_PRIMS */
+    float* radius;   /* resident: n_prims_padded radii; streamed: NULL */
+    uint16_t* cand;  /* R * RT3_CAND_CAP * RT3_CTA_THREADS deferred candidate ids */
 };
 
-__device__ __forceinline__ rt3_smem_view smem_view(unsigned char* base) {
+__host__ __device__ inline size_t rt3_smem_tile_bytes(uint32_t n_prims_padded, bool resident) {
+    size_t n = resident ? (size_t) n_prims_padded : (size_t) 2 * RT3_TILE_PRIMS;
+    return (n ? n : 1) * 16;
+}
+__host__ __device__ inline size_t rt3_smem_bytes(uint32_t n_prims_padded, bool resident, int rays_per_thread) {
+    size_t radius = resident ? (((size_t) n_prims_padded * 4 + 15) / 16) * 16 : 0;
+    return 64 + rt3_smem_tile_bytes(n_prims_padded, resident) + radius + (size_t) rays_per_thread * RT3_CAND_CAP * RT3_CTA_THREADS * 2;
+}
+
+__device__ __forceinline__ rt3_smem_view smem_view(unsigned char* base, uint32_t n_prims_padded, bool resident) {
     rt3_smem_view v;
     v.bars = reinterpret_cast<uint64_t*>(base);
     v.tiles = reinterpret_cast<float4*>(base + 64);
+    unsigned char* p = base + 64 + rt3_smem_tile_bytes(n_prims_padded, resident);
+    v.radius = resident ? reinterpret_cast<float*>(p) : nullptr;
+    if (resident) { p += (((size_t) n_prims_padded * 4 + 15) / 16) * 16; }
+    v.cand = reinterpret_cast<uint16_t*>(p);
     return v;
 }
 
-/* Brings the prefilter array into shared memory once (resident scenes) with one
- * bulk asynchronous copy per 32 KB, or arms the streaming barriers. */
+/* Brings the prefilter array (and radii) into shared memory once (resident
+ * scenes) with bulk asynchronous copies, or arms the streaming barriers. */
 __device__ __forceinline__ void scene_prologue(const rt3_scene_view& S, const rt3_smem_view& sm, bool resident) {
     if (threadIdx.x == 0) {
         mbar_init(&sm.bars[0], 1);
@@ -56,13 +71,14 @@ __device__ __forceinline__ void scene_prologue(const rt3_scene_view& S, const rt
     __syncthreads();
     if (resident) {
         if (threadIdx.x == 0 && S.n_prims_padded > 0) {
-            uint32_t bytes = S.n_prims_padded * 16u;
-            mbar_expect_tx(&sm.bars[0], bytes);
+            const uint32_t bytes = S.n_prims_padded * 16u, rbytes = S.n_prims_padded * 4u;
+            mbar_expect_tx(&sm.bars[0], bytes + rbytes);
             for (uint32_t off = 0; off < bytes; off += 32768u) {
                 uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
                 bulk_copy_g2s(reinterpret_cast<unsigned char*>(sm.tiles) + off, reinterpret_cast<const unsigned char*>(S.bounds) + off, n,
                               &sm.bars[0]);
             }
+            bulk_copy_g2s(sm.radius, S.prim_radius, rbytes, &sm.bars[0]);
         }
         if (S.n_prims_padded > 0) { mbar_wait(&sm.bars[0], 0); }
     }
@@ -76,16 +92,22 @@ __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_s
                                             const rt3_vec3 (&o)[R], const rt3_vec3 (&d)[R], const rt3_vec3 (&dn)[R],
                                             const bool (&live)[R], rt3_hit (&best)[R]) {
     rt3_ray_filter f[R];
+    uint32_t n_cand[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
         f[r] = make_ray_filter(o[r], dn[r]);
         best[r].t = __int_as_float(0x7f800000);
         best[r].prim = RT3_NO_HIT;
+        n_cand[r] = 0;
     }
+    rt3_tile_view T;
+    T.cand = sm.cand;
     if (resident) {
+        T.bounds = sm.tiles; T.radius = sm.radius; T.first_prim = 0;
         for (uint32_t base = 0; base < S.n_prims_padded; base += RT3_BLOCK_PRIMS) {
-            sweep_block<R, PATH_MODE>(S, sm.tiles + base, base, f, o, d, live, best);
+            sweep_block<R, PATH_MODE>(S, T, base, f, o, d, live, n_cand, best);
         }
+        drain_candidates<R, PATH_MODE>(S, T, o, d, n_cand, best);
         return;
     }
     const uint32_t n_tiles = (S.n_prims_padded + RT3_TILE_PRIMS - 1) / RT3_TILE_PRIMS;
@@ -94,6 +116,7 @@ __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_s
         mbar_expect_tx(&sm.bars[0], n0 * 16u);
         bulk_copy_g2s(sm.tiles, S.bounds, n0 * 16u, &sm.bars[0]);
     }
+    T.radius = nullptr;
     for (uint32_t t = 0; t < n_tiles; t++) {
         const uint32_t stage = t & 1u;
         if (threadIdx.x == 0 && t + 1 < n_tiles) {
@@ -107,10 +130,11 @@ __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_s
         phase ^= 1u << stage;
         const uint32_t first = t * RT3_TILE_PRIMS;
         const uint32_t n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
-        const float4* tile = sm.tiles + stage * RT3_TILE_PRIMS;
+        T.bounds = sm.tiles + stage * RT3_TILE_PRIMS; T.first_prim = first;
         for (uint32_t base = 0; base < n; base += RT3_BLOCK_PRIMS) {
-            sweep_block<R, PATH_MODE>(S, tile + base, first + base, f, o, d, live, best);
+            sweep_block<R, PATH_MODE>(S, T, base, f, o, d, live, n_cand, best);
         }
+        drain_candidates<R, PATH_MODE>(S, T, o, d, n_cand, best);
         __syncthreads();
     }
 }
@@ -119,12 +143,12 @@ __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_s
  * Reference mode: SequentialRenderer.cpp:269-308 (+ AOVs)
  * ------------------------------------------------------------------------ */
 template <int R>
-__global__ void __launch_bounds__(RT3_CTA_THREADS, 2)
+__global__ void __launch_bounds__(RT3_CTA_THREADS, RT3_CTAS_PER_SM)
 reference_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, uint32_t* __restrict__ frame, uint32_t* __restrict__ hit_prim,
                  uint32_t* __restrict__ hit_entity, float* __restrict__ hit_t, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const rt3_smem_view sm = smem_view(smem_raw);
     const bool resident = P.resident != 0;
+    const rt3_smem_view sm = smem_view(smem_raw, S.n_prims_padded, resident);
     scene_prologue(S, sm, resident);
     uint32_t phase = resident ? 1u : 0u;
 
@@ -232,12 +256,12 @@ __device__ __forceinline__ bool claim_item(bool want, unsigned long long& cur, u
 }
 
 template <int R>
-__global__ void __launch_bounds__(RT3_CTA_THREADS, 2)
+__global__ void __launch_bounds__(RT3_CTA_THREADS, RT3_CTAS_PER_SM)
 pathtrace_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, unsigned long long* __restrict__ accum,
                  unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const rt3_smem_view sm = smem_view(smem_raw);
     const bool resident = P.resident != 0;
+    const rt3_smem_view sm = smem_view(smem_raw, S.n_prims_padded, resident);
     scene_prologue(S, sm, resident);
     uint32_t phase = resident ? 1u : 0u;
 
