@@ -59,7 +59,6 @@ template <class T> struct DeviceBuffer {
 struct rt3_ctx {
     int device = 0;
     int sm_count = 0;
-    int rays_per_thread = 2;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_copy = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     cudaStream_t last_stream = nullptr; /* stream of the most recent render */
@@ -168,6 +167,12 @@ void triangle_bound(const double a[3], const double b[3], const double c[3], dou
     *radius = r;
 }
 
+/* Prefilter record in the duplicated layout the packed (FFMA2) operands want: (cx,cx,cy,cy) (cz,cz,-k,-k). */
+void store_bound(std::vector<float4>& recs, uint32_t i, float4 b) {
+    recs[2 * (size_t) i] = make_float4(b.x, b.x, b.y, b.y);
+    recs[2 * (size_t) i + 1] = make_float4(b.z, b.z, -b.w, -b.w);
+}
+
 template <class T> int upload(DeviceBuffer<T>& buf, const std::vector<T>& host, cudaStream_t stream) {
     int rc = buf.reserve(host.size() ? host.size() : 1);
     if (rc != RT3_OK) { return rc; }
@@ -175,9 +180,9 @@ template <class T> int upload(DeviceBuffer<T>& buf, const std::vector<T>& host, 
     return RT3_OK;
 }
 
-size_t render_smem_bytes(const rt3_scene_view& v, int rays_per_thread, bool* resident) {
+size_t render_smem_bytes(const rt3_scene_view& v, bool* resident) {
     *resident = v.n_prims_padded <= RT3_RESIDENT_PRIMS;
-    return rt3_smem_bytes(v.n_prims_padded, *resident, rays_per_thread);
+    return rt3_smem_bytes(v.n_prims_padded, *resident);
 }
 
 template <class K> int configure(K kernel, size_t smem, int* blocks_per_sm) {
@@ -186,29 +191,30 @@ template <class K> int configure(K kernel, size_t smem, int* blocks_per_sm) {
     return RT3_OK;
 }
 
-template <int R>
+template <bool RESIDENT>
 int launch_reference(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp, size_t smem, uint32_t* frame, uint32_t* prim,
                      uint32_t* ent, float* t, cudaStream_t stream) {
-    int rc = configure(reference_kernel<R>, smem, nullptr);
+    int rc = configure(reference_kernel<RESIDENT>, smem, nullptr);
     if (rc != RT3_OK) { return rc; }
-    unsigned long long per_cta = (unsigned long long) RT3_CTA_THREADS * R;
+    unsigned long long per_cta = (unsigned long long) RT3_CTA_THREADS * RT3_RAYS;
     unsigned grid = (unsigned) ((kp.n_pixels + per_cta - 1) / per_cta);
-    reference_kernel<R><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, cam, kp, frame, prim, ent, t, ctx->counters.ptr);
+    reference_kernel<RESIDENT><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, cam, kp, frame, prim, ent, t, ctx->counters.ptr);
     RT3_CUDA(cudaGetLastError());
     return RT3_OK;
 }
 
-template <int R>
+template <bool RESIDENT>
 int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp, size_t smem, cudaStream_t stream) {
     int per_sm = 0;
-    int rc = configure(pathtrace_kernel<R>, smem, &per_sm);
+    int rc = configure(pathtrace_kernel<RESIDENT>, smem, &per_sm);
     if (rc != RT3_OK) { return rc; }
     if (per_sm < 1) { return fail(RT3_ERR_CUDA, "pathtrace kernel does not fit on an SM (smem %zu)", smem); }
-    /* persistent grid: every SM full, no more CTAs than there are warps' worth of paths */
-    unsigned long long want = (kp.n_items + (unsigned long long) RT3_CTA_THREADS * R - 1) / ((unsigned long long) RT3_CTA_THREADS * R);
+    /* persistent grid: every SM full, no more CTAs than there are CTAs' worth of paths */
+    unsigned long long per_cta = (unsigned long long) RT3_CTA_THREADS * RT3_RAYS;
+    unsigned long long want = (kp.n_items + per_cta - 1) / per_cta;
     unsigned grid = (unsigned) ctx->sm_count * (unsigned) per_sm;
     if (want < grid) { grid = want ? (unsigned) want : 1u; }
-    pathtrace_kernel<R><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, cam, kp, ctx->accum.ptr, ctx->counters.ptr);
+    pathtrace_kernel<RESIDENT><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, cam, kp, ctx->accum.ptr, ctx->counters.ptr);
     RT3_CUDA(cudaGetLastError());
     return RT3_OK;
 }
@@ -218,7 +224,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
                    uint32_t* prim, uint32_t* ent, float* t, cudaStream_t stream) {
     rt3_kparams kp = kp_in;
     bool resident = false;
-    size_t smem = render_smem_bytes(ctx->view, ctx->rays_per_thread, &resident);
+    size_t smem = render_smem_bytes(ctx->view, &resident);
     kp.resident = resident ? 1u : 0u;
     ctx->stats.kernel_launches = 0;
     ctx->stats.rows_rendered = kp.owned_rows;
@@ -236,11 +242,8 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     }
     if (params->mode == RT3_MODE_REFERENCE) {
         RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
-        switch (ctx->rays_per_thread) {
-            case 1: rc = launch_reference<1>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream); break;
-            case 4: rc = launch_reference<4>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream); break;
-            default: rc = launch_reference<2>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream); break;
-        }
+        rc = resident ? launch_reference<true>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream)
+                      : launch_reference<false>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream);
         if (rc != RT3_OK) { return rc; }
         RT3_CUDA(cudaEventRecord(ctx->ev_k1, stream));
         RT3_CUDA(cudaEventRecord(ctx->ev_end, stream));
@@ -254,11 +257,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     clear_accum_kernel<<<clear_grid, 256, 0, stream>>>(kp, ctx->accum.ptr);
     RT3_CUDA(cudaGetLastError());
     RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
-    switch (ctx->rays_per_thread) {
-        case 1: rc = launch_pathtrace<1>(ctx, *cam, kp, smem, stream); break;
-        case 4: rc = launch_pathtrace<4>(ctx, *cam, kp, smem, stream); break;
-        default: rc = launch_pathtrace<2>(ctx, *cam, kp, smem, stream); break;
-    }
+    rc = resident ? launch_pathtrace<true>(ctx, *cam, kp, smem, stream) : launch_pathtrace<false>(ctx, *cam, kp, smem, stream);
     if (rc != RT3_OK) { return rc; }
     RT3_CUDA(cudaEventRecord(ctx->ev_k1, stream));
     unsigned resolve_grid = (unsigned) ((kp.n_pixels + 255ull) / 256ull);
@@ -369,10 +368,6 @@ int rt3_create(rt3_ctx** out, int device) {
     rt3_ctx* ctx = new rt3_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char* env = getenv("RT3_RAYS_PER_THREAD")) {
-        int r = atoi(env);
-        if (r == 1 || r == 2 || r == 4) { ctx->rays_per_thread = r; }
-    }
     cudaError_t err = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_begin); }
     if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_end); }
@@ -415,9 +410,10 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     ctx->has_scene = false;
 
     const uint32_t nf = s->n_faces, ns = s->n_spheres, np = nf + ns;
-    const uint32_t np_pad = (np + RT3_BLOCK_PRIMS - 1) / RT3_BLOCK_PRIMS * RT3_BLOCK_PRIMS;
+    const uint32_t np_pad = (np + RT3_PAD_PRIMS - 1) / RT3_PAD_PRIMS * RT3_PAD_PRIMS;
     const float inf = std::numeric_limits<float>::infinity();
-    std::vector<float4> bounds(np_pad, make_float4(0.f, 0.f, 0.f, inf));
+    std::vector<float4> bounds((size_t) np_pad * 2, make_float4(0.f, 0.f, -inf, -inf)); /* never-hit: -k = -inf */
+    for (uint32_t i = 0; i < np_pad; i++) { bounds[2 * (size_t) i] = make_float4(0.f, 0.f, 0.f, 0.f); }
     std::vector<float4> fn(nf), p1(nf), p2(nf), p3(nf), sph(ns), color(np), mats((size_t) s->n_materials * 2);
     std::vector<uint32_t> pmat(np, RT3_NO_HIT), pent(np, 0u);
     std::vector<float> prad(np_pad, 0.0f);
@@ -439,7 +435,7 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
         p3[i] = make_float4(c.x, c.y, c.z, 0.f);
         double da[3] = { a.x, a.y, a.z }, db[3] = { b.x, b.y, b.z }, dc[3] = { c.x, c.y, c.z }, centre[3], radius;
         triangle_bound(da, db, dc, centre, &radius);
-        bounds[i] = make_bound(centre, radius);
+        store_bound(bounds, i, make_bound(centre, radius));
         color[i] = make_float4(f.color[0], f.color[1], f.color[2], 0.f);
         if (s->face_material) {
             if (s->face_material[i] >= s->n_materials) { return fail(RT3_ERR_INVALID, "face %u: material %u out of range", i, s->face_material[i]); }
@@ -452,7 +448,7 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
         sph[i] = make_float4(sp.cx, sp.cy, sp.cz, sp.r);
         prad[nf + i] = sp.r;
         double c[3] = { sp.cx, sp.cy, sp.cz };
-        bounds[nf + i] = make_bound(c, std::fabs((double) sp.r));
+        store_bound(bounds, nf + i, make_bound(c, std::fabs((double) sp.r)));
         if (s->sphere_color) { color[nf + i] = make_float4(s->sphere_color[3 * i], s->sphere_color[3 * i + 1], s->sphere_color[3 * i + 2], 0.f); }
         else { color[nf + i] = make_float4(1.f, 1.f, 1.f, 0.f); }
         if (s->sphere_material) {

@@ -21,13 +21,17 @@
 #define RT3_TMIN 0.001f
 #define RT3_ACC_SCALE 16777216.0f
 
+#define RT3_RAYS 2              /* rays per thread: one packed-FP32 (FFMA2) pair */
 #define RT3_BLOCK_PRIMS 32      /* primitives per candidate-mask block */
-#define RT3_TILE_PRIMS 2048     /* primitives per streamed shared-memory tile (32 KB) */
-#define RT3_RESIDENT_PRIMS 4096 /* scenes up to this size live in shared memory for the whole kernel (64 KB) */
+#define RT3_GROUP 4             /* primitives filtered abreast (independent FMA chains in flight) */
+#define RT3_PAD_PRIMS 8         /* the primitive array is padded to a multiple of this with never-hit records */
+#define RT3_REC_BYTES 32        /* prefilter record: (cx,cx,cy,cy) (cz,cz,-k,-k), duplicated for the packed operands */
+#define RT3_TILE_PRIMS 1024     /* primitives per streamed shared-memory tile (32 KB) */
+#define RT3_RESIDENT_PRIMS 2048 /* scenes up to this size live in shared memory for the whole kernel (64 KB) */
 #define RT3_CTA_THREADS 128
 #define RT3_CTAS_PER_SM 5       /* register budget: 65536 / (128 * 5) = 102 per thread */
 #define RT3_ITEM_CHUNK 1024u    /* path items a warp claims per global atomic */
-#define RT3_CAND_CAP 16         /* per-ray deferred-candidate list entries (shared memory, 16-bit tile-relative ids) */
+#define RT3_CAND_CAP 32         /* per-ray deferred-candidate list entries (shared memory, 16-bit tile-relative ids) */
 
 /* Relative slack folded into the prefilter (64 ulp of binary32): covers the
  * rounding of the prefilter's own FMA chains plus that of the exact sphere
@@ -70,8 +74,8 @@ struct rt3_scene_view {
     uint32_t n_faces;
     uint32_t n_spheres;
     uint32_t n_prims;        /* n_faces + n_spheres; primitive id = face index, then n_faces + sphere index */
-    uint32_t n_prims_padded; /* rounded up to RT3_BLOCK_PRIMS with never-hit entries */
-    const float4* bounds;    /* per primitive: prefilter sphere (cx, cy, cz, |c|^2 - r_eff^2 - slack) */
+    uint32_t n_prims_padded; /* rounded up to RT3_PAD_PRIMS with never-hit records */
+    const float4* bounds;    /* per primitive 2 x float4: (cx,cx,cy,cy) (cz,cz,-k,-k), k = |c|^2 - r_eff^2 - slack */
     const float4* face_n;    /* per face: (nx, ny, nz, dot3(n, p1)) */
     const float4* face_p1;   /* per face: p1.xyz */
     const float4* face_p2;
@@ -86,28 +90,34 @@ struct rt3_scene_view {
 
 struct rt3_hit { float t; uint32_t prim; };
 
-/* Per-ray constants of the prefilter. For a sphere (c, r) and a ray (o, unit dn):
+/* Prefilter, two rays at a time. For a sphere (c, r) and a ray (o, unit dn):
  *   h    = (c - o) . dn            = c.dn - o.dn
  *   q    = |c - o|^2 - r^2         = (|c|^2 - r^2) + |o|^2 - 2 c.o
  *   disc = h^2 - q  >= 0  <=>  the line meets the sphere.
- * Three FFMA for h, one FADD + three FFMA for q, one FFMA for disc. */
-struct rt3_ray_filter { float dx, dy, dz, nod, m2ox, m2oy, m2oz, oo; };
+ * Each operation is one packed fma.rn.f32x2 / add.rn.f32x2 over the ray pair
+ * (SASS FFMA2 / FADD2): three for h, one add + three for -q, one for disc --
+ * eight FMA-pipe instructions per primitive for two rays. */
+struct rt3_pair_filter { float2 dx, dy, dz, nod, p2ox, p2oy, p2oz, noo; };
 
-__device__ __forceinline__ rt3_ray_filter make_ray_filter(rt3_vec3 o, rt3_vec3 dn) {
-    rt3_ray_filter f;
-    f.dx = dn.x; f.dy = dn.y; f.dz = dn.z;
-    f.nod = -dot3(o, dn);
-    f.m2ox = -2.0f * o.x; f.m2oy = -2.0f * o.y; f.m2oz = -2.0f * o.z;
-    float oo = dot3(o, o);
-    f.oo = oo - RT3_FILTER_SLACK * oo; /* lowering q can only add candidates */
+__device__ __forceinline__ rt3_pair_filter make_pair_filter(const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&dn)[RT3_RAYS]) {
+    rt3_pair_filter f;
+    f.dx = make_float2(dn[0].x, dn[1].x); f.dy = make_float2(dn[0].y, dn[1].y); f.dz = make_float2(dn[0].z, dn[1].z);
+    f.nod = make_float2(-dot3(o[0], dn[0]), -dot3(o[1], dn[1]));
+    f.p2ox = make_float2(2.0f * o[0].x, 2.0f * o[1].x);
+    f.p2oy = make_float2(2.0f * o[0].y, 2.0f * o[1].y);
+    f.p2oz = make_float2(2.0f * o[0].z, 2.0f * o[1].z);
+    float oo0 = dot3(o[0], o[0]), oo1 = dot3(o[1], o[1]);
+    /* -(|o|^2 - slack |o|^2): lowering q can only add candidates */
+    f.noo = make_float2(RT3_FILTER_SLACK * oo0 - oo0, RT3_FILTER_SLACK * oo1 - oo1);
     return f;
 }
 
-/* One prefilter test; returns disc (sign bit set <=> certainly no hit). */
-__device__ __forceinline__ float filter_disc(const float4 b, const rt3_ray_filter& f) {
-    float h = __fmaf_rn(b.x, f.dx, __fmaf_rn(b.y, f.dy, __fmaf_rn(b.z, f.dz, f.nod)));
-    float q = __fmaf_rn(b.x, f.m2ox, __fmaf_rn(b.y, f.m2oy, __fmaf_rn(b.z, f.m2oz, b.w + f.oo)));
-    return __fmaf_rn(h, h, -q);
+/* One prefilter test for the ray pair; the sign bit of each half is set <=> that ray certainly misses. */
+__device__ __forceinline__ float2 filter_pair(const float4 A, const float4 B, const rt3_pair_filter& f) {
+    const float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w), cz = make_float2(B.x, B.y), nk = make_float2(B.z, B.w);
+    float2 h = __ffma2_rn(cx, f.dx, __ffma2_rn(cy, f.dy, __ffma2_rn(cz, f.dz, f.nod)));
+    float2 nq = __ffma2_rn(cx, f.p2ox, __ffma2_rn(cy, f.p2oy, __ffma2_rn(cz, f.p2oz, __fadd2_rn(nk, f.noo))));
+    return __ffma2_rn(h, h, nq);
 }
 
 /* Exact ray-triangle test: the body of the reference's face loop,
@@ -178,10 +188,11 @@ __device__ __forceinline__ void exact_prim(const rt3_scene_view& S, uint32_t pri
  * per-primitive radii (shared memory for resident scenes, else NULL) and the
  * per-thread deferred-candidate lists. */
 struct rt3_tile_view {
-    const float4* bounds;   /* shared: prefilter records of this tile */
+    const float4* recs;     /* shared: prefilter records of this tile, 2 float4 per primitive */
     const float* radius;    /* shared: sphere radii of this tile, or NULL (fetch S.spheres from global) */
-    uint16_t* cand;         /* shared: [R][RT3_CAND_CAP][RT3_CTA_THREADS] tile-relative candidate ids */
+    uint16_t* cand;         /* shared: [RT3_RAYS][RT3_CAND_CAP][RT3_CTA_THREADS] tile-relative candidate ids */
     uint32_t first_prim;    /* global id of the tile's first primitive */
+    uint32_t n;             /* primitives in this tile (multiple of RT3_PAD_PRIMS) */
 };
 
 template <bool PATH_MODE>
@@ -189,66 +200,102 @@ __device__ __forceinline__ void exact_candidate(const rt3_scene_view& S, const r
     const uint32_t prim = T.first_prim + rel;
     float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
     if (prim >= S.n_faces && prim < S.n_prims) {
-        if (T.radius) { sp = T.bounds[rel]; sp.w = T.radius[rel]; }   /* the prefilter centre of a sphere is its own centre */
-        else { sp = __ldg(&S.spheres[prim - S.n_faces]); }
+        if (T.radius) {
+            /* the prefilter centre of a sphere is its own centre */
+            const float4 A = T.recs[2 * rel], B = T.recs[2 * rel + 1];
+            sp = make_float4(A.x, A.z, B.x, T.radius[rel]);
+        } else {
+            sp = __ldg(&S.spheres[prim - S.n_faces]);
+        }
     }
     exact_prim<PATH_MODE>(S, prim, sp, o, d, best);
 }
 
-/* Filters one block of RT3_BLOCK_PRIMS primitives (shared memory, broadcast
- * LDS.128) against R rays. Survivors are appended to the ray's deferred list
- * (ascending primitive order); when a list is full the exact test runs at
- * once, which is still in ascending order. */
-template <int R, bool PATH_MODE>
-__device__ __forceinline__ void sweep_block(const rt3_scene_view& S, const rt3_tile_view& T, uint32_t rel_base,
-                                            const rt3_ray_filter (&f)[R], const rt3_vec3 (&o)[R], const rt3_vec3 (&d)[R],
-                                            const bool (&live)[R], uint32_t (&n_cand)[R], rt3_hit (&best)[R]) {
-    const float4* __restrict__ blk = T.bounds + rel_base;
-    uint32_t miss[R];
+/* Closest hit of the ray pair against one shared-memory tile.
+ *
+ * Per block of 32 primitives: one broadcast LDS.128 pair per primitive, eight
+ * packed FMA-pipe instructions and two funnel shifts that collect the sign
+ * bits of disc into a per-ray miss mask. Survivors go to the ray's deferred
+ * list in ascending primitive order; the exact tests run once per tile (or
+ * earlier if a list would overflow), from a single call site, still in
+ * ascending order -- so the strict `t < best` rule keeps the lowest index on
+ * ties exactly like the reference loop (SequentialRenderer.cpp:71). */
+template <bool PATH_MODE>
+__device__ __forceinline__ void sweep_tile(const rt3_scene_view& S, const rt3_tile_view& T, const rt3_pair_filter& f,
+                                           const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&d)[RT3_RAYS], const bool (&live)[RT3_RAYS],
+                                           uint32_t (&n_cand)[RT3_RAYS], rt3_hit (&best)[RT3_RAYS]) {
+    for (uint32_t base = 0;; base += RT3_BLOCK_PRIMS) {
+        const bool last = base >= T.n;
+        uint32_t cand[RT3_RAYS] = { 0u, 0u };
+        uint32_t nb = 0;
+        if (!last) {
+            nb = T.n - base < RT3_BLOCK_PRIMS ? T.n - base : RT3_BLOCK_PRIMS;
+            const float4* __restrict__ blk = T.recs + 2 * base;
+            uint32_t miss0 = 0xFFFFFFFFu, miss1 = 0xFFFFFFFFu;
+            for (uint32_t j = 0; j < nb; j += RT3_PAD_PRIMS) {
+                /* Stage order, RT3_GROUP primitives abreast: each packed FMA of a stage shares its ray-constant
+                 * operand with the previous one (operand-reuse cache), so only the primitive pair and the
+                 * accumulator pair come from the register file -- two registers per pipe cycle, evenly split
+                 * over both banks -- and dependent instructions sit RT3_GROUP issues apart. */
 #pragma unroll
-    for (int r = 0; r < R; r++) { miss[r] = 0u; }
-#pragma unroll 8
-    for (int j = 0; j < RT3_BLOCK_PRIMS; j++) {
-        const float4 b = blk[j];
+                for (int g = 0; g < RT3_PAD_PRIMS; g += RT3_GROUP) {
+                    float4 A[RT3_GROUP], B[RT3_GROUP];
+                    float2 h[RT3_GROUP], nq[RT3_GROUP];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            float disc = filter_disc(b, f[r]);
-            /* shift the sign bit of disc into the mask: bit (31 - j) set <=> primitive j cannot be hit */
-            miss[r] = __funnelshift_l(__float_as_uint(disc), miss[r], 1);
-        }
-    }
+                    for (int u = 0; u < RT3_GROUP; u++) { A[u] = blk[2 * (j + g + u)]; B[u] = blk[2 * (j + g + u) + 1]; }
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-        uint32_t cand = live[r] ? ~miss[r] : 0u;
-        while (cand) {
-            int j = __clz(cand);
-            cand &= ~(0x80000000u >> j);
-            const uint32_t rel = rel_base + (uint32_t) j;
-            if (n_cand[r] < RT3_CAND_CAP) {
-                T.cand[(r * RT3_CAND_CAP + n_cand[r]) * RT3_CTA_THREADS + threadIdx.x] = (uint16_t) rel;
-                n_cand[r]++;
-            } else {
-                /* list full: drain it first so that the order of exact tests stays ascending */
-                for (uint32_t e = 0; e < RT3_CAND_CAP; e++) {
-                    exact_candidate<PATH_MODE>(S, T, T.cand[(r * RT3_CAND_CAP + e) * RT3_CTA_THREADS + threadIdx.x], o[r], d[r], best[r]);
+                    for (int u = 0; u < RT3_GROUP; u++) { nq[u] = __fadd2_rn(make_float2(B[u].z, B[u].w), f.noo); }
+#pragma unroll
+                    for (int u = 0; u < RT3_GROUP; u++) { h[u] = __ffma2_rn(make_float2(B[u].x, B[u].y), f.dz, f.nod); }
+#pragma unroll
+                    for (int u = 0; u < RT3_GROUP; u++) { nq[u] = __ffma2_rn(make_float2(B[u].x, B[u].y), f.p2oz, nq[u]); }
+#pragma unroll
+                    for (int u = 0; u < RT3_GROUP; u++) { h[u] = __ffma2_rn(make_float2(A[u].z, A[u].w), f.dy, h[u]); }
+#pragma unroll
+                    for (int u = 0; u < RT3_GROUP; u++) { nq[u] = __ffma2_rn(make_float2(A[u].z, A[u].w), f.p2oy, nq[u]); }
+#pragma unroll
+                    for (int u = 0; u < RT3_GROUP; u++) { h[u] = __ffma2_rn(make_float2(A[u].x, A[u].y), f.dx, h[u]); }
+#pragma unroll
+                    for (int u = 0; u < RT3_GROUP; u++) { nq[u] = __ffma2_rn(make_float2(A[u].x, A[u].y), f.p2ox, nq[u]); }
+#pragma unroll
+                    for (int u = 0; u < RT3_GROUP; u++) { h[u] = __ffma2_rn(h[u], h[u], nq[u]); }
+#pragma unroll
+                    for (int u = 0; u < RT3_GROUP; u++) {
+                        miss0 = __funnelshift_l(__float_as_uint(h[u].x), miss0, 1);
+                        miss1 = __funnelshift_l(__float_as_uint(h[u].y), miss1, 1);
+                    }
                 }
-                T.cand[(r * RT3_CAND_CAP) * RT3_CTA_THREADS + threadIdx.x] = (uint16_t) rel;
-                n_cand[r] = 1;
+            }
+            /* after nb shifts bit (nb - 1 - j) belongs to primitive j; higher bits keep their initial 1 (= miss) */
+            cand[0] = live[0] ? ~miss0 : 0u;
+            cand[1] = live[1] ? ~miss1 : 0u;
+        }
+        bool drain = last;
+#pragma unroll
+        for (int r = 0; r < RT3_RAYS; r++) { drain = drain || (n_cand[r] + (uint32_t) __popc(cand[r]) > RT3_CAND_CAP); }
+        if (drain) {
+            const uint32_t nmax = n_cand[0] > n_cand[1] ? n_cand[0] : n_cand[1];
+            for (uint32_t e = 0; e < nmax; e++) {
+#pragma unroll
+                for (int r = 0; r < RT3_RAYS; r++) {
+                    if (e < n_cand[r]) {
+                        exact_candidate<PATH_MODE>(S, T, T.cand[(r * RT3_CAND_CAP + e) * RT3_CTA_THREADS + threadIdx.x], o[r], d[r], best[r]);
+                    }
+                }
+            }
+            n_cand[0] = 0; n_cand[1] = 0;
+        }
+        if (last) { break; }
+#pragma unroll
+        for (int r = 0; r < RT3_RAYS; r++) {
+            uint32_t c = cand[r];
+            while (c) {
+                const uint32_t bit = 31u - (uint32_t) __clz(c);
+                c &= ~(1u << bit);
+                T.cand[(r * RT3_CAND_CAP + n_cand[r]) * RT3_CTA_THREADS + threadIdx.x] = (uint16_t) (base + (nb - 1u - bit));
+                n_cand[r]++;
             }
         }
-    }
-}
-
-/* Runs the exact tests of every deferred candidate of this tile. */
-template <int R, bool PATH_MODE>
-__device__ __forceinline__ void drain_candidates(const rt3_scene_view& S, const rt3_tile_view& T, const rt3_vec3 (&o)[R],
-                                                 const rt3_vec3 (&d)[R], uint32_t (&n_cand)[R], rt3_hit (&best)[R]) {
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        for (uint32_t e = 0; e < n_cand[r]; e++) {
-            exact_candidate<PATH_MODE>(S, T, T.cand[(r * RT3_CAND_CAP + e) * RT3_CTA_THREADS + threadIdx.x], o[r], d[r], best[r]);
-        }
-        n_cand[r] = 0;
     }
 }
 

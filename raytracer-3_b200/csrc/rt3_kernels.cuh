@@ -32,89 +32,91 @@ __device__ __forceinline__ uint32_t owned_row_to_global(const rt3_kparams& P, ui
     return (lt * P.part_count + P.part_index) * P.tile_rows + within;
 }
 
-/* Shared-memory layout: [mbarriers (64 B)] [prefilter tiles] [radii (resident only)] [candidate lists]. */
+/* Shared-memory layout: [mbarriers (64 B)] [prefilter records] [radii (resident only)] [candidate lists]. */
 struct rt3_smem_view {
     uint64_t* bars;  /* one "tile landed" mbarrier per stage */
-    float4* tiles;   /* resident: n_prims_padded records; streamed: 2 stages of RT3_TILE_PRIMS */
+    float4* recs;    /* resident: n_prims_padded records; streamed: 2 stages of RT3_TILE_PRIMS */
     float* radius;   /* resident: n_prims_padded radii; streamed: NULL */
-    uint16_t* cand;  /* R * RT3_CAND_CAP * RT3_CTA_THREADS deferred candidate ids */
+    uint16_t* cand;  /* RT3_RAYS * RT3_CAND_CAP * RT3_CTA_THREADS deferred candidate ids */
 };
 
-__host__ __device__ inline size_t rt3_smem_tile_bytes(uint32_t n_prims_padded, bool resident) {
+__host__ __device__ inline size_t rt3_smem_rec_bytes(uint32_t n_prims_padded, bool resident) {
     size_t n = resident ? (size_t) n_prims_padded : (size_t) 2 * RT3_TILE_PRIMS;
-    return (n ? n : 1) * 16;
+    return (n ? n : 1) * RT3_REC_BYTES;
 }
-__host__ __device__ inline size_t rt3_smem_bytes(uint32_t n_prims_padded, bool resident, int rays_per_thread) {
-    size_t radius = resident ? (((size_t) n_prims_padded * 4 + 15) / 16) * 16 : 0;
-    return 64 + rt3_smem_tile_bytes(n_prims_padded, resident) + radius + (size_t) rays_per_thread * RT3_CAND_CAP * RT3_CTA_THREADS * 2;
+__host__ __device__ inline size_t rt3_smem_radius_bytes(uint32_t n_prims_padded, bool resident) {
+    return resident ? (((size_t) n_prims_padded * 4 + 15) / 16) * 16 : 0;
+}
+__host__ __device__ inline size_t rt3_smem_bytes(uint32_t n_prims_padded, bool resident) {
+    return 64 + rt3_smem_rec_bytes(n_prims_padded, resident) + rt3_smem_radius_bytes(n_prims_padded, resident) +
+           (size_t) RT3_RAYS * RT3_CAND_CAP * RT3_CTA_THREADS * 2;
 }
 
-__device__ __forceinline__ rt3_smem_view smem_view(unsigned char* base, uint32_t n_prims_padded, bool resident) {
+template <bool RESIDENT>
+__device__ __forceinline__ rt3_smem_view smem_view(unsigned char* base, uint32_t n_prims_padded) {
     rt3_smem_view v;
     v.bars = reinterpret_cast<uint64_t*>(base);
-    v.tiles = reinterpret_cast<float4*>(base + 64);
-    unsigned char* p = base + 64 + rt3_smem_tile_bytes(n_prims_padded, resident);
-    v.radius = resident ? reinterpret_cast<float*>(p) : nullptr;
-    if (resident) { p += (((size_t) n_prims_padded * 4 + 15) / 16) * 16; }
+    v.recs = reinterpret_cast<float4*>(base + 64);
+    unsigned char* p = base + 64 + rt3_smem_rec_bytes(n_prims_padded, RESIDENT);
+    v.radius = RESIDENT ? reinterpret_cast<float*>(p) : nullptr;
+    p += rt3_smem_radius_bytes(n_prims_padded, RESIDENT);
     v.cand = reinterpret_cast<uint16_t*>(p);
     return v;
 }
 
-/* Brings the prefilter array (and radii) into shared memory once (resident
- * scenes) with bulk asynchronous copies, or arms the streaming barriers. */
-__device__ __forceinline__ void scene_prologue(const rt3_scene_view& S, const rt3_smem_view& sm, bool resident) {
+/* Brings the prefilter records (and radii) into shared memory once (resident
+ * scenes) with bulk asynchronous copies (TMA, SASS UBLKCP), or arms the
+ * streaming barriers. */
+template <bool RESIDENT>
+__device__ __forceinline__ void scene_prologue(const rt3_scene_view& S, const rt3_smem_view& sm) {
     if (threadIdx.x == 0) {
         mbar_init(&sm.bars[0], 1);
         mbar_init(&sm.bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (resident) {
-        if (threadIdx.x == 0 && S.n_prims_padded > 0) {
-            const uint32_t bytes = S.n_prims_padded * 16u, rbytes = S.n_prims_padded * 4u;
+    if (RESIDENT && S.n_prims_padded > 0) {
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = S.n_prims_padded * RT3_REC_BYTES, rbytes = S.n_prims_padded * 4u;
             mbar_expect_tx(&sm.bars[0], bytes + rbytes);
             for (uint32_t off = 0; off < bytes; off += 32768u) {
                 uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
-                bulk_copy_g2s(reinterpret_cast<unsigned char*>(sm.tiles) + off, reinterpret_cast<const unsigned char*>(S.bounds) + off, n,
+                bulk_copy_g2s(reinterpret_cast<unsigned char*>(sm.recs) + off, reinterpret_cast<const unsigned char*>(S.bounds) + off, n,
                               &sm.bars[0]);
             }
             bulk_copy_g2s(sm.radius, S.prim_radius, rbytes, &sm.bars[0]);
         }
-        if (S.n_prims_padded > 0) { mbar_wait(&sm.bars[0], 0); }
+        mbar_wait(&sm.bars[0], 0);
     }
 }
 
-/* Closest hit of R rays against the whole scene. For streamed scenes every
- * thread of the CTA must call this together (tile barriers); `phase` carries
- * the mbarrier parities across calls. */
-template <int R, bool PATH_MODE>
-__device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_smem_view& sm, bool resident, uint32_t& phase,
-                                            const rt3_vec3 (&o)[R], const rt3_vec3 (&d)[R], const rt3_vec3 (&dn)[R],
-                                            const bool (&live)[R], rt3_hit (&best)[R]) {
-    rt3_ray_filter f[R];
-    uint32_t n_cand[R];
+/* Closest hit of the ray pair against the whole scene. For streamed scenes
+ * every thread of the CTA must call this together (tile barriers); `phase`
+ * carries the mbarrier parities across calls. */
+template <bool PATH_MODE, bool RESIDENT>
+__device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_smem_view& sm, uint32_t& phase,
+                                            const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&d)[RT3_RAYS], const rt3_vec3 (&dn)[RT3_RAYS],
+                                            const bool (&live)[RT3_RAYS], rt3_hit (&best)[RT3_RAYS]) {
+    const rt3_pair_filter f = make_pair_filter(o, dn);
+    uint32_t n_cand[RT3_RAYS];
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-        f[r] = make_ray_filter(o[r], dn[r]);
+    for (int r = 0; r < RT3_RAYS; r++) {
         best[r].t = __int_as_float(0x7f800000);
         best[r].prim = RT3_NO_HIT;
         n_cand[r] = 0;
     }
     rt3_tile_view T;
     T.cand = sm.cand;
-    if (resident) {
-        T.bounds = sm.tiles; T.radius = sm.radius; T.first_prim = 0;
-        for (uint32_t base = 0; base < S.n_prims_padded; base += RT3_BLOCK_PRIMS) {
-            sweep_block<R, PATH_MODE>(S, T, base, f, o, d, live, n_cand, best);
-        }
-        drain_candidates<R, PATH_MODE>(S, T, o, d, n_cand, best);
+    if (RESIDENT) {
+        T.recs = sm.recs; T.radius = sm.radius; T.first_prim = 0; T.n = S.n_prims_padded;
+        sweep_tile<PATH_MODE>(S, T, f, o, d, live, n_cand, best);
         return;
     }
     const uint32_t n_tiles = (S.n_prims_padded + RT3_TILE_PRIMS - 1) / RT3_TILE_PRIMS;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && n_tiles > 0) {
         uint32_t n0 = S.n_prims_padded < RT3_TILE_PRIMS ? S.n_prims_padded : RT3_TILE_PRIMS;
-        mbar_expect_tx(&sm.bars[0], n0 * 16u);
-        bulk_copy_g2s(sm.tiles, S.bounds, n0 * 16u, &sm.bars[0]);
+        mbar_expect_tx(&sm.bars[0], n0 * RT3_REC_BYTES);
+        bulk_copy_g2s(sm.recs, S.bounds, n0 * RT3_REC_BYTES, &sm.bars[0]);
     }
     T.radius = nullptr;
     for (uint32_t t = 0; t < n_tiles; t++) {
@@ -123,18 +125,17 @@ __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_s
             /* stage^1 was last read for tile t-1; the __syncthreads below ordered those reads before this copy */
             uint32_t first = (t + 1) * RT3_TILE_PRIMS;
             uint32_t n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
-            mbar_expect_tx(&sm.bars[stage ^ 1u], n * 16u);
-            bulk_copy_g2s(sm.tiles + (stage ^ 1u) * RT3_TILE_PRIMS, S.bounds + first, n * 16u, &sm.bars[stage ^ 1u]);
+            mbar_expect_tx(&sm.bars[stage ^ 1u], n * RT3_REC_BYTES);
+            bulk_copy_g2s(sm.recs + (size_t) (stage ^ 1u) * RT3_TILE_PRIMS * 2, S.bounds + (size_t) first * 2, n * RT3_REC_BYTES,
+                          &sm.bars[stage ^ 1u]);
         }
         mbar_wait(&sm.bars[stage], (phase >> stage) & 1u);
         phase ^= 1u << stage;
         const uint32_t first = t * RT3_TILE_PRIMS;
-        const uint32_t n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
-        T.bounds = sm.tiles + stage * RT3_TILE_PRIMS; T.first_prim = first;
-        for (uint32_t base = 0; base < n; base += RT3_BLOCK_PRIMS) {
-            sweep_block<R, PATH_MODE>(S, T, base, f, o, d, live, n_cand, best);
-        }
-        drain_candidates<R, PATH_MODE>(S, T, o, d, n_cand, best);
+        T.recs = sm.recs + (size_t) stage * RT3_TILE_PRIMS * 2;
+        T.first_prim = first;
+        T.n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
+        sweep_tile<PATH_MODE>(S, T, f, o, d, live, n_cand, best);
         __syncthreads();
     }
 }
@@ -142,15 +143,15 @@ __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_s
 /* ------------------------------------------------------------------------ *
  * Reference mode: SequentialRenderer.cpp:269-308 (+ AOVs)
  * ------------------------------------------------------------------------ */
-template <int R>
+template <bool RESIDENT>
 __global__ void __launch_bounds__(RT3_CTA_THREADS, RT3_CTAS_PER_SM)
 reference_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, uint32_t* __restrict__ frame, uint32_t* __restrict__ hit_prim,
                  uint32_t* __restrict__ hit_entity, float* __restrict__ hit_t, unsigned long long* __restrict__ counters) {
+    constexpr int R = RT3_RAYS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const bool resident = P.resident != 0;
-    const rt3_smem_view sm = smem_view(smem_raw, S.n_prims_padded, resident);
-    scene_prologue(S, sm, resident);
-    uint32_t phase = resident ? 1u : 0u;
+    const rt3_smem_view sm = smem_view<RESIDENT>(smem_raw, S.n_prims_padded);
+    scene_prologue<RESIDENT>(S, sm);
+    uint32_t phase = 0u;
 
     const rt3_vec3 origin = v3(cam.origin[0], cam.origin[1], cam.origin[2]);
     const rt3_vec3 hor = v3(cam.horizontal[0], cam.horizontal[1], cam.horizontal[2]);
@@ -177,7 +178,7 @@ reference_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, uint32_t* __re
         d[r] = ((llc + u * hor) + v * ver) - origin;
         dn[r] = normalize3(d[r]);
     }
-    sweep_scene<R, false>(S, sm, resident, phase, o, d, dn, live, best);
+    sweep_scene<false, RESIDENT>(S, sm, phase, o, d, dn, live, best);
     unsigned long long rays = 0;
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -227,43 +228,61 @@ __device__ __forceinline__ unsigned long long to_fixed(float c) {
     return (unsigned long long) (c * RT3_ACC_SCALE + 0.5f);
 }
 
-/* Warp-cooperative claim of one path item per requesting lane. `cur`/`end`
- * are the warp's current chunk (uniform); chunks come from one global counter. */
-__device__ __forceinline__ bool claim_item(bool want, unsigned long long& cur, unsigned long long& end, bool& dry,
-                                           unsigned long long n_items, unsigned long long* next_item, unsigned long long& item) {
+/* A warp's current chunk of path items [cur, end) out of the global counter,
+ * with the (pixel, sample) of its first item so that per-item decoding needs
+ * 32-bit arithmetic only. All fields are warp-uniform. */
+struct rt3_chunk {
+    unsigned long long cur, end, start;
+    uint32_t pixel0, sample0; /* item `start` = (pixel0, sample0) */
+    bool dry;                 /* the global counter is exhausted */
+};
+
+/* Warp-cooperative claim of one path item per requesting lane. Items are
+ * item = pixel * spp + sample over this partition's compact pixel list. */
+__device__ __forceinline__ bool claim_item(bool want, rt3_chunk& c, const rt3_kparams& P, unsigned long long* next_item,
+                                           uint32_t& pixel, uint32_t& sample) {
     const unsigned lane = threadIdx.x & 31u;
     unsigned m = __ballot_sync(0xffffffffu, want);
     int n = __popc(m);
     int rank = __popc(m & ((1u << lane) - 1u));
     bool got = false;
-    while (n > 0 && !dry) {
-        if (cur == end) {
-            unsigned long long c = 0;
-            if (lane == 0) { c = atomicAdd(next_item, (unsigned long long) RT3_ITEM_CHUNK); }
-            c = __shfl_sync(0xffffffffu, c, 0);
-            if (c >= n_items) { dry = true; break; }
-            cur = c;
-            end = c + RT3_ITEM_CHUNK < n_items ? c + RT3_ITEM_CHUNK : n_items;
+    while (n > 0 && !c.dry) {
+        if (c.cur == c.end) {
+            unsigned long long v = 0;
+            if (lane == 0) { v = atomicAdd(next_item, (unsigned long long) RT3_ITEM_CHUNK); }
+            v = __shfl_sync(0xffffffffu, v, 0);
+            if (v >= P.n_items) { c.dry = true; break; }
+            c.cur = c.start = v;
+            c.end = v + RT3_ITEM_CHUNK < P.n_items ? v + RT3_ITEM_CHUNK : P.n_items;
+            unsigned long long p0 = v / P.spp; /* one 64-bit divide per chunk */
+            c.pixel0 = (uint32_t) p0;
+            c.sample0 = (uint32_t) (v - p0 * P.spp);
         }
-        unsigned long long avail = end - cur;
+        unsigned long long avail = c.end - c.cur;
         int take = (unsigned long long) n < avail ? n : (int) avail;
-        if (want && !got && rank >= 0 && rank < take) { item = cur + (unsigned long long) rank; got = true; }
+        if (want && !got && rank >= 0 && rank < take) {
+            uint32_t k = (uint32_t) (c.cur - c.start) + (uint32_t) rank + c.sample0; /* < spp + chunk */
+            uint32_t dp = k / P.spp;
+            pixel = c.pixel0 + dp;
+            sample = k - dp * P.spp;
+            got = true;
+        }
         rank -= take;
-        cur += (unsigned long long) take;
+        c.cur += (unsigned long long) take;
         n -= take;
     }
     return got;
 }
 
-template <int R>
+template <bool RESIDENT>
 __global__ void __launch_bounds__(RT3_CTA_THREADS, RT3_CTAS_PER_SM)
 pathtrace_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, unsigned long long* __restrict__ accum,
                  unsigned long long* __restrict__ counters) {
+    constexpr int R = RT3_RAYS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const bool resident = P.resident != 0;
-    const rt3_smem_view sm = smem_view(smem_raw, S.n_prims_padded, resident);
-    scene_prologue(S, sm, resident);
-    uint32_t phase = resident ? 1u : 0u;
+    const rt3_smem_view sm = smem_view<RESIDENT>(smem_raw, S.n_prims_padded);
+    scene_prologue<RESIDENT>(S, sm);
+    uint32_t phase = 0u;
 
     const rt3_vec3 cam_o = v3(cam.origin[0], cam.origin[1], cam.origin[2]);
     const rt3_vec3 hor = v3(cam.horizontal[0], cam.horizontal[1], cam.horizontal[2]);
@@ -278,19 +297,18 @@ pathtrace_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, unsigned long 
     rt3_hit best[R];
 #pragma unroll
     for (int r = 0; r < R; r++) { live[r] = false; bounce[r] = 0; key[r] = 0; pix[r] = 0; o[r] = d[r] = thr[r] = v3(0.f, 0.f, 0.f); }
-    unsigned long long cur = 0, end = 0, rays = 0;
-    bool dry = false;
+    unsigned long long rays = 0;
+    rt3_chunk chunk;
+    chunk.cur = chunk.end = chunk.start = 0; chunk.pixel0 = chunk.sample0 = 0; chunk.dry = false;
 
     for (;;) {
         /* (1) regenerate: every free slot starts the next (pixel, sample) item */
         bool any = false;
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            unsigned long long item = 0;
-            if (claim_item(!live[r], cur, end, dry, P.n_items, &counters[0], item)) {
-                unsigned long long p = item / P.spp;
-                uint32_t sample = (uint32_t) (item - p * P.spp);
-                uint32_t local_row = (uint32_t) (p / P.width), x = (uint32_t) (p - (unsigned long long) local_row * P.width);
+            uint32_t p = 0, sample = 0;
+            if (claim_item(!live[r], chunk, P, &counters[0], p, sample)) {
+                uint32_t local_row = p / P.width, x = p - local_row * P.width;
                 uint32_t y = owned_row_to_global(P, local_row);
                 uint32_t pixel_index = y * P.width + x;
                 pix[r] = (size_t) pixel_index;
@@ -319,11 +337,11 @@ pathtrace_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, unsigned long 
             }
             any = any || live[r];
         }
-        if (resident) { if (!__any_sync(0xffffffffu, any)) { break; } }
-        else { if (!__syncthreads_or(any ? 1 : 0)) { break; } }
+        if (RESIDENT) { if (!__any_sync(0xffffffffu, any)) { break; } }   /* warps run independently */
+        else { if (!__syncthreads_or(any ? 1 : 0)) { break; } }           /* tiles are CTA-wide */
 
         /* (2) closest hit of every live ray against the whole scene */
-        sweep_scene<R, true>(S, sm, resident, phase, o, d, d, live, best);
+        sweep_scene<true, RESIDENT>(S, sm, phase, o, d, d, live, best);
 
         /* (3) shade: miss -> sky * throughput; hit -> scatter */
 #pragma unroll
