@@ -150,7 +150,7 @@ def main():
     import numpy as np
     import torch
     import rt3_b200  # noqa: F401
-    from rt3_b200 import abi, scenes
+    from rt3_b200 import abi, distributed, scenes
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -179,7 +179,6 @@ def main():
     my_rows = lib.rt3_partition_rows(H, TILE_ROWS, rank, world)
     max_rows = max(lib.rt3_partition_rows(H, TILE_ROWS, r, world) for r in range(world))
     slab = torch.zeros(max_rows * W, dtype=torch.int32, device=dev)
-    gathered = [torch.zeros(max_rows * W, dtype=torch.int32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
     host_frame_t = torch.zeros(H * W, dtype=torch.int32).pin_memory()
     host_frame = host_frame_t.numpy().view(np.uint32).reshape(H, W)
     launches_per_step = 3  # clear_accum + pathtrace + resolve
@@ -189,7 +188,7 @@ def main():
         ctx.render_device(cam, params, frame.data_ptr(), stream.cuda_stream)
         if world > 1:
             ctx.pack_partition(frame.data_ptr(), slab.data_ptr(), W, H, TILE_ROWS, rank, world, stream.cuda_stream)
-            dist.gather(slab, gathered, dst=0)
+            gathered = distributed.gather_slabs(dist, slab, rank, world)  # NCCL, frame end only
             if rank == 0:
                 for r in range(1, world):
                     ctx.unpack_partition(gathered[r].data_ptr(), frame.data_ptr(), W, H, TILE_ROWS, r, world, stream.cuda_stream)

@@ -6,4 +6,4 @@ package is plumbing for tests and benchmarks (ctypes bindings, synthetic
 scenes). It is loaded through the top-level ``rt3_b200`` module because the
 directory name is not a valid Python identifier.
 """
-from . import abi, scenes  # noqa: F401
+from . import abi, distributed, scenes  # noqa: F401

@@ -1,0 +1,180 @@
+/* renderer/CudaRenderer.cpp — see CudaRenderer.hpp. */
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include <CppDebugger.hpp>
+
+#include "entities/Triangle.hpp"
+#include "entities/Sphere.hpp"
+#include "entities/Object.hpp"
+
+#include "CudaRenderer.hpp"
+
+using namespace RayTracer;
+using namespace RayTracer::ECS;
+using namespace CppDebugger::SeverityValues;
+
+static_assert(sizeof(GFace) == sizeof(rt3_face), "GFace and rt3_face must share a layout");
+static_assert(sizeof(glm::vec4) == sizeof(rt3_vertex), "vec4 and rt3_vertex must share a layout");
+
+namespace {
+    void check(int status, const char* what) {
+        if (status != RT3_OK) { DLOG(fatal, std::string(what) + ": " + rt3_last_error()); }
+    }
+
+    uint32_t env_u32(const char* name, uint32_t fallback) {
+        const char* v = std::getenv(name);
+        return (v && *v) ? (uint32_t) std::strtoul(v, nullptr, 0) : fallback;
+    }
+}
+
+CudaRenderSettings CudaRenderSettings::from_environment(int* device) {
+    CudaRenderSettings s;
+    const char* mode = std::getenv("RT3_MODE");
+    if (mode && std::string(mode) == "pathtrace") { s.mode = RT3_MODE_PATHTRACE; }
+    s.spp = env_u32("RT3_SPP", s.spp);
+    s.max_depth = env_u32("RT3_DEPTH", s.max_depth);
+    s.seed = env_u32("RT3_SEED", s.seed);
+    s.analytic_spheres = env_u32("RT3_ANALYTIC_SPHERES", 0) != 0;
+    if (device) { *device = (int) env_u32("RT3_DEVICE", 0); }
+    return s;
+}
+
+CudaRenderer::CudaRenderer(int device) : Renderer(), ctx(nullptr) {
+    std::memset(&this->last_stats, 0, sizeof this->last_stats);
+    check(rt3_create(&this->ctx, device), "Could not create the CUDA render context");
+}
+
+CudaRenderer::~CudaRenderer() { rt3_destroy(this->ctx); }
+
+void CudaRenderer::prerender(const Tools::Array<ECS::RenderEntity*>& entities) {
+    this->flat_faces.clear(); this->flat_vertices.clear(); this->flat_face_entity.clear(); this->flat_spheres.clear();
+    std::vector<uint32_t> face_material, sphere_material, sphere_entity;
+    std::vector<float> sphere_color;
+    std::vector<rt3_material> table;
+    bool any_material = !this->materials.empty();
+
+    Tools::Array<GFace> faces;
+    Tools::Array<glm::vec4> vertices;
+    for (size_t i = 0; i < entities.size(); i++) {
+        RenderEntity* e = entities[i];
+        if (!(e->pre_render_mode & EntityPreRenderModeFlags::eprmf_cpu)) {
+            DLOG(fatal, "Entity " + std::to_string(i) + " of type " + entity_type_names[e->type] + " cannot be pre-rendered on the CPU.");
+        }
+        /* material row of this entity: explicit, or Lambertian(colour) when any material is in use */
+        uint32_t material_index = 0;
+        glm::vec3 entity_color(1.0f, 1.0f, 1.0f);
+        switch (e->pre_render_operation) {
+            case EntityPreRenderOperation::epro_generate_triangle: entity_color = ((Triangle*) e)->color; break;
+            case EntityPreRenderOperation::epro_generate_sphere: entity_color = ((Sphere*) e)->color; break;
+            case EntityPreRenderOperation::epro_load_object_file: entity_color = ((Object*) e)->color; break;
+            default: break;
+        }
+        if (any_material) {
+            Material m;
+            m.albedo = entity_color;
+            std::map<size_t, Material>::const_iterator it = this->materials.find(i);
+            if (it != this->materials.end()) { m = it->second; }
+            rt3_material row;
+            std::memset(&row, 0, sizeof row);
+            row.kind = (uint32_t) m.kind;
+            row.albedo[0] = m.albedo.x; row.albedo[1] = m.albedo.y; row.albedo[2] = m.albedo.z;
+            row.fuzz = m.fuzz; row.ior = m.ior;
+            material_index = (uint32_t) table.size();
+            table.push_back(row);
+        }
+
+        if (e->pre_render_operation == EntityPreRenderOperation::epro_generate_sphere && this->settings.analytic_spheres) {
+            const Sphere* s = (const Sphere*) e;
+            rt3_sphere sp = { s->center.x, s->center.y, s->center.z, s->radius };
+            this->flat_spheres.push_back(sp);
+            sphere_color.push_back(s->color.x); sphere_color.push_back(s->color.y); sphere_color.push_back(s->color.z);
+            sphere_entity.push_back((uint32_t) i);
+            sphere_material.push_back(material_index);
+            continue;
+        }
+
+        /* tessellate / load into per-entity buffers of the announced size (SequentialRenderer.cpp:216-243) */
+        faces.clear(); vertices.clear();
+        faces.resize(e->pre_render_faces);
+        vertices.resize(e->pre_render_vertices);
+        switch (e->pre_render_operation) {
+            case EntityPreRenderOperation::epro_generate_triangle: cpu_pre_render_triangle(faces, vertices, (Triangle*) e); break;
+            case EntityPreRenderOperation::epro_generate_sphere: cpu_pre_render_sphere(faces, vertices, (Sphere*) e); break;
+            case EntityPreRenderOperation::epro_load_object_file: cpu_pre_render_object(faces, vertices, (Object*) e); break;
+            default:
+                DLOG(fatal, "Entity " + std::to_string(i) + " wants to be pre-rendered using unsupported operation '" +
+                                entity_pre_render_operation_names[e->pre_render_operation] + "'.");
+        }
+        /* append with re-based indices (SequentialRenderer.cpp:174-195) */
+        const uint32_t offset = (uint32_t) this->flat_vertices.size();
+        for (size_t f = 0; f < faces.size(); f++) {
+            rt3_face out;
+            std::memcpy(&out, &faces[f], sizeof out);
+            out.v1 += offset; out.v2 += offset; out.v3 += offset;
+            this->flat_faces.push_back(out);
+            this->flat_face_entity.push_back((uint32_t) i);
+            face_material.push_back(material_index);
+        }
+        for (size_t v = 0; v < vertices.size(); v++) {
+            rt3_vertex out;
+            std::memcpy(&out, &vertices[v], sizeof out);
+            this->flat_vertices.push_back(out);
+        }
+    }
+
+    rt3_scene scene;
+    std::memset(&scene, 0, sizeof scene);
+    scene.n_faces = (uint32_t) this->flat_faces.size();
+    scene.n_vertices = (uint32_t) this->flat_vertices.size();
+    scene.faces = this->flat_faces.data();
+    scene.vertices = this->flat_vertices.data();
+    scene.face_entity = this->flat_face_entity.data();
+    scene.face_material = any_material ? face_material.data() : nullptr;
+    scene.n_spheres = (uint32_t) this->flat_spheres.size();
+    scene.spheres = this->flat_spheres.data();
+    scene.sphere_color = sphere_color.data();
+    scene.sphere_entity = sphere_entity.data();
+    scene.sphere_material = any_material ? sphere_material.data() : nullptr;
+    scene.n_materials = (uint32_t) table.size();
+    scene.materials = table.data();
+    check(rt3_scene_upload(this->ctx, &scene), "Could not upload the scene");
+}
+
+void CudaRenderer::render(Camera& camera) const {
+    rt3_camera cam;
+    std::memset(&cam, 0, sizeof cam);
+    const glm::vec3* src[4] = { &camera.origin, &camera.horizontal, &camera.vertical, &camera.lower_left_corner };
+    float* dst[4] = { cam.origin, cam.horizontal, cam.vertical, cam.lower_left_corner };
+    for (int i = 0; i < 4; i++) { dst[i][0] = src[i]->x; dst[i][1] = src[i]->y; dst[i][2] = src[i]->z; }
+#ifdef RT3_HOST_CAMERA_CAMERA_HPP /* the thin lens exists only in this repo's Camera, not in the reference's */
+    cam.lens_radius = camera.lens_radius;
+    cam.lens_u[0] = camera.lens_u.x; cam.lens_u[1] = camera.lens_u.y; cam.lens_u[2] = camera.lens_u.z;
+    cam.lens_v[0] = camera.lens_v.x; cam.lens_v[1] = camera.lens_v.y; cam.lens_v[2] = camera.lens_v.z;
+#endif
+
+    rt3_params params;
+    std::memset(&params, 0, sizeof params);
+    params.width = camera.w();
+    params.height = camera.h();
+    params.mode = this->settings.mode;
+    params.spp = this->settings.spp;
+    params.max_depth = this->settings.max_depth;
+    params.seed = this->settings.seed;
+    params.flags = this->settings.flags;
+    params.tile_rows = this->settings.tile_rows;
+    params.part_index = this->settings.part_index;
+    params.part_count = this->settings.part_count;
+    check(rt3_render(this->ctx, &cam, &params, camera.get_frame().d()), "Render failed");
+    check(rt3_get_stats(this->ctx, &this->last_stats), "Could not read render statistics");
+}
+
+/* Factory of this backend (reference Renderer.hpp:63; counterpart of SequentialRenderer.cpp:315-323). */
+Renderer* RayTracer::initialize_renderer() {
+    int device = 0;
+    CudaRenderSettings settings = CudaRenderSettings::from_environment(&device);
+    CudaRenderer* renderer = new CudaRenderer(device);
+    renderer->set_settings(settings);
+    return (Renderer*) renderer;
+}

@@ -1,0 +1,80 @@
+/* renderer/CudaRenderer.hpp — the B200 backend behind RayTracer::Renderer.
+ *
+ * Replaces SequentialRenderer / VulkanRenderer (reference
+ * src/lib/renderer/SequentialRenderer.hpp:25-45, VulkanRenderer.hpp:40-95) for
+ * the render path: prerender() flattens the ECS entities exactly as the
+ * reference does (SequentialRenderer.cpp:174-266) and uploads them once;
+ * render() runs the CUDA core through the C ABI of include/rt3cuda.h and writes
+ * Camera::get_frame() in place. Failures go through DLOG(fatal, ...) like the
+ * reference's backends.
+ *
+ * Written against the reference's own header names (renderer/Renderer.hpp,
+ * entities/..., camera/Camera.hpp, tools/Array.hpp), so the same source
+ * builds standalone against raytracer-3_b200/host/ and inside the reference
+ * tree (oracle/Makefile target `dropin`).
+ */
+#ifndef RT3_HOST_RENDERER_CUDA_RENDERER_HPP
+#define RT3_HOST_RENDERER_CUDA_RENDERER_HPP
+
+#include <cstdint>
+#include <map>
+#include <vector>
+
+#include "renderer/Renderer.hpp"
+#include "rt3cuda.h"
+
+namespace RayTracer {
+    /* Material of an entity for the bounce loop. The reference's entities only carry a colour
+     * (Sphere.hpp:44 etc.), so materials are a side table keyed by entity index. */
+    struct Material {
+        enum Kind { lambertian = RT3_MAT_LAMBERTIAN, metal = RT3_MAT_METAL, dielectric = RT3_MAT_DIELECTRIC };
+        Kind kind = lambertian;
+        glm::vec3 albedo = glm::vec3(0.5f, 0.5f, 0.5f);
+        float fuzz = 0.0f;
+        float ior = 1.5f;
+    };
+
+    struct CudaRenderSettings {
+        uint32_t mode = RT3_MODE_REFERENCE; /* RT3_MODE_REFERENCE reproduces the reference's image */
+        uint32_t spp = 100;
+        uint32_t max_depth = 50;
+        uint32_t seed = 1;
+        uint32_t flags = 0;
+        bool analytic_spheres = false;      /* keep ECS spheres analytic instead of tessellating them */
+        uint32_t tile_rows = 8, part_index = 0, part_count = 1;
+        /* Reads RT3_MODE (reference|pathtrace), RT3_SPP, RT3_DEPTH, RT3_SEED, RT3_ANALYTIC_SPHERES, RT3_DEVICE. */
+        static CudaRenderSettings from_environment(int* device);
+    };
+
+    class CudaRenderer : public Renderer {
+        rt3_ctx* ctx;
+        CudaRenderSettings settings;
+        std::map<size_t, Material> materials;
+        mutable rt3_stats last_stats;
+
+    public:
+        explicit CudaRenderer(int device = 0);
+        CudaRenderer(const CudaRenderer&) = delete;
+        virtual ~CudaRenderer();
+
+        void set_settings(const CudaRenderSettings& s) { this->settings = s; }
+        const CudaRenderSettings& get_settings() const { return this->settings; }
+        /* Applies to the next prerender(). */
+        void set_material(size_t entity_index, const Material& material) { this->materials[entity_index] = material; }
+        void clear_materials() { this->materials.clear(); }
+
+        virtual void prerender(const Tools::Array<ECS::RenderEntity*>& entities);
+        virtual void render(Camera& camera) const;
+
+        /* Device timings / ray counters of the last render(). */
+        const rt3_stats& stats() const { return this->last_stats; }
+
+        /* The flattened scene of the last prerender() (host copies, for inspection and tests). */
+        std::vector<rt3_face> flat_faces;
+        std::vector<rt3_vertex> flat_vertices;
+        std::vector<uint32_t> flat_face_entity;
+        std::vector<rt3_sphere> flat_spheres;
+    };
+}
+
+#endif

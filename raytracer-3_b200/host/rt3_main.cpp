@@ -1,0 +1,77 @@
+/* rt3_main.cpp — command-line driver of the host backend: the shape of reference src/Main.cpp:246-315
+ * (create renderer, camera, entities; prerender; render; save), with the scene chosen by name.
+ *
+ *   rt3_render [-W width] [-H height] [-s scene] [-o out.ppm] [--teddy path/to/teddy.obj]
+ *   scenes: default (reference Main.cpp:280-283, needs --teddy), triangle, sphere, rtiow (path traced, C1)
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include <CppDebugger.hpp>
+
+#include "entities/Triangle.hpp"
+#include "entities/Sphere.hpp"
+#include "entities/Object.hpp"
+#include "renderer/CudaRenderer.hpp"
+
+using namespace RayTracer;
+
+int main(int argc, const char** argv) {
+    uint32_t width = 800, height = 600; /* reference defaults, Main.cpp:78-79 */
+    std::string scene = "triangle", out = "result.ppm", teddy = "bin/objects/teddy.obj";
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char* { if (i + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", a.c_str()); std::exit(1); } return argv[++i]; };
+        if (a == "-W") { width = (uint32_t) std::strtoul(next(), nullptr, 0); }
+        else if (a == "-H") { height = (uint32_t) std::strtoul(next(), nullptr, 0); }
+        else if (a == "-s") { scene = next(); }
+        else if (a == "-o") { out = next(); }
+        else if (a == "--teddy") { teddy = next(); }
+        else { std::fprintf(stderr, "usage: %s [-W w] [-H h] [-s default|triangle|sphere|rtiow] [-o out.ppm] [--teddy file]\n", argv[0]); return a == "-h" ? 0 : 1; }
+    }
+    try {
+        Renderer* renderer = initialize_renderer();
+        CudaRenderer* cuda = (CudaRenderer*) renderer;
+        Camera cam;
+        Tools::Array<ECS::RenderEntity*> entities;
+        if (scene == "default") {
+            entities.push_back(ECS::create_object(teddy, {0.0f, 0.0f, -3.0f}, 1.0f / 17.0f, {1.0f, 0.0f, 0.0f}));
+            entities.push_back(ECS::create_sphere({-2.0f, 0.0f, -5.0f}, 1.0f, 8, 8, {0.0f, 0.0f, 1.0f}));
+        } else if (scene == "sphere") {
+            entities.push_back(ECS::create_sphere({0.0f, 0.0f, -3.0f}, 1.0f, 8, 8, {1.0f, 0.0f, 0.0f}));
+        } else if (scene == "rtiow") {
+            entities.push_back(ECS::create_sphere({0.0f, -100.5f, -1.0f}, 100.0f, 8, 8, {0.8f, 0.8f, 0.0f}));
+            entities.push_back(ECS::create_sphere({0.0f, 0.0f, -1.0f}, 0.5f, 8, 8, {0.1f, 0.2f, 0.5f}));
+            entities.push_back(ECS::create_sphere({-1.0f, 0.0f, -1.0f}, 0.5f, 8, 8, {1.0f, 1.0f, 1.0f}));
+            entities.push_back(ECS::create_sphere({1.0f, 0.0f, -1.0f}, 0.5f, 8, 8, {0.8f, 0.6f, 0.2f}));
+            CudaRenderSettings st = cuda->get_settings();
+            st.mode = RT3_MODE_PATHTRACE; st.analytic_spheres = true;
+            cuda->set_settings(st);
+            Material glass; glass.kind = Material::dielectric; glass.ior = 1.5f;
+            Material gold; gold.kind = Material::metal; gold.albedo = glm::vec3(0.8f, 0.6f, 0.2f);
+            cuda->set_material(2, glass);
+            cuda->set_material(3, gold);
+        } else {
+            entities.push_back(ECS::create_triangle({1.0f, 0.0f, -3.0f}, {-1.0f, 0.0f, -3.0f}, {0.0f, 1.0f, -3.0f}, {1.0f, 0.0f, 0.0f}));
+        }
+        if (scene == "rtiow") { cam.update(width, height, 1.0f, ((float) width / (float) height) * 2.0f, 2.0f); }
+        else { cam.update(width, height, 2.0f, ((float) width / (float) height) * 2.0f, 2.0f); }
+        renderer->prerender(entities);
+        renderer->render(cam);
+        for (size_t i = 0; i < entities.size(); i++) {
+            if (entities[i]->type == ECS::et_object) { delete (ECS::Object*) entities[i]; }
+            else if (entities[i]->type == ECS::et_sphere) { delete (ECS::Sphere*) entities[i]; }
+            else { delete (ECS::Triangle*) entities[i]; }
+        }
+        cam.get_frame().to_ppm(out);
+        std::printf("%s: %ux%u, %.3f ms on the device, %llu rays -> %s\n", scene.c_str(), width, height, cuda->stats().device_ms,
+                    (unsigned long long) cuda->stats().rays, out.c_str());
+        delete renderer;
+    } catch (CppDebugger::Fatal& e) {
+        std::fprintf(stderr, "fatal: %s\n", e.what());
+        return -1;
+    }
+    return 0;
+}

@@ -1,0 +1,65 @@
+"""GPU: the C++ host backend end to end (ECS::create_* -> CudaRenderer::prerender -> render -> Frame),
+and the drop-in proof: the reference's UNMODIFIED main() linked against CudaRenderer renders the
+reference's default scene to the reference's golden image."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import hostlib
+import oraclelib as ol
+from conftest import ROOT, load_golden
+from rt3_b200 import abi, scenes
+
+pytestmark = pytest.mark.gpu
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def test_reference_mode_through_the_host_backend(built):
+    g, _ = load_golden("sphere8_400x225")
+    hs = hostlib.HostScene()
+    hs.add_sphere((0, 0, -3), 1.0, 8, 8, (1, 0, 0))
+    hs.create_renderer(mode=abi.MODE_REFERENCE)
+    hs.prerender()
+    frame, ms, rays = hs.render(400, 225)
+    assert np.array_equal(frame[:224], g["frame"])
+    assert rays == 400 * 225 and ms > 0
+    # render() may be called again with another camera after one prerender() (Renderer.hpp:48-50)
+    frame2, _, _ = hs.render(200, 113)
+    small, _, _, _ = ol.oracle_reference(hs.flatten(), abi.reference_camera(200, 113), 200, 113)
+    assert np.array_equal(frame2, small)
+
+
+def test_path_tracing_through_the_host_backend(built):
+    """C1 built through ECS::create_sphere + the material side table equals the oracle on the same scene."""
+    w, h = 96, 54
+    hs = hostlib.HostScene()
+    for c, r, col in (((0, -100.5, -1), 100.0, (0.8, 0.8, 0.0)), ((0, 0, -1), 0.5, (0.1, 0.2, 0.5)),
+                      ((-1, 0, -1), 0.5, (1, 1, 1)), ((1, 0, -1), 0.5, (0.8, 0.6, 0.2))):
+        hs.add_sphere(c, r, 8, 8, col)
+    hs.create_renderer(mode=abi.MODE_PATHTRACE, spp=8, max_depth=50, seed=3, analytic_spheres=True)
+    hs.set_material(2, abi.MAT_DIELECTRIC, (1, 1, 1), 0.0, 1.5)
+    hs.set_material(3, abi.MAT_METAL, (0.8, 0.6, 0.2), 0.0, 1.0)
+    hs.prerender()
+    frame, _, rays = hs.render(w, h, focal=1.0)
+    scene, cam = scenes.rtiow_four_spheres(w, h)
+    cpu, _, cpu_rays = ol.oracle_pathtrace(scene, cam, abi.make_params(w, h, mode=abi.MODE_PATHTRACE, spp=8, max_depth=50, seed=3))
+    assert rays == cpu_rays and np.array_equal(frame, cpu)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_DIR, "raytracer_cuda")), reason="drop-in binary not built (needs /root/reference at build time)")
+def test_reference_main_with_cuda_backend_renders_the_golden_image(tmp_path):
+    g, _ = load_golden("default_400x225")
+    out = tmp_path / "out.ppm"
+    subprocess.run([os.path.join(REF_DIR, "raytracer_cuda"), "-W", "400", "-H", "225", "-f", "ppm", str(out)], cwd=REF_DIR, check=True,
+                   stdout=subprocess.DEVNULL, timeout=120)
+    tokens = out.read_bytes().split(maxsplit=4)
+    assert tokens[0] in (b"P3", b"P6") and (int(tokens[1]), int(tokens[2])) == (400, 225)
+    if tokens[0] == b"P6":
+        rgb = np.frombuffer(tokens[4], np.uint8)[:400 * 225 * 3]
+    else:
+        rgb = np.array(out.read_bytes().split()[4:], dtype=np.uint8)
+    rgb = rgb.reshape(225, 400, 3).astype(np.uint32)
+    frame = (rgb[..., 0] << 24) | (rgb[..., 1] << 16) | (rgb[..., 2] << 8) | 0xFF
+    assert np.array_equal(frame[:224], g["frame"])
