@@ -10,6 +10,7 @@
  * Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
  * (see __graft_entry__.build()). There is no CPU path in this library.
  */
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -119,21 +120,76 @@ float round_down(double v) {
     return f;
 }
 
-/* Prefilter entry for a bounding sphere (double centre c, radius r >= 0). */
+/* Prefilter record (cx, cy, cz, -R^2) for a bounding sphere (double centre c, radius r >= 0).
+ * R^2 = r_inflated^2 + slack |c|^2, rounded so that the record can only admit more. */
 float4 make_bound(const double c[3], double r) {
-    const float never[4] = { 0.0f, 0.0f, 0.0f, std::numeric_limits<float>::infinity() };
-    float4 out = { never[0], never[1], never[2], never[3] };
+    float4 out = make_float4(0.0f, 0.0f, 0.0f, std::numeric_limits<float>::infinity()); /* never survives */
     if (!(std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]) && std::isfinite(r))) { return out; }
     float cf[3] = { (float) c[0], (float) c[1], (float) c[2] };
     double cc = (double) cf[0] * cf[0] + (double) cf[1] * cf[1] + (double) cf[2] * cf[2];
     double clen = std::sqrt(cc);
-    /* inflate: relative 2^-10, absolute 2^-16 (|c| + r) (centre rounding, hit-point rounding of the exact tests) */
+    /* inflate: relative 2^-10, absolute 2^-16 (|c| + r) (centre rounding, rounding of a and b, hit-point rounding of the exact tests) */
     double re = r * (1.0 + 1.0 / 1024.0) + (clen + r) / 65536.0 + 1e-30;
-    double k = cc - re * re - (double) RT3_FILTER_SLACK * (cc + re * re);
-    float kf = round_down(k);
-    if (!std::isfinite(kf)) { return out; }
-    out.x = cf[0]; out.y = cf[1]; out.z = cf[2]; out.w = kf;
+    double R2 = re * re + (double) RT3_FILTER_SLACK * cc;
+    float nR2 = round_down(-R2);
+    if (!std::isfinite(nR2)) { return out; }
+    out.x = cf[0]; out.y = cf[1]; out.z = cf[2]; out.w = nR2;
     return out;
+}
+
+/* Jacobi eigen-decomposition of a symmetric 3x3 matrix; eigenvectors in the columns of v. */
+void jacobi3(double a[3][3], double v[3][3], double w[3]) {
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) { v[i][j] = i == j ? 1.0 : 0.0; } }
+    for (int sweep = 0; sweep < 32; sweep++) {
+        double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        if (off < 1e-300) { break; }
+        for (int p = 0; p < 2; p++) {
+            for (int q = p + 1; q < 3; q++) {
+                if (std::fabs(a[p][q]) < 1e-300) { continue; }
+                double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; k++) { double akp = a[k][p], akq = a[k][q]; a[k][p] = c * akp - s * akq; a[k][q] = s * akp + c * akq; }
+                for (int k = 0; k < 3; k++) { double apk = a[p][k], aqk = a[q][k]; a[p][k] = c * apk - s * aqk; a[q][k] = s * apk + c * aqk; }
+                for (int k = 0; k < 3; k++) { double vkp = v[k][p], vkq = v[k][q]; v[k][p] = c * vkp - s * vkq; v[k][q] = s * vkp + c * vkq; }
+            }
+        }
+    }
+    for (int i = 0; i < 3; i++) { w[i] = a[i][i]; }
+}
+
+/* The axis along which the primitive centres spread least, and a unit vector perpendicular to it.
+ * Primitives far larger than the typical one (a ground sphere of radius 1000) survive every slab anyway
+ * and would only skew the statistics, so they are left out. */
+void thin_axis(const std::vector<float4>& recs, uint32_t n, float axis[3], float alt[3]) {
+    axis[0] = 0.f; axis[1] = 1.f; axis[2] = 0.f; alt[0] = 1.f; alt[1] = 0.f; alt[2] = 0.f;
+    std::vector<float> r2;
+    for (uint32_t i = 0; i < n; i++) { if (std::isfinite(recs[i].w)) { r2.push_back(-recs[i].w); } }
+    if (r2.size() < 2) { return; }
+    std::nth_element(r2.begin(), r2.begin() + r2.size() / 2, r2.end());
+    const float r2_cap = 100.0f * r2[r2.size() / 2];
+    auto used = [&](uint32_t i) { return std::isfinite(recs[i].w) && -recs[i].w <= r2_cap; };
+    double mean[3] = { 0, 0, 0 };
+    uint32_t cnt = 0;
+    for (uint32_t i = 0; i < n; i++) { if (used(i)) { mean[0] += recs[i].x; mean[1] += recs[i].y; mean[2] += recs[i].z; cnt++; } }
+    if (cnt < 2) { return; }
+    for (int k = 0; k < 3; k++) { mean[k] /= cnt; }
+    double cov[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+    for (uint32_t i = 0; i < n; i++) {
+        if (!used(i)) { continue; }
+        double d[3] = { recs[i].x - mean[0], recs[i].y - mean[1], recs[i].z - mean[2] };
+        for (int p = 0; p < 3; p++) { for (int q = 0; q < 3; q++) { cov[p][q] += d[p] * d[q]; } }
+    }
+    double vec[3][3], val[3];
+    jacobi3(cov, vec, val);
+    if (!(std::isfinite(val[0]) && std::isfinite(val[1]) && std::isfinite(val[2]))) { return; }
+    int lo = 0, hi = 0;
+    for (int k = 1; k < 3; k++) { if (val[k] < val[lo]) { lo = k; } if (val[k] > val[hi]) { hi = k; } }
+    if (lo == hi) { return; }
+    double la = 0, lb = 0;
+    for (int k = 0; k < 3; k++) { la += vec[k][lo] * vec[k][lo]; lb += vec[k][hi] * vec[k][hi]; }
+    if (!(la > 0.5 && lb > 0.5)) { return; }
+    for (int k = 0; k < 3; k++) { axis[k] = (float) (vec[k][lo] / std::sqrt(la)); alt[k] = (float) (vec[k][hi] / std::sqrt(lb)); }
 }
 
 /* Smallest sphere through/around a triangle (double precision). */
@@ -165,12 +221,6 @@ void triangle_bound(const double a[3], const double b[3], const double c[3], dou
     double r = 0.0;
     for (int i = 0; i < 3; i++) { double l = dist(centre, v[i]); if (l > r) { r = l; } }
     *radius = r;
-}
-
-/* Prefilter record in the duplicated layout the packed (FFMA2) operands want: (cx,cx,cy,cy) (cz,cz,-k,-k). */
-void store_bound(std::vector<float4>& recs, uint32_t i, float4 b) {
-    recs[2 * (size_t) i] = make_float4(b.x, b.x, b.y, b.y);
-    recs[2 * (size_t) i + 1] = make_float4(b.z, b.z, -b.w, -b.w);
 }
 
 template <class T> int upload(DeviceBuffer<T>& buf, const std::vector<T>& host, cudaStream_t stream) {
@@ -412,8 +462,7 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     const uint32_t nf = s->n_faces, ns = s->n_spheres, np = nf + ns;
     const uint32_t np_pad = (np + RT3_PAD_PRIMS - 1) / RT3_PAD_PRIMS * RT3_PAD_PRIMS;
     const float inf = std::numeric_limits<float>::infinity();
-    std::vector<float4> bounds((size_t) np_pad * 2, make_float4(0.f, 0.f, -inf, -inf)); /* never-hit: -k = -inf */
-    for (uint32_t i = 0; i < np_pad; i++) { bounds[2 * (size_t) i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    std::vector<float4> bounds(np_pad, make_float4(0.f, 0.f, 0.f, inf)); /* never survives: a^2 + inf > 0 */
     std::vector<float4> fn(nf), p1(nf), p2(nf), p3(nf), sph(ns), color(np), mats((size_t) s->n_materials * 2);
     std::vector<uint32_t> pmat(np, RT3_NO_HIT), pent(np, 0u);
     std::vector<float> prad(np_pad, 0.0f);
@@ -435,7 +484,7 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
         p3[i] = make_float4(c.x, c.y, c.z, 0.f);
         double da[3] = { a.x, a.y, a.z }, db[3] = { b.x, b.y, b.z }, dc[3] = { c.x, c.y, c.z }, centre[3], radius;
         triangle_bound(da, db, dc, centre, &radius);
-        store_bound(bounds, i, make_bound(centre, radius));
+        bounds[i] = make_bound(centre, radius);
         color[i] = make_float4(f.color[0], f.color[1], f.color[2], 0.f);
         if (s->face_material) {
             if (s->face_material[i] >= s->n_materials) { return fail(RT3_ERR_INVALID, "face %u: material %u out of range", i, s->face_material[i]); }
@@ -448,7 +497,7 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
         sph[i] = make_float4(sp.cx, sp.cy, sp.cz, sp.r);
         prad[nf + i] = sp.r;
         double c[3] = { sp.cx, sp.cy, sp.cz };
-        store_bound(bounds, nf + i, make_bound(c, std::fabs((double) sp.r)));
+        bounds[nf + i] = make_bound(c, std::fabs((double) sp.r));
         if (s->sphere_color) { color[nf + i] = make_float4(s->sphere_color[3 * i], s->sphere_color[3 * i + 1], s->sphere_color[3 * i + 2], 0.f); }
         else { color[nf + i] = make_float4(1.f, 1.f, 1.f, 0.f); }
         if (s->sphere_material) {
@@ -466,6 +515,24 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
         mats[2 * i + 1] = make_float4(m.fuzz, m.ior, 0.f, 0.f);
     }
 
+    float axis[3], axis_alt[3], ray_slack;
+    thin_axis(bounds, np, axis, axis_alt);
+    {
+        /* smallest R^2 in the scene, floored at 1/400 of the median so that one sliver cannot inflate every slab */
+        std::vector<float> r2;
+        for (uint32_t i = 0; i < np; i++) { if (std::isfinite(bounds[i].w)) { r2.push_back(-bounds[i].w); } }
+        float r2min = 1.0f;
+        if (!r2.empty()) {
+            std::nth_element(r2.begin(), r2.begin() + r2.size() / 2, r2.end());
+            float median = r2[r2.size() / 2], lowest = *std::min_element(r2.begin(), r2.end());
+            r2min = std::max(lowest, median / 400.0f);
+            if (!(r2min > 0.0f)) { r2min = 1e-30f; }
+            /* records below the floor are raised to it (admits more, never less) */
+            for (uint32_t i = 0; i < np; i++) { if (std::isfinite(bounds[i].w) && -bounds[i].w < r2min) { bounds[i].w = -r2min; } }
+        }
+        ray_slack = RT3_FILTER_SLACK / r2min;
+    }
+
     int rc;
     if ((rc = upload(ctx->bounds, bounds, ctx->stream)) != RT3_OK) { return rc; }
     if ((rc = upload(ctx->face_n, fn, ctx->stream)) != RT3_OK) { return rc; }
@@ -481,6 +548,8 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     RT3_CUDA(cudaStreamSynchronize(ctx->stream)); /* host vectors go out of scope */
 
     rt3_scene_view& v = ctx->view;
+    for (int k = 0; k < 3; k++) { v.axis[k] = axis[k]; v.axis_alt[k] = axis_alt[k]; }
+    v.ray_slack = ray_slack;
     v.n_faces = nf; v.n_spheres = ns; v.n_prims = np; v.n_prims_padded = np_pad;
     v.bounds = ctx->bounds.ptr;
     v.face_n = ctx->face_n.ptr; v.face_p1 = ctx->face_p1.ptr; v.face_p2 = ctx->face_p2.ptr; v.face_p3 = ctx->face_p3.ptr;

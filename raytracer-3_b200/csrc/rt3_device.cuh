@@ -21,21 +21,22 @@
 #define RT3_TMIN 0.001f
 #define RT3_ACC_SCALE 16777216.0f
 
-#define RT3_RAYS 2              /* rays per thread: one packed-FP32 (FFMA2) pair */
+#define RT3_RAYS 2              /* rays (path slots) per thread */
 #define RT3_BLOCK_PRIMS 32      /* primitives per candidate-mask block */
-#define RT3_GROUP 4             /* primitives filtered abreast (independent FMA chains in flight) */
 #define RT3_PAD_PRIMS 8         /* the primitive array is padded to a multiple of this with never-hit records */
-#define RT3_REC_BYTES 32        /* prefilter record: (cx,cx,cy,cy) (cz,cz,-k,-k), duplicated for the packed operands */
-#define RT3_TILE_PRIMS 1024     /* primitives per streamed shared-memory tile (32 KB) */
-#define RT3_RESIDENT_PRIMS 2048 /* scenes up to this size live in shared memory for the whole kernel (64 KB) */
+#define RT3_REC_BYTES 16        /* prefilter record: (cx, cy, cz, -R^2) */
+#define RT3_TILE_PRIMS 2048     /* primitives per streamed shared-memory tile (32 KB) */
+#define RT3_RESIDENT_PRIMS 4096 /* scenes up to this size live in shared memory for the whole kernel (64 KB) */
 #define RT3_CTA_THREADS 128
 #define RT3_CTAS_PER_SM 5       /* register budget: 65536 / (128 * 5) = 102 per thread */
 #define RT3_ITEM_CHUNK 1024u    /* path items a warp claims per global atomic */
 #define RT3_CAND_CAP 32         /* per-ray deferred-candidate list entries (shared memory, 16-bit tile-relative ids) */
 
-/* Relative slack folded into the prefilter (64 ulp of binary32): covers the
- * rounding of the prefilter's own FMA chains plus that of the exact sphere
- * test it stands in front of, both bounded by ~28 eps (|c|^2 + |o|^2). */
+/* Relative slack of the prefilter (64 ulp of binary32), applied to |c|^2 per
+ * primitive (host, folded into R^2) and to |o|^2 per ray (folded into the
+ * scale of the slab basis). It covers the rounding of the prefilter's own FMA
+ * chains plus that of the exact sphere test it stands in front of, which is
+ * bounded by ~14 eps |c - o|^2 <= 28 eps (|c|^2 + |o|^2). */
 #define RT3_FILTER_SLACK 3.814697265625e-06f
 
 struct rt3_vec3 { float x, y, z; };
@@ -75,7 +76,7 @@ struct rt3_scene_view {
     uint32_t n_spheres;
     uint32_t n_prims;        /* n_faces + n_spheres; primitive id = face index, then n_faces + sphere index */
     uint32_t n_prims_padded; /* rounded up to RT3_PAD_PRIMS with never-hit records */
-    const float4* bounds;    /* per primitive 2 x float4: (cx,cx,cy,cy) (cz,cz,-k,-k), k = |c|^2 - r_eff^2 - slack */
+    const float4* bounds;    /* per primitive: (cx, cy, cz, -R^2), R = inflated bounding radius (R^2 includes the per-primitive slack) */
     const float4* face_n;    /* per face: (nx, ny, nz, dot3(n, p1)) */
     const float4* face_p1;   /* per face: p1.xyz */
     const float4* face_p2;
@@ -85,39 +86,53 @@ struct rt3_scene_view {
     const uint32_t* prim_material; /* per primitive: index into materials, or RT3_NO_HIT for Lambertian(prim_color) */
     const uint32_t* prim_entity;
     const float* prim_radius; /* per primitive (padded): sphere radius, 0 for faces */
+    float axis[3];            /* unit vector along which the scene is thinnest (PCA of the primitive centres) */
+    float axis_alt[3];        /* a unit vector perpendicular to axis */
+    float ray_slack;          /* RT3_FILTER_SLACK / min R^2: per-ray inflation of the slab is 1 + ray_slack |o|^2 */
     const float4* materials; /* 2 float4 per material: (kind bits, albedo rgb), (fuzz, ior, -, -) */
 };
 
 struct rt3_hit { float t; uint32_t prim; };
 
-/* Prefilter, two rays at a time. For a sphere (c, r) and a ray (o, unit dn):
- *   h    = (c - o) . dn            = c.dn - o.dn
- *   q    = |c - o|^2 - r^2         = (|c|^2 - r^2) + |o|^2 - 2 c.o
- *   disc = h^2 - q  >= 0  <=>  the line meets the sphere.
- * Each operation is one packed fma.rn.f32x2 / add.rn.f32x2 over the ray pair
- * (SASS FFMA2 / FADD2): three for h, one add + three for -q, one for disc --
- * eight FMA-pipe instructions per primitive for two rays. */
-struct rt3_pair_filter { float2 dx, dy, dz, nod, p2ox, p2oy, p2oz, noo; };
+/* Two-level conservative prefilter in a per-ray orthonormal basis (u, v) of the
+ * plane perpendicular to the unit direction dn. With a = (c - o).u and
+ * b = (c - o).v the distance of a centre c from the ray's line is
+ * sqrt(a^2 + b^2), so
+ *   level 1 (every primitive, 4 FMA):   a^2     - R^2 < 0   (the slab |a| < R)
+ *   level 2 (level-1 survivors, 8 FMA): a^2+b^2 - R^2 < 0   (the line meets the bounding sphere)
+ * are both necessary for any hit. u is chosen perpendicular to the scene's
+ * thinnest axis, so the slab (a plane through the ray containing that axis)
+ * cuts across the scene's long extent and few primitives survive level 1.
+ * The per-ray slack (oracle rounding ~ eps |c-o|^2) is folded into the basis:
+ * u and v are scaled by s = 1/sqrt(1 + ray_slack |o|^2) <= 1, which inflates
+ * every R^2 by at least RT3_FILTER_SLACK |o|^2 at no per-test cost. */
+struct rt3_ray_slab { float ux, uy, uz, nou, vx, vy, vz, nov; };
 
-__device__ __forceinline__ rt3_pair_filter make_pair_filter(const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&dn)[RT3_RAYS]) {
-    rt3_pair_filter f;
-    f.dx = make_float2(dn[0].x, dn[1].x); f.dy = make_float2(dn[0].y, dn[1].y); f.dz = make_float2(dn[0].z, dn[1].z);
-    f.nod = make_float2(-dot3(o[0], dn[0]), -dot3(o[1], dn[1]));
-    f.p2ox = make_float2(2.0f * o[0].x, 2.0f * o[1].x);
-    f.p2oy = make_float2(2.0f * o[0].y, 2.0f * o[1].y);
-    f.p2oz = make_float2(2.0f * o[0].z, 2.0f * o[1].z);
-    float oo0 = dot3(o[0], o[0]), oo1 = dot3(o[1], o[1]);
-    /* -(|o|^2 - slack |o|^2): lowering q can only add candidates */
-    f.noo = make_float2(RT3_FILTER_SLACK * oo0 - oo0, RT3_FILTER_SLACK * oo1 - oo1);
+__device__ __forceinline__ rt3_ray_slab make_ray_slab(const rt3_scene_view& S, rt3_vec3 o, rt3_vec3 dn) {
+    rt3_vec3 u = cross3(dn, v3(S.axis[0], S.axis[1], S.axis[2]));
+    float uu = dot3(u, u);
+    if (!(uu >= 0.01f)) { u = cross3(dn, v3(S.axis_alt[0], S.axis_alt[1], S.axis_alt[2])); uu = dot3(u, u); }
+    const float scale = 1.0f / sqrtf(uu * (1.0f + S.ray_slack * dot3(o, o)));
+    u = scale * u;
+    const rt3_vec3 v = cross3(dn, u); /* |v| = |u| (dn is unit and perpendicular to u) */
+    rt3_ray_slab f;
+    f.ux = u.x; f.uy = u.y; f.uz = u.z; f.nou = -dot3(o, u);
+    f.vx = v.x; f.vy = v.y; f.vz = v.z; f.nov = -dot3(o, v);
     return f;
 }
 
-/* One prefilter test for the ray pair; the sign bit of each half is set <=> that ray certainly misses. */
-__device__ __forceinline__ float2 filter_pair(const float4 A, const float4 B, const rt3_pair_filter& f) {
-    const float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w), cz = make_float2(B.x, B.y), nk = make_float2(B.z, B.w);
-    float2 h = __ffma2_rn(cx, f.dx, __ffma2_rn(cy, f.dy, __ffma2_rn(cz, f.dz, f.nod)));
-    float2 nq = __ffma2_rn(cx, f.p2ox, __ffma2_rn(cy, f.p2oy, __ffma2_rn(cz, f.p2oz, __fadd2_rn(nk, f.noo))));
-    return __ffma2_rn(h, h, nq);
+/* Level 1: sign bit set <=> the primitive survives (|a| < R). Four FMA-pipe instructions. */
+__device__ __forceinline__ float slab_test(const float4 b, const rt3_ray_slab& f) {
+    const float a = __fmaf_rn(b.x, f.ux, __fmaf_rn(b.y, f.uy, __fmaf_rn(b.z, f.uz, f.nou)));
+    return __fmaf_rn(a, a, b.w);
+}
+
+/* Level 2: true <=> the ray's line may meet the primitive's bounding sphere. */
+__device__ __forceinline__ bool line_test(const float4 b, const rt3_ray_slab& f) {
+    const float a = __fmaf_rn(b.x, f.ux, __fmaf_rn(b.y, f.uy, __fmaf_rn(b.z, f.uz, f.nou)));
+    const float c = __fmaf_rn(b.x, f.vx, __fmaf_rn(b.y, f.vy, __fmaf_rn(b.z, f.vz, f.nov)));
+    const float d2 = __fmaf_rn(c, c, __fmaf_rn(a, a, b.w));
+    return !(d2 > 0.0f);
 }
 
 /* Exact ray-triangle test: the body of the reference's face loop,
@@ -188,102 +203,95 @@ __device__ __forceinline__ void exact_prim(const rt3_scene_view& S, uint32_t pri
  * per-primitive radii (shared memory for resident scenes, else NULL) and the
  * per-thread deferred-candidate lists. */
 struct rt3_tile_view {
-    const float4* recs;     /* shared: prefilter records of this tile, 2 float4 per primitive */
+    const float4* recs;     /* shared: prefilter records of this tile */
     const float* radius;    /* shared: sphere radii of this tile, or NULL (fetch S.spheres from global) */
     uint16_t* cand;         /* shared: [RT3_RAYS][RT3_CAND_CAP][RT3_CTA_THREADS] tile-relative candidate ids */
     uint32_t first_prim;    /* global id of the tile's first primitive */
     uint32_t n;             /* primitives in this tile (multiple of RT3_PAD_PRIMS) */
 };
 
+/* Exact test of one level-2 survivor. */
 template <bool PATH_MODE>
 __device__ __forceinline__ void exact_candidate(const rt3_scene_view& S, const rt3_tile_view& T, uint32_t rel, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
     const uint32_t prim = T.first_prim + rel;
     float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
     if (prim >= S.n_faces && prim < S.n_prims) {
-        if (T.radius) {
-            /* the prefilter centre of a sphere is its own centre */
-            const float4 A = T.recs[2 * rel], B = T.recs[2 * rel + 1];
-            sp = make_float4(A.x, A.z, B.x, T.radius[rel]);
-        } else {
-            sp = __ldg(&S.spheres[prim - S.n_faces]);
-        }
+        /* the prefilter centre of a sphere is its own centre */
+        if (T.radius) { const float4 rec = T.recs[rel]; sp = make_float4(rec.x, rec.y, rec.z, T.radius[rel]); }
+        else { sp = __ldg(&S.spheres[prim - S.n_faces]); }
     }
     exact_prim<PATH_MODE>(S, prim, sp, o, d, best);
 }
 
-/* Closest hit of the ray pair against one shared-memory tile.
+/* Closest hit of the thread's rays against one shared-memory tile.
  *
- * Per block of 32 primitives: one broadcast LDS.128 pair per primitive, eight
- * packed FMA-pipe instructions and two funnel shifts that collect the sign
- * bits of disc into a per-ray miss mask. Survivors go to the ray's deferred
- * list in ascending primitive order; the exact tests run once per tile (or
- * earlier if a list would overflow), from a single call site, still in
- * ascending order -- so the strict `t < best` rule keeps the lowest index on
- * ties exactly like the reference loop (SequentialRenderer.cpp:71). */
+ * Per block of 32 primitives and per ray: one broadcast LDS.128 per primitive
+ * (shared by the rays), four FMA-pipe instructions (level 1) and one funnel
+ * shift that collects the sign bit into a 32-primitive survivor mask.
+ * Survivors go to the ray's deferred list in ascending primitive order; the
+ * list is drained once per tile (or earlier if it would overflow) from a single
+ * call site: level 2, then the exact test, still in ascending order -- so the
+ * strict `t < best` rule keeps the lowest index on ties exactly like the
+ * reference loop (SequentialRenderer.cpp:71). */
 template <bool PATH_MODE>
-__device__ __forceinline__ void sweep_tile(const rt3_scene_view& S, const rt3_tile_view& T, const rt3_pair_filter& f,
+__device__ __forceinline__ void sweep_tile(const rt3_scene_view& S, const rt3_tile_view& T, const rt3_ray_slab (&f)[RT3_RAYS],
                                            const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&d)[RT3_RAYS], const bool (&live)[RT3_RAYS],
                                            uint32_t (&n_cand)[RT3_RAYS], rt3_hit (&best)[RT3_RAYS]) {
     for (uint32_t base = 0;; base += RT3_BLOCK_PRIMS) {
         const bool last = base >= T.n;
-        uint32_t cand[RT3_RAYS] = { 0u, 0u };
+        uint32_t cand[RT3_RAYS];
+#pragma unroll
+        for (int r = 0; r < RT3_RAYS; r++) { cand[r] = 0u; }
         uint32_t nb = 0;
         if (!last) {
             nb = T.n - base < RT3_BLOCK_PRIMS ? T.n - base : RT3_BLOCK_PRIMS;
-            const float4* __restrict__ blk = T.recs + 2 * base;
-            uint32_t miss0 = 0xFFFFFFFFu, miss1 = 0xFFFFFFFFu;
+            const float4* __restrict__ blk = T.recs + base;
             for (uint32_t j = 0; j < nb; j += RT3_PAD_PRIMS) {
-                /* Stage order, RT3_GROUP primitives abreast: each packed FMA of a stage shares its ray-constant
-                 * operand with the previous one (operand-reuse cache), so only the primitive pair and the
-                 * accumulator pair come from the register file -- two registers per pipe cycle, evenly split
-                 * over both banks -- and dependent instructions sit RT3_GROUP issues apart. */
 #pragma unroll
-                for (int g = 0; g < RT3_PAD_PRIMS; g += RT3_GROUP) {
-                    float4 A[RT3_GROUP], B[RT3_GROUP];
-                    float2 h[RT3_GROUP], nq[RT3_GROUP];
+                for (int u = 0; u < RT3_PAD_PRIMS; u++) {
+                    const float4 b = blk[j + u];
 #pragma unroll
-                    for (int u = 0; u < RT3_GROUP; u++) { A[u] = blk[2 * (j + g + u)]; B[u] = blk[2 * (j + g + u) + 1]; }
-#pragma unroll
-                    for (int u = 0; u < RT3_GROUP; u++) { nq[u] = __fadd2_rn(make_float2(B[u].z, B[u].w), f.noo); }
-#pragma unroll
-                    for (int u = 0; u < RT3_GROUP; u++) { h[u] = __ffma2_rn(make_float2(B[u].x, B[u].y), f.dz, f.nod); }
-#pragma unroll
-                    for (int u = 0; u < RT3_GROUP; u++) { nq[u] = __ffma2_rn(make_float2(B[u].x, B[u].y), f.p2oz, nq[u]); }
-#pragma unroll
-                    for (int u = 0; u < RT3_GROUP; u++) { h[u] = __ffma2_rn(make_float2(A[u].z, A[u].w), f.dy, h[u]); }
-#pragma unroll
-                    for (int u = 0; u < RT3_GROUP; u++) { nq[u] = __ffma2_rn(make_float2(A[u].z, A[u].w), f.p2oy, nq[u]); }
-#pragma unroll
-                    for (int u = 0; u < RT3_GROUP; u++) { h[u] = __ffma2_rn(make_float2(A[u].x, A[u].y), f.dx, h[u]); }
-#pragma unroll
-                    for (int u = 0; u < RT3_GROUP; u++) { nq[u] = __ffma2_rn(make_float2(A[u].x, A[u].y), f.p2ox, nq[u]); }
-#pragma unroll
-                    for (int u = 0; u < RT3_GROUP; u++) { h[u] = __ffma2_rn(h[u], h[u], nq[u]); }
-#pragma unroll
-                    for (int u = 0; u < RT3_GROUP; u++) {
-                        miss0 = __funnelshift_l(__float_as_uint(h[u].x), miss0, 1);
-                        miss1 = __funnelshift_l(__float_as_uint(h[u].y), miss1, 1);
+                    for (int r = 0; r < RT3_RAYS; r++) {
+                        cand[r] = __funnelshift_l(__float_as_uint(slab_test(b, f[r])), cand[r], 1);
                     }
                 }
             }
-            /* after nb shifts bit (nb - 1 - j) belongs to primitive j; higher bits keep their initial 1 (= miss) */
-            cand[0] = live[0] ? ~miss0 : 0u;
-            cand[1] = live[1] ? ~miss1 : 0u;
+            /* after nb shifts bit (nb - 1 - j) belongs to primitive j */
+#pragma unroll
+            for (int r = 0; r < RT3_RAYS; r++) { if (!live[r]) { cand[r] = 0u; } }
         }
         bool drain = last;
 #pragma unroll
         for (int r = 0; r < RT3_RAYS; r++) { drain = drain || (n_cand[r] + (uint32_t) __popc(cand[r]) > RT3_CAND_CAP); }
         if (drain) {
-            const uint32_t nmax = n_cand[0] > n_cand[1] ? n_cand[0] : n_cand[1];
+            /* level 2 over the list, compacting the survivors in place (order preserved) */
+            uint32_t nmax = 0, n_keep[RT3_RAYS];
+#pragma unroll
+            for (int r = 0; r < RT3_RAYS; r++) { nmax = n_cand[r] > nmax ? n_cand[r] : nmax; n_keep[r] = 0; }
             for (uint32_t e = 0; e < nmax; e++) {
 #pragma unroll
                 for (int r = 0; r < RT3_RAYS; r++) {
                     if (e < n_cand[r]) {
+                        uint16_t* list = T.cand + (r * RT3_CAND_CAP) * RT3_CTA_THREADS + threadIdx.x;
+                        const uint16_t rel = list[e * RT3_CTA_THREADS];
+                        if (line_test(T.recs[rel], f[r])) { list[n_keep[r] * RT3_CTA_THREADS] = rel; n_keep[r]++; }
+                    }
+                }
+            }
+            /* exact tests of what is left, ascending primitive order */
+            nmax = 0;
+#pragma unroll
+            for (int r = 0; r < RT3_RAYS; r++) { nmax = n_keep[r] > nmax ? n_keep[r] : nmax; }
+            for (uint32_t e = 0; e < nmax; e++) {
+#pragma unroll
+                for (int r = 0; r < RT3_RAYS; r++) {
+                    if (e < n_keep[r]) {
                         exact_candidate<PATH_MODE>(S, T, T.cand[(r * RT3_CAND_CAP + e) * RT3_CTA_THREADS + threadIdx.x], o[r], d[r], best[r]);
                     }
                 }
             }
-            n_cand[0] = 0; n_cand[1] = 0;
+#pragma unroll
+            for (int r = 0; r < RT3_RAYS; r++) { n_cand[r] = 0; }
         }
         if (last) { break; }
 #pragma unroll

@@ -9,8 +9,9 @@
  *   fma_peak_kernel    : FFMA throughput probe (roofline denominator).
  *
  * Both render kernels run the same sweep: per primitive one broadcast LDS.128
- * of its prefilter sphere from shared memory and nine FP32-pipe instructions
- * per ray (rt3_device.cuh), exact tests only on the survivors.
+ * of its prefilter record from shared memory and, per ray, four FMA-pipe
+ * instructions of a conservative slab test (rt3_device.cuh); a second
+ * conservative test and the exact tests run only on the survivors.
  */
 #pragma once
 
@@ -97,10 +98,11 @@ template <bool PATH_MODE, bool RESIDENT>
 __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_smem_view& sm, uint32_t& phase,
                                             const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&d)[RT3_RAYS], const rt3_vec3 (&dn)[RT3_RAYS],
                                             const bool (&live)[RT3_RAYS], rt3_hit (&best)[RT3_RAYS]) {
-    const rt3_pair_filter f = make_pair_filter(o, dn);
+    rt3_ray_slab f[RT3_RAYS];
     uint32_t n_cand[RT3_RAYS];
 #pragma unroll
     for (int r = 0; r < RT3_RAYS; r++) {
+        f[r] = make_ray_slab(S, o[r], dn[r]);
         best[r].t = __int_as_float(0x7f800000);
         best[r].prim = RT3_NO_HIT;
         n_cand[r] = 0;
@@ -126,13 +128,13 @@ __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_s
             uint32_t first = (t + 1) * RT3_TILE_PRIMS;
             uint32_t n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
             mbar_expect_tx(&sm.bars[stage ^ 1u], n * RT3_REC_BYTES);
-            bulk_copy_g2s(sm.recs + (size_t) (stage ^ 1u) * RT3_TILE_PRIMS * 2, S.bounds + (size_t) first * 2, n * RT3_REC_BYTES,
+            bulk_copy_g2s(sm.recs + (size_t) (stage ^ 1u) * RT3_TILE_PRIMS, S.bounds + first, n * RT3_REC_BYTES,
                           &sm.bars[stage ^ 1u]);
         }
         mbar_wait(&sm.bars[stage], (phase >> stage) & 1u);
         phase ^= 1u << stage;
         const uint32_t first = t * RT3_TILE_PRIMS;
-        T.recs = sm.recs + (size_t) stage * RT3_TILE_PRIMS * 2;
+        T.recs = sm.recs + (size_t) stage * RT3_TILE_PRIMS;
         T.first_prim = first;
         T.n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
         sweep_tile<PATH_MODE>(S, T, f, o, d, live, n_cand, best);
