@@ -16,7 +16,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -68,9 +70,10 @@ struct rt3_ctx {
 
     bool has_scene = false;
     rt3_scene_view view{};
-    DeviceBuffer<float4> bounds, face_n, face_p1, face_p2, face_p3, spheres, prim_color, materials;
+    uint64_t scene_id = 0; /* identifies the uploaded scene as owner of the constant-bank records */
+    DeviceBuffer<float4> pair_xy, filt3, face_n, face_p1, face_p2, face_p3, spheres, prim_color, materials;
+    DeviceBuffer<float2> pair_w;
     DeviceBuffer<uint32_t> prim_material, prim_entity;
-    DeviceBuffer<float> prim_radius;
 
     DeviceBuffer<uint32_t> frame, aov_prim, aov_entity;
     DeviceBuffer<float> aov_t;
@@ -120,21 +123,19 @@ float round_down(double v) {
     return f;
 }
 
-/* Prefilter record (cx, cy, cz, -R^2) for a bounding sphere (double centre c, radius r >= 0).
- * R^2 = r_inflated^2 + slack |c|^2, rounded so that the record can only admit more. */
-float4 make_bound(const double c[3], double r) {
-    float4 out = make_float4(0.0f, 0.0f, 0.0f, std::numeric_limits<float>::infinity()); /* never survives */
-    if (!(std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]) && std::isfinite(r))) { return out; }
-    float cf[3] = { (float) c[0], (float) c[1], (float) c[2] };
-    double cc = (double) cf[0] * cf[0] + (double) cf[1] * cf[1] + (double) cf[2] * cf[2];
-    double clen = std::sqrt(cc);
-    /* inflate: relative 2^-10, absolute 2^-16 (|c| + r) (centre rounding, rounding of a and b, hit-point rounding of the exact tests) */
-    double re = r * (1.0 + 1.0 / 1024.0) + (clen + r) / 65536.0 + 1e-30;
-    double R2 = re * re + (double) RT3_FILTER_SLACK * cc;
-    float nR2 = round_down(-R2);
-    if (!std::isfinite(nR2)) { return out; }
-    out.x = cf[0]; out.y = cf[1]; out.z = cf[2]; out.w = nR2;
-    return out;
+/* Bounding sphere of a primitive as the prefilter sees it: centre (double) and R^2 with the
+ * per-primitive slack folded in, R^2 = r^2 + RT3_FILTER_SLACK (|c|^2 + r^2); negative R^2 marks
+ * a primitive that can never be hit (non-finite data). */
+struct Bound { double c[3]; double R2; };
+
+Bound make_bound(const double c[3], double r) {
+    Bound b = { { 0.0, 0.0, 0.0 }, -1.0 };
+    if (!(std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]) && std::isfinite(r))) { return b; }
+    const double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    const double R2 = (r * r + (double) RT3_FILTER_SLACK * (cc + r * r)) * (1.0 + 1e-6) + 1e-30;
+    if (!std::isfinite(R2) || R2 > 1e37) { return b; }
+    b.c[0] = c[0]; b.c[1] = c[1]; b.c[2] = c[2]; b.R2 = R2;
+    return b;
 }
 
 /* Jacobi eigen-decomposition of a symmetric 3x3 matrix; eigenvectors in the columns of v. */
@@ -158,26 +159,27 @@ void jacobi3(double a[3][3], double v[3][3], double w[3]) {
     for (int i = 0; i < 3; i++) { w[i] = a[i][i]; }
 }
 
-/* The axis along which the primitive centres spread least, and a unit vector perpendicular to it.
- * Primitives far larger than the typical one (a ground sphere of radius 1000) survive every slab anyway
- * and would only skew the statistics, so they are left out. */
-void thin_axis(const std::vector<float4>& recs, uint32_t n, float axis[3], float alt[3]) {
-    axis[0] = 0.f; axis[1] = 1.f; axis[2] = 0.f; alt[0] = 1.f; alt[1] = 0.f; alt[2] = 0.f;
-    std::vector<float> r2;
-    for (uint32_t i = 0; i < n; i++) { if (std::isfinite(recs[i].w)) { r2.push_back(-recs[i].w); } }
+/* Scene basis for the slab prefilter: e3 = the direction along which the primitive centres spread
+ * least (PCA), e1 = the direction of largest spread, e2 = e3 x e1; rounded to float. Primitives far
+ * larger than the typical one (a ground sphere of radius 1000) survive every slab anyway and would
+ * only skew the statistics, so they are left out. */
+void scene_basis(const std::vector<Bound>& b, float e[3][3]) {
+    const float dflt[3][3] = { { 1.f, 0.f, 0.f }, { 0.f, 0.f, -1.f }, { 0.f, 1.f, 0.f } }; /* e3 = y */
+    memcpy(e, dflt, sizeof dflt);
+    std::vector<double> r2;
+    for (const Bound& x : b) { if (x.R2 >= 0) { r2.push_back(x.R2); } }
     if (r2.size() < 2) { return; }
     std::nth_element(r2.begin(), r2.begin() + r2.size() / 2, r2.end());
-    const float r2_cap = 100.0f * r2[r2.size() / 2];
-    auto used = [&](uint32_t i) { return std::isfinite(recs[i].w) && -recs[i].w <= r2_cap; };
+    const double cap = 100.0 * r2[r2.size() / 2];
     double mean[3] = { 0, 0, 0 };
-    uint32_t cnt = 0;
-    for (uint32_t i = 0; i < n; i++) { if (used(i)) { mean[0] += recs[i].x; mean[1] += recs[i].y; mean[2] += recs[i].z; cnt++; } }
+    size_t cnt = 0;
+    for (const Bound& x : b) { if (x.R2 >= 0 && x.R2 <= cap) { for (int k = 0; k < 3; k++) { mean[k] += x.c[k]; } cnt++; } }
     if (cnt < 2) { return; }
-    for (int k = 0; k < 3; k++) { mean[k] /= cnt; }
+    for (int k = 0; k < 3; k++) { mean[k] /= (double) cnt; }
     double cov[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
-    for (uint32_t i = 0; i < n; i++) {
-        if (!used(i)) { continue; }
-        double d[3] = { recs[i].x - mean[0], recs[i].y - mean[1], recs[i].z - mean[2] };
+    for (const Bound& x : b) {
+        if (!(x.R2 >= 0 && x.R2 <= cap)) { continue; }
+        double d[3] = { x.c[0] - mean[0], x.c[1] - mean[1], x.c[2] - mean[2] };
         for (int p = 0; p < 3; p++) { for (int q = 0; q < 3; q++) { cov[p][q] += d[p] * d[q]; } }
     }
     double vec[3][3], val[3];
@@ -186,11 +188,23 @@ void thin_axis(const std::vector<float4>& recs, uint32_t n, float axis[3], float
     int lo = 0, hi = 0;
     for (int k = 1; k < 3; k++) { if (val[k] < val[lo]) { lo = k; } if (val[k] > val[hi]) { hi = k; } }
     if (lo == hi) { return; }
-    double la = 0, lb = 0;
-    for (int k = 0; k < 3; k++) { la += vec[k][lo] * vec[k][lo]; lb += vec[k][hi] * vec[k][hi]; }
+    double a3[3], a1[3], la = 0, lb = 0;
+    for (int k = 0; k < 3; k++) { a3[k] = vec[k][lo]; a1[k] = vec[k][hi]; la += a3[k] * a3[k]; lb += a1[k] * a1[k]; }
     if (!(la > 0.5 && lb > 0.5)) { return; }
-    for (int k = 0; k < 3; k++) { axis[k] = (float) (vec[k][lo] / std::sqrt(la)); alt[k] = (float) (vec[k][hi] / std::sqrt(lb)); }
+    for (int k = 0; k < 3; k++) { a3[k] /= std::sqrt(la); a1[k] /= std::sqrt(lb); }
+    /* re-orthogonalise e1 against e3 (eigenvectors of a symmetric matrix already are, up to rounding) */
+    double dp = a1[0] * a3[0] + a1[1] * a3[1] + a1[2] * a3[2], l1 = 0;
+    for (int k = 0; k < 3; k++) { a1[k] -= dp * a3[k]; l1 += a1[k] * a1[k]; }
+    if (!(l1 > 0.25)) { return; }
+    for (int k = 0; k < 3; k++) { a1[k] /= std::sqrt(l1); }
+    const double a2[3] = { a3[1] * a1[2] - a3[2] * a1[1], a3[2] * a1[0] - a3[0] * a1[2], a3[0] * a1[1] - a3[1] * a1[0] };
+    for (int k = 0; k < 3; k++) { e[0][k] = (float) a1[k]; e[1][k] = (float) a2[k]; e[2][k] = (float) a3[k]; }
 }
+
+/* Which scene owns the constant-bank records of each device (rt3_device.cuh c_pair_xy / c_pair_w). */
+std::mutex g_const_mutex;
+uint64_t g_const_owner[64] = { 0 };
+std::atomic<uint64_t> g_next_scene_id{ 1 };
 
 /* Smallest sphere through/around a triangle (double precision). */
 void triangle_bound(const double a[3], const double b[3], const double c[3], double centre[3], double* radius) {
@@ -231,8 +245,8 @@ template <class T> int upload(DeviceBuffer<T>& buf, const std::vector<T>& host, 
 }
 
 size_t render_smem_bytes(const rt3_scene_view& v, bool* resident) {
-    *resident = v.n_prims_padded <= RT3_RESIDENT_PRIMS;
-    return rt3_smem_bytes(v.n_prims_padded, *resident);
+    *resident = v.n_prims_padded <= RT3_CONST_PRIMS;
+    return rt3_smem_bytes(*resident);
 }
 
 template <class K> int configure(K kernel, size_t smem, int* blocks_per_sm) {
@@ -269,6 +283,24 @@ int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
     return RT3_OK;
 }
 
+/* Makes this context's scene the owner of the device's constant-bank records. The bank is one per
+ * device and module, so a change of owner waits for everything in flight on the device, copies the
+ * records (device to device) and waits for the copy; renders of one scene never pay this. */
+int claim_constant_bank(rt3_ctx* ctx, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (ctx->device < 0 || ctx->device >= 64) { return fail(RT3_ERR_INVALID, "device %d out of range", ctx->device); }
+    if (g_const_owner[ctx->device] == ctx->scene_id) { return RT3_OK; }
+    RT3_CUDA(cudaDeviceSynchronize());
+    const size_t pairs = ctx->view.n_prims_padded / 2;
+    if (pairs) {
+        RT3_CUDA(cudaMemcpyToSymbolAsync(c_pair_xy, ctx->pair_xy.ptr, pairs * sizeof(float4), 0, cudaMemcpyDeviceToDevice, stream));
+        RT3_CUDA(cudaMemcpyToSymbolAsync(c_pair_w, ctx->pair_w.ptr, pairs * sizeof(float2), 0, cudaMemcpyDeviceToDevice, stream));
+    }
+    RT3_CUDA(cudaStreamSynchronize(stream));
+    g_const_owner[ctx->device] = ctx->scene_id;
+    return RT3_OK;
+}
+
 /* Enqueues one render of this partition into device_frame (full-frame indexing). */
 int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params, const rt3_kparams& kp_in, uint32_t* device_frame,
                    uint32_t* prim, uint32_t* ent, float* t, cudaStream_t stream) {
@@ -281,9 +313,10 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     ctx->last_stream = stream;
     ctx->stats_pending = true;
     ctx->copy_timed = false;
+    int rc = RT3_OK;
+    if (resident && kp.n_pixels != 0 && (rc = claim_constant_bank(ctx, stream)) != RT3_OK) { return rc; }
     RT3_CUDA(cudaEventRecord(ctx->ev_begin, stream));
     RT3_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 2 * sizeof(unsigned long long), stream));
-    int rc = RT3_OK;
     if (kp.n_pixels == 0) {
         RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
         RT3_CUDA(cudaEventRecord(ctx->ev_k1, stream));
@@ -437,8 +470,8 @@ int rt3_destroy(rt3_ctx* ctx) {
     if (!ctx) { return RT3_OK; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
-    ctx->bounds.release(); ctx->face_n.release(); ctx->face_p1.release(); ctx->face_p2.release(); ctx->face_p3.release();
-    ctx->spheres.release(); ctx->prim_color.release(); ctx->materials.release(); ctx->prim_material.release(); ctx->prim_entity.release(); ctx->prim_radius.release();
+    ctx->pair_xy.release(); ctx->pair_w.release(); ctx->filt3.release(); ctx->face_n.release(); ctx->face_p1.release(); ctx->face_p2.release(); ctx->face_p3.release();
+    ctx->spheres.release(); ctx->prim_color.release(); ctx->materials.release(); ctx->prim_material.release(); ctx->prim_entity.release();
     ctx->frame.release(); ctx->aov_prim.release(); ctx->aov_entity.release(); ctx->aov_t.release(); ctx->accum.release(); ctx->counters.release();
     if (ctx->ev_begin) { cudaEventDestroy(ctx->ev_begin); }
     if (ctx->ev_end) { cudaEventDestroy(ctx->ev_end); }
@@ -461,11 +494,9 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
 
     const uint32_t nf = s->n_faces, ns = s->n_spheres, np = nf + ns;
     const uint32_t np_pad = (np + RT3_PAD_PRIMS - 1) / RT3_PAD_PRIMS * RT3_PAD_PRIMS;
-    const float inf = std::numeric_limits<float>::infinity();
-    std::vector<float4> bounds(np_pad, make_float4(0.f, 0.f, 0.f, inf)); /* never survives: a^2 + inf > 0 */
+    std::vector<Bound> bounds(np);
     std::vector<float4> fn(nf), p1(nf), p2(nf), p3(nf), sph(ns), color(np), mats((size_t) s->n_materials * 2);
     std::vector<uint32_t> pmat(np, RT3_NO_HIT), pent(np, 0u);
-    std::vector<float> prad(np_pad, 0.0f);
 
     for (uint32_t i = 0; i < nf; i++) {
         const rt3_face& f = s->faces[i];
@@ -484,6 +515,9 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
         p3[i] = make_float4(c.x, c.y, c.z, 0.f);
         double da[3] = { a.x, a.y, a.z }, db[3] = { b.x, b.y, b.z }, dc[3] = { c.x, c.y, c.z }, centre[3], radius;
         triangle_bound(da, db, dc, centre, &radius);
+        /* faces: the exact test accepts hit points up to a few ulps of the coordinates outside the triangle;
+         * widen the bounding sphere by 2^-10 relative and 2^-16 (|c| + r) absolute on top of the common slack */
+        radius = radius * (1.0 + 1.0 / 1024.0) + (std::sqrt(centre[0] * centre[0] + centre[1] * centre[1] + centre[2] * centre[2]) + radius) / 65536.0;
         bounds[i] = make_bound(centre, radius);
         color[i] = make_float4(f.color[0], f.color[1], f.color[2], 0.f);
         if (s->face_material) {
@@ -495,7 +529,6 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     for (uint32_t i = 0; i < ns; i++) {
         const rt3_sphere& sp = s->spheres[i];
         sph[i] = make_float4(sp.cx, sp.cy, sp.cz, sp.r);
-        prad[nf + i] = sp.r;
         double c[3] = { sp.cx, sp.cy, sp.cz };
         bounds[nf + i] = make_bound(c, std::fabs((double) sp.r));
         if (s->sphere_color) { color[nf + i] = make_float4(s->sphere_color[3 * i], s->sphere_color[3 * i + 1], s->sphere_color[3 * i + 2], 0.f); }
@@ -515,26 +548,46 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
         mats[2 * i + 1] = make_float4(m.fuzz, m.ior, 0.f, 0.f);
     }
 
-    float axis[3], axis_alt[3], ray_slack;
-    thin_axis(bounds, np, axis, axis_alt);
+    /* prefilter records in the scene basis */
+    float basis[3][3];
+    scene_basis(bounds, basis);
+    double r2min = 1.0;
     {
-        /* smallest R^2 in the scene, floored at 1/400 of the median so that one sliver cannot inflate every slab */
-        std::vector<float> r2;
-        for (uint32_t i = 0; i < np; i++) { if (std::isfinite(bounds[i].w)) { r2.push_back(-bounds[i].w); } }
-        float r2min = 1.0f;
+        /* smallest R^2 in the scene, floored at 1/400 of the median so that one sliver cannot widen every slab;
+         * records below the floor are raised to it (admits more, never less) */
+        std::vector<double> r2;
+        for (const Bound& b : bounds) { if (b.R2 >= 0) { r2.push_back(b.R2); } }
         if (!r2.empty()) {
             std::nth_element(r2.begin(), r2.begin() + r2.size() / 2, r2.end());
-            float median = r2[r2.size() / 2], lowest = *std::min_element(r2.begin(), r2.end());
-            r2min = std::max(lowest, median / 400.0f);
-            if (!(r2min > 0.0f)) { r2min = 1e-30f; }
-            /* records below the floor are raised to it (admits more, never less) */
-            for (uint32_t i = 0; i < np; i++) { if (std::isfinite(bounds[i].w) && -bounds[i].w < r2min) { bounds[i].w = -r2min; } }
+            const double median = r2[r2.size() / 2], lowest = *std::min_element(r2.begin(), r2.end());
+            r2min = std::max(lowest, median / 400.0);
+            if (!(r2min > 0.0)) { r2min = 1e-30; }
         }
-        ray_slack = RT3_FILTER_SLACK / r2min;
+    }
+    const float ray_slack = (float) ((double) RT3_FILTER_SLACK / r2min * (1.0 + 1e-6));
+    const float inf = std::numeric_limits<float>::infinity();
+    std::vector<float4> filt3(np_pad, make_float4(0.f, 0.f, 0.f, inf)); /* never survives: a^2 + inf > 0 */
+    for (uint32_t i = 0; i < np; i++) {
+        const Bound& b = bounds[i];
+        if (b.R2 < 0) { continue; }
+        float p[3];
+        for (int k = 0; k < 3; k++) { p[k] = (float) (b.c[0] * (double) basis[k][0] + b.c[1] * (double) basis[k][1] + b.c[2] * (double) basis[k][2]); }
+        const float w = round_down(-std::max(b.R2, r2min));
+        if (!std::isfinite(w) || !std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) { continue; }
+        filt3[i] = make_float4(p[0], p[1], p[2], w);
+    }
+    std::vector<float4> pair_xy(np_pad / 2);
+    std::vector<float2> pair_w(np_pad / 2);
+    for (uint32_t j = 0; j < np_pad / 2; j++) {
+        const float4 &a = filt3[2 * j], &b = filt3[2 * j + 1];
+        pair_xy[j] = make_float4(a.x, b.x, a.y, b.y);
+        pair_w[j] = make_float2(a.w, b.w);
     }
 
     int rc;
-    if ((rc = upload(ctx->bounds, bounds, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->pair_xy, pair_xy, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->pair_w, pair_w, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->filt3, filt3, ctx->stream)) != RT3_OK) { return rc; }
     if ((rc = upload(ctx->face_n, fn, ctx->stream)) != RT3_OK) { return rc; }
     if ((rc = upload(ctx->face_p1, p1, ctx->stream)) != RT3_OK) { return rc; }
     if ((rc = upload(ctx->face_p2, p2, ctx->stream)) != RT3_OK) { return rc; }
@@ -544,17 +597,17 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     if ((rc = upload(ctx->materials, mats, ctx->stream)) != RT3_OK) { return rc; }
     if ((rc = upload(ctx->prim_material, pmat, ctx->stream)) != RT3_OK) { return rc; }
     if ((rc = upload(ctx->prim_entity, pent, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->prim_radius, prad, ctx->stream)) != RT3_OK) { return rc; }
     RT3_CUDA(cudaStreamSynchronize(ctx->stream)); /* host vectors go out of scope */
 
     rt3_scene_view& v = ctx->view;
-    for (int k = 0; k < 3; k++) { v.axis[k] = axis[k]; v.axis_alt[k] = axis_alt[k]; }
+    for (int k = 0; k < 3; k++) { v.e1[k] = basis[0][k]; v.e2[k] = basis[1][k]; v.e3[k] = basis[2][k]; }
     v.ray_slack = ray_slack;
+    ctx->scene_id = g_next_scene_id.fetch_add(1);
     v.n_faces = nf; v.n_spheres = ns; v.n_prims = np; v.n_prims_padded = np_pad;
-    v.bounds = ctx->bounds.ptr;
+    v.pair_xy = ctx->pair_xy.ptr; v.pair_w = ctx->pair_w.ptr; v.filt3 = ctx->filt3.ptr;
     v.face_n = ctx->face_n.ptr; v.face_p1 = ctx->face_p1.ptr; v.face_p2 = ctx->face_p2.ptr; v.face_p3 = ctx->face_p3.ptr;
     v.spheres = ctx->spheres.ptr; v.prim_color = ctx->prim_color.ptr;
-    v.prim_material = ctx->prim_material.ptr; v.prim_entity = ctx->prim_entity.ptr; v.prim_radius = ctx->prim_radius.ptr; v.materials = ctx->materials.ptr;
+    v.prim_material = ctx->prim_material.ptr; v.prim_entity = ctx->prim_entity.ptr; v.materials = ctx->materials.ptr;
     ctx->has_scene = true;
     return RT3_OK;
 }

@@ -22,21 +22,21 @@
 #define RT3_ACC_SCALE 16777216.0f
 
 #define RT3_RAYS 2              /* rays (path slots) per thread */
-#define RT3_BLOCK_PRIMS 32      /* primitives per candidate-mask block */
-#define RT3_PAD_PRIMS 8         /* the primitive array is padded to a multiple of this with never-hit records */
-#define RT3_REC_BYTES 16        /* prefilter record: (cx, cy, cz, -R^2) */
-#define RT3_TILE_PRIMS 2048     /* primitives per streamed shared-memory tile (32 KB) */
-#define RT3_RESIDENT_PRIMS 4096 /* scenes up to this size live in shared memory for the whole kernel (64 KB) */
+#define RT3_WORD_PRIMS 32       /* primitives per survivor-mask word; the primitive array is padded to a multiple of this */
+#define RT3_PAD_PRIMS RT3_WORD_PRIMS
+#define RT3_CHUNK_WORDS 16      /* mask words swept before the survivors are drained (512 primitives) */
+#define RT3_CONST_PRIMS 4096    /* scenes up to this size are swept out of the constant bank (48 KB of records) */
+#define RT3_TILE_PRIMS 1024     /* larger scenes: primitives per streamed shared-memory tile (12 KB per stage) */
 #define RT3_CTA_THREADS 128
 #define RT3_CTAS_PER_SM 5       /* register budget: 65536 / (128 * 5) = 102 per thread */
 #define RT3_ITEM_CHUNK 1024u    /* path items a warp claims per global atomic */
-#define RT3_CAND_CAP 32         /* per-ray deferred-candidate list entries (shared memory, 16-bit tile-relative ids) */
 
-/* Relative slack of the prefilter (64 ulp of binary32), applied to |c|^2 per
- * primitive (host, folded into R^2) and to |o|^2 per ray (folded into the
- * scale of the slab basis). It covers the rounding of the prefilter's own FMA
- * chains plus that of the exact sphere test it stands in front of, which is
- * bounded by ~14 eps |c - o|^2 <= 28 eps (|c|^2 + |o|^2). */
+/* Relative slack of the prefilter (64 units of 2^-24), applied to |c|^2 + r^2
+ * per primitive (host, folded into R^2) and to |o|^2 per ray (folded into the
+ * scale of the slab direction). It covers the rounding of the prefilter's own
+ * FMA chain (a few 2^-24 (|c| + |o|) on a) plus that of the exact tests it
+ * stands in front of -- the exact sphere discriminant is off by up to
+ * ~15 2^-24 |c - o|^2 -- see DESIGN.md section 3.1 for the bound. */
 #define RT3_FILTER_SLACK 3.814697265625e-06f
 
 struct rt3_vec3 { float x, y, z; };
@@ -75,8 +75,12 @@ struct rt3_scene_view {
     uint32_t n_faces;
     uint32_t n_spheres;
     uint32_t n_prims;        /* n_faces + n_spheres; primitive id = face index, then n_faces + sphere index */
-    uint32_t n_prims_padded; /* rounded up to RT3_PAD_PRIMS with never-hit records */
-    const float4* bounds;    /* per primitive: (cx, cy, cz, -R^2), R = inflated bounding radius (R^2 includes the per-primitive slack) */
+    uint32_t n_prims_padded; /* rounded up to RT3_WORD_PRIMS with never-surviving records */
+    /* Prefilter records in the scene basis (e1, e2, e3): p_k = c . e_k for the bounding-sphere centre c,
+     * w = -R^2 (inflated radius, per-primitive slack included). */
+    const float4* pair_xy;   /* per primitive PAIR (2j, 2j+1): (p1a, p1b, p2a, p2b) */
+    const float2* pair_w;    /* per primitive pair: (wa, wb) */
+    const float4* filt3;     /* per primitive: (p1, p2, p3, w), level 2 */
     const float4* face_n;    /* per face: (nx, ny, nz, dot3(n, p1)) */
     const float4* face_p1;   /* per face: p1.xyz */
     const float4* face_p2;
@@ -85,53 +89,64 @@ struct rt3_scene_view {
     const float4* prim_color;     /* per primitive: flat colour / albedo */
     const uint32_t* prim_material; /* per primitive: index into materials, or RT3_NO_HIT for Lambertian(prim_color) */
     const uint32_t* prim_entity;
-    const float* prim_radius; /* per primitive (padded): sphere radius, 0 for faces */
-    float axis[3];            /* unit vector along which the scene is thinnest (PCA of the primitive centres) */
-    float axis_alt[3];        /* a unit vector perpendicular to axis */
-    float ray_slack;          /* RT3_FILTER_SLACK / min R^2: per-ray inflation of the slab is 1 + ray_slack |o|^2 */
+    float e1[3], e2[3], e3[3]; /* scene basis: e3 is the direction along which the primitive centres spread least */
+    float ray_slack;           /* RT3_FILTER_SLACK / min R^2: the slab of a ray at o is widened by 1 + ray_slack |o|^2 */
     const float4* materials; /* 2 float4 per material: (kind bits, albedo rgb), (fuzz, ior, -, -) */
 };
 
 struct rt3_hit { float t; uint32_t prim; };
 
-/* Two-level conservative prefilter in a per-ray orthonormal basis (u, v) of the
- * plane perpendicular to the unit direction dn. With a = (c - o).u and
- * b = (c - o).v the distance of a centre c from the ray's line is
- * sqrt(a^2 + b^2), so
- *   level 1 (every primitive, 4 FMA):   a^2     - R^2 < 0   (the slab |a| < R)
- *   level 2 (level-1 survivors, 8 FMA): a^2+b^2 - R^2 < 0   (the line meets the bounding sphere)
- * are both necessary for any hit. u is chosen perpendicular to the scene's
- * thinnest axis, so the slab (a plane through the ray containing that axis)
- * cuts across the scene's long extent and few primitives survive level 1.
- * The per-ray slack (oracle rounding ~ eps |c-o|^2) is folded into the basis:
- * u and v are scaled by s = 1/sqrt(1 + ray_slack |o|^2) <= 1, which inflates
- * every R^2 by at least RT3_FILTER_SLACK |o|^2 at no per-test cost. */
-struct rt3_ray_slab { float ux, uy, uz, nou, vx, vy, vz, nov; };
+/* Two-level conservative prefilter.
+ *
+ * Every primitive has a bounding sphere (c, R). In the scene basis (e1, e2, e3)
+ * let u be the unit vector of the (e1, e2) plane perpendicular to the ray
+ * direction dn: u = (-g2, g1) / |(g1, g2)| with g_k = dn . e_k. u is
+ * perpendicular to dn, so with a = (c - o) . u the distance of c from the ray's
+ * line is at least |a|, and
+ *   level 1 (every primitive):    a^2 - R^2 < 0        -- the slab |a| < R
+ * is necessary for a hit. Because u has no e3 component, a needs only the two
+ * in-plane coordinates of c: a = p1 u1 + p2 u2 - o.u, two FMAs, and one more for
+ * a^2 - R^2. The slab is the plane through the ray that contains e3, the
+ * direction along which the scene is thinnest, so it cuts across the scene's
+ * long extent and few primitives survive.
+ *   level 2 (faces that survive): a^2 + b^2 - R^2 < 0, b = (c - o) . (dn x u)
+ * is the full line / bounding-sphere test; spheres go straight to their exact
+ * test, which starts with the same discriminant.
+ * The per-ray slack is folded into the scale of u: |u| = 1/sqrt(1 + ray_slack |o|^2),
+ * which widens every R^2 by at least RT3_FILTER_SLACK |o|^2 at no per-test cost. */
+struct rt3_ray_filter {
+    float u1, u2, nou;   /* level 1 */
+    float g1, g2, g3;    /* dn in the scene basis (level 2 builds v = dn x u from it) */
+    float o1, o2, o3;    /* o in the scene basis */
+};
 
-__device__ __forceinline__ rt3_ray_slab make_ray_slab(const rt3_scene_view& S, rt3_vec3 o, rt3_vec3 dn) {
-    rt3_vec3 u = cross3(dn, v3(S.axis[0], S.axis[1], S.axis[2]));
-    float uu = dot3(u, u);
-    if (!(uu >= 0.01f)) { u = cross3(dn, v3(S.axis_alt[0], S.axis_alt[1], S.axis_alt[2])); uu = dot3(u, u); }
-    const float scale = 1.0f / sqrtf(uu * (1.0f + S.ray_slack * dot3(o, o)));
-    u = scale * u;
-    const rt3_vec3 v = cross3(dn, u); /* |v| = |u| (dn is unit and perpendicular to u) */
-    rt3_ray_slab f;
-    f.ux = u.x; f.uy = u.y; f.uz = u.z; f.nou = -dot3(o, u);
-    f.vx = v.x; f.vy = v.y; f.vz = v.z; f.nov = -dot3(o, v);
+__device__ __forceinline__ rt3_ray_filter make_ray_filter(const rt3_scene_view& S, rt3_vec3 o, rt3_vec3 dn) {
+    const rt3_vec3 e1 = v3(S.e1[0], S.e1[1], S.e1[2]), e2 = v3(S.e2[0], S.e2[1], S.e2[2]), e3 = v3(S.e3[0], S.e3[1], S.e3[2]);
+    rt3_ray_filter f;
+    f.g1 = dot3(dn, e1); f.g2 = dot3(dn, e2); f.g3 = dot3(dn, e3);
+    f.o1 = dot3(o, e1); f.o2 = dot3(o, e2); f.o3 = dot3(o, e3);
+    const float s2 = f.g1 * f.g1 + f.g2 * f.g2;
+    const float widen = 1.0f + S.ray_slack * ((f.o1 * f.o1 + f.o2 * f.o2) + f.o3 * f.o3);
+    if (s2 > 1e-30f) {
+        const float inv = 1.0f / sqrtf(s2 * widen);
+        f.u1 = -f.g2 * inv; f.u2 = f.g1 * inv;
+    } else {
+        /* dn is along e3: every in-plane direction is perpendicular to it */
+        f.u1 = 1.0f / sqrtf(widen); f.u2 = 0.0f;
+    }
+    f.nou = -(f.o1 * f.u1 + f.o2 * f.u2);
+    if (!(f.nou == f.nou) || !(f.u1 == f.u1) || !(f.u2 == f.u2)) { f.u1 = 0.0f; f.u2 = 0.0f; f.nou = 0.0f; } /* degenerate ray: keep everything */
     return f;
 }
 
-/* Level 1: sign bit set <=> the primitive survives (|a| < R). Four FMA-pipe instructions. */
-__device__ __forceinline__ float slab_test(const float4 b, const rt3_ray_slab& f) {
-    const float a = __fmaf_rn(b.x, f.ux, __fmaf_rn(b.y, f.uy, __fmaf_rn(b.z, f.uz, f.nou)));
-    return __fmaf_rn(a, a, b.w);
-}
-
-/* Level 2: true <=> the ray's line may meet the primitive's bounding sphere. */
-__device__ __forceinline__ bool line_test(const float4 b, const rt3_ray_slab& f) {
-    const float a = __fmaf_rn(b.x, f.ux, __fmaf_rn(b.y, f.uy, __fmaf_rn(b.z, f.uz, f.nou)));
-    const float c = __fmaf_rn(b.x, f.vx, __fmaf_rn(b.y, f.vy, __fmaf_rn(b.z, f.vz, f.nov)));
-    const float d2 = __fmaf_rn(c, c, __fmaf_rn(a, a, b.w));
+/* Level 2: true <=> the ray's line may meet the bounding sphere of `rec` = (p1, p2, p3, -R^2). */
+__device__ __forceinline__ bool line_test(const float4 rec, const rt3_ray_filter& f) {
+    /* v = dn x u in basis coordinates; u = (u1, u2, 0) */
+    const float v1 = -f.g3 * f.u2, v2 = f.g3 * f.u1, v3c = f.g1 * f.u2 - f.g2 * f.u1;
+    const float nov = -((f.o1 * v1 + f.o2 * v2) + f.o3 * v3c);
+    const float a = __fmaf_rn(rec.x, f.u1, __fmaf_rn(rec.y, f.u2, f.nou));
+    const float b = __fmaf_rn(rec.x, v1, __fmaf_rn(rec.y, v2, __fmaf_rn(rec.z, v3c, nov)));
+    const float d2 = __fmaf_rn(b, b, __fmaf_rn(a, a, rec.w));
     return !(d2 > 0.0f);
 }
 
@@ -186,123 +201,103 @@ __device__ __forceinline__ void exact_sphere_path(const rt3_scene_view& S, uint3
     best.prim = S.n_faces + si; best.t = t;
 }
 
-/* Exact test of one candidate primitive. `sp` is the sphere record (centre,
- * radius) when the primitive is a sphere; the caller fetches it from shared
- * memory when the scene is resident, from global memory otherwise. */
-template <bool PATH_MODE>
-__device__ __forceinline__ void exact_prim(const rt3_scene_view& S, uint32_t prim, float4 sp, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
-    if (prim < S.n_faces) {
-        exact_face(S, prim, o, d, PATH_MODE ? RT3_TMIN : 0.0f, best);
-    } else if (prim < S.n_prims) {
-        if (PATH_MODE) { exact_sphere_path(S, prim - S.n_faces, sp, o, d, best); }
-        else { exact_sphere_v4(S, prim - S.n_faces, sp, o, d, best); }
+/* Records of scenes up to RT3_CONST_PRIMS live in the constant bank: the sweep
+ * reads them through uniform registers (SASS LDCU), so the packed FMAs take the
+ * primitive operand from the uniform datapath and only the ray's constants and
+ * the accumulator from the vector register file. The host copies a context's
+ * records here before a launch when another scene owned the bank (rt3_core.cu). */
+__constant__ float4 c_pair_xy[RT3_CONST_PRIMS / 2];
+__constant__ float2 c_pair_w[RT3_CONST_PRIMS / 2];
+
+/* Per-thread survivor masks of the chunk being swept: [RT3_RAYS][RT3_CHUNK_WORDS][RT3_CTA_THREADS] words. */
+#define RT3_MASK_BYTES (RT3_RAYS * RT3_CHUNK_WORDS * RT3_CTA_THREADS * 4)
+
+/* Level 1 over `n_words` mask words (32 primitives each) starting at pair index
+ * `first_pair` of `xy` / `w` (constant bank or a shared-memory tile).
+ * Per primitive pair and ray: three packed FMAs (fma.rn.f32x2, SASS FFMA2: both
+ * primitives of the pair at once) and two funnel shifts that push the sign bits
+ * of a^2 - R^2 into the ray's mask word. Bit 31 - k of a word belongs to its
+ * k-th primitive. Words go to shared memory; `nz` gets one bit per non-empty word. */
+template <bool CONST_BANK>
+__device__ __forceinline__ void sweep_chunk(const float4* __restrict__ xy, const float2* __restrict__ w, uint32_t first_pair, uint32_t n_words,
+                                            const rt3_ray_filter (&f)[RT3_RAYS], uint32_t* __restrict__ masks, uint32_t (&nz)[RT3_RAYS]) {
+    float2 nou2[RT3_RAYS], u1[RT3_RAYS], u2[RT3_RAYS];
+#pragma unroll
+    for (int r = 0; r < RT3_RAYS; r++) {
+        nou2[r] = make_float2(f[r].nou, f[r].nou); u1[r] = make_float2(f[r].u1, f[r].u1); u2[r] = make_float2(f[r].u2, f[r].u2);
+        nz[r] = 0u;
     }
-}
-
-/* Where the sweep finds its data: the prefilter tile in shared memory, the
- * per-primitive radii (shared memory for resident scenes, else NULL) and the
- * per-thread deferred-candidate lists. */
-struct rt3_tile_view {
-    const float4* recs;     /* shared: prefilter records of this tile */
-    const float* radius;    /* shared: sphere radii of this tile, or NULL (fetch S.spheres from global) */
-    uint16_t* cand;         /* shared: [RT3_RAYS][RT3_CAND_CAP][RT3_CTA_THREADS] tile-relative candidate ids */
-    uint32_t first_prim;    /* global id of the tile's first primitive */
-    uint32_t n;             /* primitives in this tile (multiple of RT3_PAD_PRIMS) */
-};
-
-/* Exact test of one level-2 survivor. */
-template <bool PATH_MODE>
-__device__ __forceinline__ void exact_candidate(const rt3_scene_view& S, const rt3_tile_view& T, uint32_t rel, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
-    const uint32_t prim = T.first_prim + rel;
-    float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (prim >= S.n_faces && prim < S.n_prims) {
-        /* the prefilter centre of a sphere is its own centre */
-        if (T.radius) { const float4 rec = T.recs[rel]; sp = make_float4(rec.x, rec.y, rec.z, T.radius[rel]); }
-        else { sp = __ldg(&S.spheres[prim - S.n_faces]); }
-    }
-    exact_prim<PATH_MODE>(S, prim, sp, o, d, best);
-}
-
-/* Closest hit of the thread's rays against one shared-memory tile.
- *
- * Per block of 32 primitives and per ray: one broadcast LDS.128 per primitive
- * (shared by the rays), four FMA-pipe instructions (level 1) and one funnel
- * shift that collects the sign bit into a 32-primitive survivor mask.
- * Survivors go to the ray's deferred list in ascending primitive order; the
- * list is drained once per tile (or earlier if it would overflow) from a single
- * call site: level 2, then the exact test, still in ascending order -- so the
- * strict `t < best` rule keeps the lowest index on ties exactly like the
- * reference loop (SequentialRenderer.cpp:71). */
-template <bool PATH_MODE>
-__device__ __forceinline__ void sweep_tile(const rt3_scene_view& S, const rt3_tile_view& T, const rt3_ray_slab (&f)[RT3_RAYS],
-                                           const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&d)[RT3_RAYS], const bool (&live)[RT3_RAYS],
-                                           uint32_t (&n_cand)[RT3_RAYS], rt3_hit (&best)[RT3_RAYS]) {
-    for (uint32_t base = 0;; base += RT3_BLOCK_PRIMS) {
-        const bool last = base >= T.n;
-        uint32_t cand[RT3_RAYS];
+    for (uint32_t wd = 0; wd < n_words; wd++) {
+        uint32_t m[RT3_RAYS];
 #pragma unroll
-        for (int r = 0; r < RT3_RAYS; r++) { cand[r] = 0u; }
-        uint32_t nb = 0;
-        if (!last) {
-            nb = T.n - base < RT3_BLOCK_PRIMS ? T.n - base : RT3_BLOCK_PRIMS;
-            const float4* __restrict__ blk = T.recs + base;
-            for (uint32_t j = 0; j < nb; j += RT3_PAD_PRIMS) {
+        for (int r = 0; r < RT3_RAYS; r++) { m[r] = 0u; }
+        const uint32_t base = first_pair + wd * (RT3_WORD_PRIMS / 2);
 #pragma unroll
-                for (int u = 0; u < RT3_PAD_PRIMS; u++) {
-                    const float4 b = blk[j + u];
+        for (int j = 0; j < RT3_WORD_PRIMS / 2; j++) {
+            const float4 A = CONST_BANK ? c_pair_xy[base + j] : xy[base + j];
+            const float2 B = CONST_BANK ? c_pair_w[base + j] : w[base + j];
 #pragma unroll
-                    for (int r = 0; r < RT3_RAYS; r++) {
-                        cand[r] = __funnelshift_l(__float_as_uint(slab_test(b, f[r])), cand[r], 1);
-                    }
-                }
+            for (int r = 0; r < RT3_RAYS; r++) {
+                const float2 a = __ffma2_rn(make_float2(A.x, A.y), u1[r], __ffma2_rn(make_float2(A.z, A.w), u2[r], nou2[r]));
+                const float2 d = __ffma2_rn(a, a, B);
+                m[r] = __funnelshift_l(__float_as_uint(d.x), m[r], 1);
+                m[r] = __funnelshift_l(__float_as_uint(d.y), m[r], 1);
             }
-            /* after nb shifts bit (nb - 1 - j) belongs to primitive j */
-#pragma unroll
-            for (int r = 0; r < RT3_RAYS; r++) { if (!live[r]) { cand[r] = 0u; } }
         }
-        bool drain = last;
-#pragma unroll
-        for (int r = 0; r < RT3_RAYS; r++) { drain = drain || (n_cand[r] + (uint32_t) __popc(cand[r]) > RT3_CAND_CAP); }
-        if (drain) {
-            /* level 2 over the list, compacting the survivors in place (order preserved) */
-            uint32_t nmax = 0, n_keep[RT3_RAYS];
-#pragma unroll
-            for (int r = 0; r < RT3_RAYS; r++) { nmax = n_cand[r] > nmax ? n_cand[r] : nmax; n_keep[r] = 0; }
-            for (uint32_t e = 0; e < nmax; e++) {
-#pragma unroll
-                for (int r = 0; r < RT3_RAYS; r++) {
-                    if (e < n_cand[r]) {
-                        uint16_t* list = T.cand + (r * RT3_CAND_CAP) * RT3_CTA_THREADS + threadIdx.x;
-                        const uint16_t rel = list[e * RT3_CTA_THREADS];
-                        if (line_test(T.recs[rel], f[r])) { list[n_keep[r] * RT3_CTA_THREADS] = rel; n_keep[r]++; }
-                    }
-                }
-            }
-            /* exact tests of what is left, ascending primitive order */
-            nmax = 0;
-#pragma unroll
-            for (int r = 0; r < RT3_RAYS; r++) { nmax = n_keep[r] > nmax ? n_keep[r] : nmax; }
-            for (uint32_t e = 0; e < nmax; e++) {
-#pragma unroll
-                for (int r = 0; r < RT3_RAYS; r++) {
-                    if (e < n_keep[r]) {
-                        exact_candidate<PATH_MODE>(S, T, T.cand[(r * RT3_CAND_CAP + e) * RT3_CTA_THREADS + threadIdx.x], o[r], d[r], best[r]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < RT3_RAYS; r++) { n_cand[r] = 0; }
-        }
-        if (last) { break; }
 #pragma unroll
         for (int r = 0; r < RT3_RAYS; r++) {
-            uint32_t c = cand[r];
-            while (c) {
-                const uint32_t bit = 31u - (uint32_t) __clz(c);
-                c &= ~(1u << bit);
-                T.cand[(r * RT3_CAND_CAP + n_cand[r]) * RT3_CTA_THREADS + threadIdx.x] = (uint16_t) (base + (nb - 1u - bit));
-                n_cand[r]++;
-            }
+            masks[(r * RT3_CHUNK_WORDS + wd) * RT3_CTA_THREADS + threadIdx.x] = m[r];
+            nz[r] |= (m[r] != 0u ? 1u : 0u) << wd;
+        }
+    }
+}
+
+/* Exact tests of one ray's level-1 survivors of a chunk, in ascending primitive
+ * order (words ascending, bits from the top), so the strict `t < best` rule
+ * keeps the lowest index on ties exactly like the reference loop
+ * (SequentialRenderer.cpp:71). Every lane walks its own survivor list. */
+template <bool PATH_MODE>
+__device__ __forceinline__ void drain_chunk(const rt3_scene_view& S, uint32_t first_prim, const rt3_ray_filter& f, rt3_vec3 o, rt3_vec3 d,
+                                            const uint32_t* __restrict__ masks, uint32_t nz, rt3_hit& best) {
+    uint32_t m = 0u, word_prim = 0u;
+    for (;;) {
+        if (m == 0u) {
+            if (nz == 0u) { break; }
+            const uint32_t wd = (uint32_t) __ffs((int) nz) - 1u;
+            nz &= nz - 1u;
+            m = masks[wd * RT3_CTA_THREADS + threadIdx.x];
+            word_prim = first_prim + wd * RT3_WORD_PRIMS;
+        }
+        const uint32_t k = (uint32_t) __clz((int) m);
+        m &= ~(0x80000000u >> k);
+        const uint32_t prim = word_prim + k;
+        if (prim < S.n_faces) {
+            if (line_test(__ldg(&S.filt3[prim]), f)) { exact_face(S, prim, o, d, PATH_MODE ? RT3_TMIN : 0.0f, best); }
+        } else if (prim < S.n_prims) {
+            const float4 sp = __ldg(&S.spheres[prim - S.n_faces]);
+            if (PATH_MODE) { exact_sphere_path(S, prim - S.n_faces, sp, o, d, best); }
+            else { exact_sphere_v4(S, prim - S.n_faces, sp, o, d, best); }
+        }
+    }
+}
+
+/* Closest hit of the thread's rays against `n_prims` primitives (a multiple of
+ * 32) whose records start at pair index `first_pair`; `first_prim` is the
+ * global id of the first one. */
+template <bool PATH_MODE, bool CONST_BANK>
+__device__ __forceinline__ void sweep_range(const rt3_scene_view& S, const float4* __restrict__ xy, const float2* __restrict__ w, uint32_t first_pair,
+                                            uint32_t first_prim, uint32_t n_prims, const rt3_ray_filter (&f)[RT3_RAYS],
+                                            const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&d)[RT3_RAYS], const bool (&live)[RT3_RAYS],
+                                            uint32_t* __restrict__ masks, rt3_hit (&best)[RT3_RAYS]) {
+    const uint32_t n_words = n_prims / RT3_WORD_PRIMS;
+    for (uint32_t w0 = 0; w0 < n_words; w0 += RT3_CHUNK_WORDS) {
+        const uint32_t nw = n_words - w0 < RT3_CHUNK_WORDS ? n_words - w0 : RT3_CHUNK_WORDS;
+        uint32_t nz[RT3_RAYS];
+        sweep_chunk<CONST_BANK>(xy, w, first_pair + w0 * (RT3_WORD_PRIMS / 2), nw, f, masks, nz);
+#pragma unroll
+        for (int r = 0; r < RT3_RAYS; r++) {
+            if (!live[r]) { nz[r] = 0u; }
+            drain_chunk<PATH_MODE>(S, first_prim + w0 * RT3_WORD_PRIMS, f[r], o[r], d[r], masks + r * RT3_CHUNK_WORDS * RT3_CTA_THREADS, nz[r], best[r]);
         }
     }
 }

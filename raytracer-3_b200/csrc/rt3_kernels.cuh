@@ -8,10 +8,11 @@
  *   pack/unpack kernels: frame <-> partition slab for the frame-end gather.
  *   fma_peak_kernel    : FFMA throughput probe (roofline denominator).
  *
- * Both render kernels run the same sweep: per primitive one broadcast LDS.128
- * of its prefilter record from shared memory and, per ray, four FMA-pipe
- * instructions of a conservative slab test (rt3_device.cuh); a second
- * conservative test and the exact tests run only on the survivors.
+ * Both render kernels run the same sweep (rt3_device.cuh): per primitive pair
+ * and ray three packed FMAs of a conservative slab test, the records coming
+ * from the constant bank through uniform registers (scenes up to
+ * RT3_CONST_PRIMS) or from TMA-streamed shared-memory tiles; the exact tests
+ * run only on the survivors.
  */
 #pragma once
 
@@ -33,111 +34,90 @@ __device__ __forceinline__ uint32_t owned_row_to_global(const rt3_kparams& P, ui
     return (lt * P.part_count + P.part_index) * P.tile_rows + within;
 }
 
-/* Shared-memory layout: [mbarriers (64 B)] [prefilter records] [radii (resident only)] [candidate lists]. */
+/* Shared-memory layout.
+ *   resident (constant-bank) scenes: [survivor masks]
+ *   streamed scenes:                 [mbarriers (64 B)] [2 stages x (pair_xy tile, pair_w tile)] [survivor masks] */
 struct rt3_smem_view {
-    uint64_t* bars;  /* one "tile landed" mbarrier per stage */
-    float4* recs;    /* resident: n_prims_padded records; streamed: 2 stages of RT3_TILE_PRIMS */
-    float* radius;   /* resident: n_prims_padded radii; streamed: NULL */
-    uint16_t* cand;  /* RT3_RAYS * RT3_CAND_CAP * RT3_CTA_THREADS deferred candidate ids */
+    uint64_t* bars;   /* streamed: one "tile landed" mbarrier per stage */
+    float4* tile_xy;  /* streamed: 2 stages of RT3_TILE_PRIMS / 2 pair records */
+    float2* tile_w;
+    uint32_t* masks;  /* RT3_RAYS * RT3_CHUNK_WORDS * RT3_CTA_THREADS words */
 };
 
-__host__ __device__ inline size_t rt3_smem_rec_bytes(uint32_t n_prims_padded, bool resident) {
-    size_t n = resident ? (size_t) n_prims_padded : (size_t) 2 * RT3_TILE_PRIMS;
-    return (n ? n : 1) * RT3_REC_BYTES;
-}
-__host__ __device__ inline size_t rt3_smem_radius_bytes(uint32_t n_prims_padded, bool resident) {
-    return resident ? (((size_t) n_prims_padded * 4 + 15) / 16) * 16 : 0;
-}
-__host__ __device__ inline size_t rt3_smem_bytes(uint32_t n_prims_padded, bool resident) {
-    return 64 + rt3_smem_rec_bytes(n_prims_padded, resident) + rt3_smem_radius_bytes(n_prims_padded, resident) +
-           (size_t) RT3_RAYS * RT3_CAND_CAP * RT3_CTA_THREADS * 2;
+#define RT3_TILE_PAIRS (RT3_TILE_PRIMS / 2)
+#define RT3_TILE_XY_BYTES (RT3_TILE_PAIRS * 16)
+#define RT3_TILE_W_BYTES (RT3_TILE_PAIRS * 8)
+
+__host__ __device__ inline size_t rt3_smem_bytes(bool resident) {
+    return resident ? (size_t) RT3_MASK_BYTES : (size_t) 64 + 2 * (RT3_TILE_XY_BYTES + RT3_TILE_W_BYTES) + RT3_MASK_BYTES;
 }
 
 template <bool RESIDENT>
-__device__ __forceinline__ rt3_smem_view smem_view(unsigned char* base, uint32_t n_prims_padded) {
+__device__ __forceinline__ rt3_smem_view smem_view(unsigned char* base) {
     rt3_smem_view v;
-    v.bars = reinterpret_cast<uint64_t*>(base);
-    v.recs = reinterpret_cast<float4*>(base + 64);
-    unsigned char* p = base + 64 + rt3_smem_rec_bytes(n_prims_padded, RESIDENT);
-    v.radius = RESIDENT ? reinterpret_cast<float*>(p) : nullptr;
-    p += rt3_smem_radius_bytes(n_prims_padded, RESIDENT);
-    v.cand = reinterpret_cast<uint16_t*>(p);
+    if (RESIDENT) {
+        v.bars = nullptr; v.tile_xy = nullptr; v.tile_w = nullptr;
+        v.masks = reinterpret_cast<uint32_t*>(base);
+    } else {
+        v.bars = reinterpret_cast<uint64_t*>(base);
+        v.tile_xy = reinterpret_cast<float4*>(base + 64);
+        v.tile_w = reinterpret_cast<float2*>(base + 64 + 2 * RT3_TILE_XY_BYTES);
+        v.masks = reinterpret_cast<uint32_t*>(base + 64 + 2 * (RT3_TILE_XY_BYTES + RT3_TILE_W_BYTES));
+    }
     return v;
 }
 
-/* Brings the prefilter records (and radii) into shared memory once (resident
- * scenes) with bulk asynchronous copies (TMA, SASS UBLKCP), or arms the
- * streaming barriers. */
+/* Arms the streaming barriers (streamed scenes only). */
 template <bool RESIDENT>
-__device__ __forceinline__ void scene_prologue(const rt3_scene_view& S, const rt3_smem_view& sm) {
+__device__ __forceinline__ void scene_prologue(const rt3_smem_view& sm) {
+    if (RESIDENT) { return; }
     if (threadIdx.x == 0) {
         mbar_init(&sm.bars[0], 1);
         mbar_init(&sm.bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (RESIDENT && S.n_prims_padded > 0) {
-        if (threadIdx.x == 0) {
-            const uint32_t bytes = S.n_prims_padded * RT3_REC_BYTES, rbytes = S.n_prims_padded * 4u;
-            mbar_expect_tx(&sm.bars[0], bytes + rbytes);
-            for (uint32_t off = 0; off < bytes; off += 32768u) {
-                uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
-                bulk_copy_g2s(reinterpret_cast<unsigned char*>(sm.recs) + off, reinterpret_cast<const unsigned char*>(S.bounds) + off, n,
-                              &sm.bars[0]);
-            }
-            bulk_copy_g2s(sm.radius, S.prim_radius, rbytes, &sm.bars[0]);
-        }
-        mbar_wait(&sm.bars[0], 0);
-    }
 }
 
-/* Closest hit of the ray pair against the whole scene. For streamed scenes
- * every thread of the CTA must call this together (tile barriers); `phase`
- * carries the mbarrier parities across calls. */
+/* Streamed scenes: one thread starts the bulk asynchronous copies (TMA, SASS UBLKCP) of tile `t` into `stage`. */
+__device__ __forceinline__ void fetch_tile(const rt3_scene_view& S, const rt3_smem_view& sm, uint32_t t, uint32_t stage) {
+    const uint32_t first_pair = t * RT3_TILE_PAIRS, total_pairs = S.n_prims_padded / 2;
+    const uint32_t n = total_pairs - first_pair < RT3_TILE_PAIRS ? total_pairs - first_pair : RT3_TILE_PAIRS;
+    mbar_expect_tx(&sm.bars[stage], n * 24u);
+    bulk_copy_g2s(sm.tile_xy + (size_t) stage * RT3_TILE_PAIRS, S.pair_xy + first_pair, n * 16u, &sm.bars[stage]);
+    bulk_copy_g2s(sm.tile_w + (size_t) stage * RT3_TILE_PAIRS, S.pair_w + first_pair, n * 8u, &sm.bars[stage]);
+}
+
+/* Closest hit of the thread's rays against the whole scene. For streamed
+ * scenes every thread of the CTA must call this together (tile barriers);
+ * `phase` carries the mbarrier parities across calls. */
 template <bool PATH_MODE, bool RESIDENT>
 __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_smem_view& sm, uint32_t& phase,
                                             const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&d)[RT3_RAYS], const rt3_vec3 (&dn)[RT3_RAYS],
                                             const bool (&live)[RT3_RAYS], rt3_hit (&best)[RT3_RAYS]) {
-    rt3_ray_slab f[RT3_RAYS];
-    uint32_t n_cand[RT3_RAYS];
+    rt3_ray_filter f[RT3_RAYS];
 #pragma unroll
     for (int r = 0; r < RT3_RAYS; r++) {
-        f[r] = make_ray_slab(S, o[r], dn[r]);
+        f[r] = make_ray_filter(S, o[r], dn[r]);
         best[r].t = __int_as_float(0x7f800000);
         best[r].prim = RT3_NO_HIT;
-        n_cand[r] = 0;
     }
-    rt3_tile_view T;
-    T.cand = sm.cand;
     if (RESIDENT) {
-        T.recs = sm.recs; T.radius = sm.radius; T.first_prim = 0; T.n = S.n_prims_padded;
-        sweep_tile<PATH_MODE>(S, T, f, o, d, live, n_cand, best);
+        sweep_range<PATH_MODE, true>(S, nullptr, nullptr, 0u, 0u, S.n_prims_padded, f, o, d, live, sm.masks, best);
         return;
     }
     const uint32_t n_tiles = (S.n_prims_padded + RT3_TILE_PRIMS - 1) / RT3_TILE_PRIMS;
-    if (threadIdx.x == 0 && n_tiles > 0) {
-        uint32_t n0 = S.n_prims_padded < RT3_TILE_PRIMS ? S.n_prims_padded : RT3_TILE_PRIMS;
-        mbar_expect_tx(&sm.bars[0], n0 * RT3_REC_BYTES);
-        bulk_copy_g2s(sm.recs, S.bounds, n0 * RT3_REC_BYTES, &sm.bars[0]);
-    }
-    T.radius = nullptr;
+    if (threadIdx.x == 0 && n_tiles > 0) { fetch_tile(S, sm, 0u, 0u); }
     for (uint32_t t = 0; t < n_tiles; t++) {
         const uint32_t stage = t & 1u;
-        if (threadIdx.x == 0 && t + 1 < n_tiles) {
-            /* stage^1 was last read for tile t-1; the __syncthreads below ordered those reads before this copy */
-            uint32_t first = (t + 1) * RT3_TILE_PRIMS;
-            uint32_t n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
-            mbar_expect_tx(&sm.bars[stage ^ 1u], n * RT3_REC_BYTES);
-            bulk_copy_g2s(sm.recs + (size_t) (stage ^ 1u) * RT3_TILE_PRIMS, S.bounds + first, n * RT3_REC_BYTES,
-                          &sm.bars[stage ^ 1u]);
-        }
+        /* stage^1 was last read for tile t-1; the __syncthreads below ordered those reads before this copy */
+        if (threadIdx.x == 0 && t + 1 < n_tiles) { fetch_tile(S, sm, t + 1, stage ^ 1u); }
         mbar_wait(&sm.bars[stage], (phase >> stage) & 1u);
         phase ^= 1u << stage;
         const uint32_t first = t * RT3_TILE_PRIMS;
-        T.recs = sm.recs + (size_t) stage * RT3_TILE_PRIMS;
-        T.first_prim = first;
-        T.n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
-        sweep_tile<PATH_MODE>(S, T, f, o, d, live, n_cand, best);
+        const uint32_t n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
+        sweep_range<PATH_MODE, false>(S, sm.tile_xy + (size_t) stage * RT3_TILE_PAIRS, sm.tile_w + (size_t) stage * RT3_TILE_PAIRS, 0u, first, n,
+                                      f, o, d, live, sm.masks, best);
         __syncthreads();
     }
 }
@@ -151,8 +131,8 @@ reference_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, uint32_t* __re
                  uint32_t* __restrict__ hit_entity, float* __restrict__ hit_t, unsigned long long* __restrict__ counters) {
     constexpr int R = RT3_RAYS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const rt3_smem_view sm = smem_view<RESIDENT>(smem_raw, S.n_prims_padded);
-    scene_prologue<RESIDENT>(S, sm);
+    const rt3_smem_view sm = smem_view<RESIDENT>(smem_raw);
+    scene_prologue<RESIDENT>(sm);
     uint32_t phase = 0u;
 
     const rt3_vec3 origin = v3(cam.origin[0], cam.origin[1], cam.origin[2]);
@@ -282,8 +262,8 @@ pathtrace_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, unsigned long 
                  unsigned long long* __restrict__ counters) {
     constexpr int R = RT3_RAYS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const rt3_smem_view sm = smem_view<RESIDENT>(smem_raw, S.n_prims_padded);
-    scene_prologue<RESIDENT>(S, sm);
+    const rt3_smem_view sm = smem_view<RESIDENT>(smem_raw);
+    scene_prologue<RESIDENT>(sm);
     uint32_t phase = 0u;
 
     const rt3_vec3 cam_o = v3(cam.origin[0], cam.origin[1], cam.origin[2]);
