@@ -255,22 +255,22 @@ template <class K> int configure(K kernel, size_t smem, int* blocks_per_sm) {
     return RT3_OK;
 }
 
-template <bool RESIDENT>
+template <bool RESIDENT, bool SPHERES_ONLY>
 int launch_reference(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp, size_t smem, uint32_t* frame, uint32_t* prim,
                      uint32_t* ent, float* t, cudaStream_t stream) {
-    int rc = configure(reference_kernel<RESIDENT>, smem, nullptr);
+    int rc = configure(reference_kernel<RESIDENT, SPHERES_ONLY>, smem, nullptr);
     if (rc != RT3_OK) { return rc; }
     unsigned long long per_cta = (unsigned long long) RT3_CTA_THREADS * RT3_RAYS;
     unsigned grid = (unsigned) ((kp.n_pixels + per_cta - 1) / per_cta);
-    reference_kernel<RESIDENT><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, cam, kp, frame, prim, ent, t, ctx->counters.ptr);
+    reference_kernel<RESIDENT, SPHERES_ONLY><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, cam, kp, frame, prim, ent, t, ctx->counters.ptr);
     RT3_CUDA(cudaGetLastError());
     return RT3_OK;
 }
 
-template <bool RESIDENT>
+template <bool RESIDENT, bool SPHERES_ONLY>
 int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp, size_t smem, cudaStream_t stream) {
     int per_sm = 0;
-    int rc = configure(pathtrace_kernel<RESIDENT>, smem, &per_sm);
+    int rc = configure(pathtrace_kernel<RESIDENT, SPHERES_ONLY>, smem, &per_sm);
     if (rc != RT3_OK) { return rc; }
     if (per_sm < 1) { return fail(RT3_ERR_CUDA, "pathtrace kernel does not fit on an SM (smem %zu)", smem); }
     /* persistent grid: every SM full, no more CTAs than there are CTAs' worth of paths */
@@ -278,7 +278,7 @@ int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
     unsigned long long want = (kp.n_items + per_cta - 1) / per_cta;
     unsigned grid = (unsigned) ctx->sm_count * (unsigned) per_sm;
     if (want < grid) { grid = want ? (unsigned) want : 1u; }
-    pathtrace_kernel<RESIDENT><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, cam, kp, ctx->accum.ptr, ctx->counters.ptr);
+    pathtrace_kernel<RESIDENT, SPHERES_ONLY><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, cam, kp, ctx->accum.ptr, ctx->counters.ptr);
     RT3_CUDA(cudaGetLastError());
     return RT3_OK;
 }
@@ -325,8 +325,11 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     }
     if (params->mode == RT3_MODE_REFERENCE) {
         RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
-        rc = resident ? launch_reference<true>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream)
-                      : launch_reference<false>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream);
+        const bool so = ctx->view.n_faces == 0;
+        rc = resident ? (so ? launch_reference<true, true>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream)
+                            : launch_reference<true, false>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream))
+                      : (so ? launch_reference<false, true>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream)
+                            : launch_reference<false, false>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream));
         if (rc != RT3_OK) { return rc; }
         RT3_CUDA(cudaEventRecord(ctx->ev_k1, stream));
         RT3_CUDA(cudaEventRecord(ctx->ev_end, stream));
@@ -340,7 +343,9 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     clear_accum_kernel<<<clear_grid, 256, 0, stream>>>(kp, ctx->accum.ptr);
     RT3_CUDA(cudaGetLastError());
     RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
-    rc = resident ? launch_pathtrace<true>(ctx, *cam, kp, smem, stream) : launch_pathtrace<false>(ctx, *cam, kp, smem, stream);
+    const bool spheres_only = ctx->view.n_faces == 0;
+    rc = resident ? (spheres_only ? launch_pathtrace<true, true>(ctx, *cam, kp, smem, stream) : launch_pathtrace<true, false>(ctx, *cam, kp, smem, stream))
+                  : (spheres_only ? launch_pathtrace<false, true>(ctx, *cam, kp, smem, stream) : launch_pathtrace<false, false>(ctx, *cam, kp, smem, stream));
     if (rc != RT3_OK) { return rc; }
     RT3_CUDA(cudaEventRecord(ctx->ev_k1, stream));
     unsigned resolve_grid = (unsigned) ((kp.n_pixels + 255ull) / 256ull);

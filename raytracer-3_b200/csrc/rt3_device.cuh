@@ -171,34 +171,31 @@ __device__ __forceinline__ void exact_face(const rt3_scene_view& S, uint32_t i, 
 }
 
 /* Exact ray-sphere test, reference mode: WIP hit_sphere, raytracer_v4.glsl:157-178
- * (abc form, near root, t >= 0), un-normalised direction. */
-__device__ __forceinline__ void exact_sphere_v4(const rt3_scene_view& S, uint32_t si, float4 sp, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
+ * (abc form, near root, t >= 0), un-normalised direction. Written without
+ * branches: the lanes of a warp walk different survivor lists, and some lane
+ * hits in nearly every step. */
+__device__ __forceinline__ void exact_sphere_v4(uint32_t prim, float4 sp, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
     rt3_vec3 oc = o - v3(sp.x, sp.y, sp.z);
     float a = dot3(d, d);
     float b = 2.0f * dot3(oc, d);
     float c = dot3(oc, oc) - sp.w * sp.w;
     float D = b * b - (4.0f * a) * c;
-    if (D >= 0) {
-        float t = (-b - sqrtf(D)) / (2.0f * a);
-        if (t >= 0.0f && t < best.t) { best.prim = S.n_faces + si; best.t = t; }
-    }
+    float t = (-b - sqrtf(fmaxf(D, 0.0f))) / (2.0f * a);
+    if (D >= 0 && t >= 0.0f && t < best.t) { best.prim = prim; best.t = t; }
 }
 
 /* Exact ray-sphere test, bounce loop: half-b form with a unit direction, near
  * then far root, accepted iff tmin <= t < best. */
-__device__ __forceinline__ void exact_sphere_path(const rt3_scene_view& S, uint32_t si, float4 sp, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
+__device__ __forceinline__ void exact_sphere_path(uint32_t prim, float4 sp, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
     rt3_vec3 oc = o - v3(sp.x, sp.y, sp.z);
     float h = dot3(oc, d);
     float c = dot3(oc, oc) - sp.w * sp.w;
     float disc = h * h - c;
-    if (!(disc >= 0.0f)) { return; }
-    float sq = sqrtf(disc);
-    float t = -h - sq;
-    if (!(t >= RT3_TMIN && t < best.t)) {
-        t = -h + sq;
-        if (!(t >= RT3_TMIN && t < best.t)) { return; }
-    }
-    best.prim = S.n_faces + si; best.t = t;
+    float sq = sqrtf(fmaxf(disc, 0.0f));
+    float t1 = -h - sq, t2 = -h + sq;
+    bool ok1 = t1 >= RT3_TMIN && t1 < best.t;
+    bool ok2 = t2 >= RT3_TMIN && t2 < best.t;
+    if (disc >= 0.0f && (ok1 || ok2)) { best.prim = prim; best.t = ok1 ? t1 : t2; }
 }
 
 /* Records of scenes up to RT3_CONST_PRIMS live in the constant bank: the sweep
@@ -255,8 +252,10 @@ __device__ __forceinline__ void sweep_chunk(const float4* __restrict__ xy, const
 /* Exact tests of one ray's level-1 survivors of a chunk, in ascending primitive
  * order (words ascending, bits from the top), so the strict `t < best` rule
  * keeps the lowest index on ties exactly like the reference loop
- * (SequentialRenderer.cpp:71). Every lane walks its own survivor list. */
-template <bool PATH_MODE>
+ * (SequentialRenderer.cpp:71). Every lane walks its own survivor list; `masks`
+ * points at this thread's first word of the ray. Padding records never survive
+ * level 1, so every bit is a real primitive. */
+template <bool PATH_MODE, bool SPHERES_ONLY>
 __device__ __forceinline__ void drain_chunk(const rt3_scene_view& S, uint32_t first_prim, const rt3_ray_filter& f, rt3_vec3 o, rt3_vec3 d,
                                             const uint32_t* __restrict__ masks, uint32_t nz, rt3_hit& best) {
     uint32_t m = 0u, word_prim = 0u;
@@ -265,18 +264,18 @@ __device__ __forceinline__ void drain_chunk(const rt3_scene_view& S, uint32_t fi
             if (nz == 0u) { break; }
             const uint32_t wd = (uint32_t) __ffs((int) nz) - 1u;
             nz &= nz - 1u;
-            m = masks[wd * RT3_CTA_THREADS + threadIdx.x];
+            m = masks[wd * RT3_CTA_THREADS];
             word_prim = first_prim + wd * RT3_WORD_PRIMS;
         }
         const uint32_t k = (uint32_t) __clz((int) m);
-        m &= ~(0x80000000u >> k);
+        m ^= 0x80000000u >> k;
         const uint32_t prim = word_prim + k;
-        if (prim < S.n_faces) {
+        if (SPHERES_ONLY || prim >= S.n_faces) {
+            const float4 sp = __ldg(&S.spheres[SPHERES_ONLY ? prim : prim - S.n_faces]);
+            if (PATH_MODE) { exact_sphere_path(prim, sp, o, d, best); }
+            else { exact_sphere_v4(prim, sp, o, d, best); }
+        } else {
             if (line_test(__ldg(&S.filt3[prim]), f)) { exact_face(S, prim, o, d, PATH_MODE ? RT3_TMIN : 0.0f, best); }
-        } else if (prim < S.n_prims) {
-            const float4 sp = __ldg(&S.spheres[prim - S.n_faces]);
-            if (PATH_MODE) { exact_sphere_path(S, prim - S.n_faces, sp, o, d, best); }
-            else { exact_sphere_v4(S, prim - S.n_faces, sp, o, d, best); }
         }
     }
 }
@@ -284,7 +283,7 @@ __device__ __forceinline__ void drain_chunk(const rt3_scene_view& S, uint32_t fi
 /* Closest hit of the thread's rays against `n_prims` primitives (a multiple of
  * 32) whose records start at pair index `first_pair`; `first_prim` is the
  * global id of the first one. */
-template <bool PATH_MODE, bool CONST_BANK>
+template <bool PATH_MODE, bool CONST_BANK, bool SPHERES_ONLY>
 __device__ __forceinline__ void sweep_range(const rt3_scene_view& S, const float4* __restrict__ xy, const float2* __restrict__ w, uint32_t first_pair,
                                             uint32_t first_prim, uint32_t n_prims, const rt3_ray_filter (&f)[RT3_RAYS],
                                             const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&d)[RT3_RAYS], const bool (&live)[RT3_RAYS],
@@ -297,7 +296,8 @@ __device__ __forceinline__ void sweep_range(const rt3_scene_view& S, const float
 #pragma unroll
         for (int r = 0; r < RT3_RAYS; r++) {
             if (!live[r]) { nz[r] = 0u; }
-            drain_chunk<PATH_MODE>(S, first_prim + w0 * RT3_WORD_PRIMS, f[r], o[r], d[r], masks + r * RT3_CHUNK_WORDS * RT3_CTA_THREADS, nz[r], best[r]);
+            drain_chunk<PATH_MODE, SPHERES_ONLY>(S, first_prim + w0 * RT3_WORD_PRIMS, f[r], o[r], d[r],
+                                                 masks + r * RT3_CHUNK_WORDS * RT3_CTA_THREADS + threadIdx.x, nz[r], best[r]);
         }
     }
 }

@@ -91,7 +91,7 @@ __device__ __forceinline__ void fetch_tile(const rt3_scene_view& S, const rt3_sm
 /* Closest hit of the thread's rays against the whole scene. For streamed
  * scenes every thread of the CTA must call this together (tile barriers);
  * `phase` carries the mbarrier parities across calls. */
-template <bool PATH_MODE, bool RESIDENT>
+template <bool PATH_MODE, bool RESIDENT, bool SPHERES_ONLY>
 __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_smem_view& sm, uint32_t& phase,
                                             const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&d)[RT3_RAYS], const rt3_vec3 (&dn)[RT3_RAYS],
                                             const bool (&live)[RT3_RAYS], rt3_hit (&best)[RT3_RAYS]) {
@@ -103,7 +103,7 @@ __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_s
         best[r].prim = RT3_NO_HIT;
     }
     if (RESIDENT) {
-        sweep_range<PATH_MODE, true>(S, nullptr, nullptr, 0u, 0u, S.n_prims_padded, f, o, d, live, sm.masks, best);
+        sweep_range<PATH_MODE, true, SPHERES_ONLY>(S, nullptr, nullptr, 0u, 0u, S.n_prims_padded, f, o, d, live, sm.masks, best);
         return;
     }
     const uint32_t n_tiles = (S.n_prims_padded + RT3_TILE_PRIMS - 1) / RT3_TILE_PRIMS;
@@ -116,7 +116,7 @@ __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_s
         phase ^= 1u << stage;
         const uint32_t first = t * RT3_TILE_PRIMS;
         const uint32_t n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
-        sweep_range<PATH_MODE, false>(S, sm.tile_xy + (size_t) stage * RT3_TILE_PAIRS, sm.tile_w + (size_t) stage * RT3_TILE_PAIRS, 0u, first, n,
+        sweep_range<PATH_MODE, false, SPHERES_ONLY>(S, sm.tile_xy + (size_t) stage * RT3_TILE_PAIRS, sm.tile_w + (size_t) stage * RT3_TILE_PAIRS, 0u, first, n,
                                       f, o, d, live, sm.masks, best);
         __syncthreads();
     }
@@ -125,7 +125,7 @@ __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_s
 /* ------------------------------------------------------------------------ *
  * Reference mode: SequentialRenderer.cpp:269-308 (+ AOVs)
  * ------------------------------------------------------------------------ */
-template <bool RESIDENT>
+template <bool RESIDENT, bool SPHERES_ONLY>
 __global__ void __launch_bounds__(RT3_CTA_THREADS, RT3_CTAS_PER_SM)
 reference_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, uint32_t* __restrict__ frame, uint32_t* __restrict__ hit_prim,
                  uint32_t* __restrict__ hit_entity, float* __restrict__ hit_t, unsigned long long* __restrict__ counters) {
@@ -160,7 +160,7 @@ reference_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, uint32_t* __re
         d[r] = ((llc + u * hor) + v * ver) - origin;
         dn[r] = normalize3(d[r]);
     }
-    sweep_scene<false, RESIDENT>(S, sm, phase, o, d, dn, live, best);
+    sweep_scene<false, RESIDENT, SPHERES_ONLY>(S, sm, phase, o, d, dn, live, best);
     unsigned long long rays = 0;
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -256,7 +256,7 @@ __device__ __forceinline__ bool claim_item(bool want, rt3_chunk& c, const rt3_kp
     return got;
 }
 
-template <bool RESIDENT>
+template <bool RESIDENT, bool SPHERES_ONLY>
 __global__ void __launch_bounds__(RT3_CTA_THREADS, RT3_CTAS_PER_SM)
 pathtrace_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, unsigned long long* __restrict__ accum,
                  unsigned long long* __restrict__ counters) {
@@ -323,7 +323,7 @@ pathtrace_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, unsigned long 
         else { if (!__syncthreads_or(any ? 1 : 0)) { break; } }           /* tiles are CTA-wide */
 
         /* (2) closest hit of every live ray against the whole scene */
-        sweep_scene<true, RESIDENT>(S, sm, phase, o, d, d, live, best);
+        sweep_scene<true, RESIDENT, SPHERES_ONLY>(S, sm, phase, o, d, d, live, best);
 
         /* (3) shade: miss -> sky * throughput; hit -> scatter */
 #pragma unroll
