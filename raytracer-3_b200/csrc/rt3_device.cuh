@@ -21,14 +21,25 @@
 #define RT3_TMIN 0.001f
 #define RT3_ACC_SCALE 16777216.0f
 
+#ifndef RT3_UNROLL_PAIRS
+#define RT3_UNROLL_PAIRS 16
+#endif
+#define RT3_PRAGMA_STR(x) _Pragma(#x)
+#define RT3_PRAGMA_UNROLL(n) RT3_PRAGMA_STR(unroll n)
+#ifndef RT3_RAYS
 #define RT3_RAYS 2              /* rays (path slots) per thread */
-#define RT3_WORD_PRIMS 32       /* primitives per survivor-mask word; the primitive array is padded to a multiple of this */
-#define RT3_PAD_PRIMS RT3_WORD_PRIMS
+#endif
+#define RT3_WORD_PRIMS 32       /* primitives per survivor-mask word */
+#define RT3_PAD_PRIMS 8         /* the primitive array is padded to a multiple of this with never-surviving records */
+#ifndef RT3_CHUNK_WORDS
 #define RT3_CHUNK_WORDS 16      /* mask words swept before the survivors are drained (512 primitives) */
+#endif
 #define RT3_CONST_PRIMS 4096    /* scenes up to this size are swept out of the constant bank (48 KB of records) */
 #define RT3_TILE_PRIMS 1024     /* larger scenes: primitives per streamed shared-memory tile (12 KB per stage) */
 #define RT3_CTA_THREADS 128
+#ifndef RT3_CTAS_PER_SM
 #define RT3_CTAS_PER_SM 5       /* register budget: 65536 / (128 * 5) = 102 per thread */
+#endif
 #define RT3_ITEM_CHUNK 1024u    /* path items a warp claims per global atomic */
 
 /* Relative slack of the prefilter (64 units of 2^-24), applied to |c|^2 + r^2
@@ -75,7 +86,7 @@ struct rt3_scene_view {
     uint32_t n_faces;
     uint32_t n_spheres;
     uint32_t n_prims;        /* n_faces + n_spheres; primitive id = face index, then n_faces + sphere index */
-    uint32_t n_prims_padded; /* rounded up to RT3_WORD_PRIMS with never-surviving records */
+    uint32_t n_prims_padded; /* rounded up to RT3_PAD_PRIMS with never-surviving records */
     /* Prefilter records in the scene basis (e1, e2, e3): p_k = c . e_k for the bounding-sphere centre c,
      * w = -R^2 (inflated radius, per-primitive slack included). */
     const float4* pair_xy;   /* per primitive PAIR (2j, 2j+1): (p1a, p1b, p2a, p2b) */
@@ -209,37 +220,57 @@ __constant__ float2 c_pair_w[RT3_CONST_PRIMS / 2];
 /* Per-thread survivor masks of the chunk being swept: [RT3_RAYS][RT3_CHUNK_WORDS][RT3_CTA_THREADS] words. */
 #define RT3_MASK_BYTES (RT3_RAYS * RT3_CHUNK_WORDS * RT3_CTA_THREADS * 4)
 
-/* Level 1 over `n_words` mask words (32 primitives each) starting at pair index
- * `first_pair` of `xy` / `w` (constant bank or a shared-memory tile).
- * Per primitive pair and ray: three packed FMAs (fma.rn.f32x2, SASS FFMA2: both
- * primitives of the pair at once) and two funnel shifts that push the sign bits
- * of a^2 - R^2 into the ray's mask word. Bit 31 - k of a word belongs to its
- * k-th primitive. Words go to shared memory; `nz` gets one bit per non-empty word. */
+/* Level 1 for one primitive pair and every ray of the thread: three packed FMAs
+ * (fma.rn.f32x2, SASS FFMA2: both primitives of the pair at once) and two funnel
+ * shifts that push the sign bits of a^2 - R^2 into the ray's mask word. */
+__device__ __forceinline__ void slab_pair(const float4 A, const float2 B, const float2 (&u1)[RT3_RAYS], const float2 (&u2)[RT3_RAYS],
+                                          const float2 (&nou2)[RT3_RAYS], uint32_t (&m)[RT3_RAYS]) {
+#pragma unroll
+    for (int r = 0; r < RT3_RAYS; r++) {
+        const float2 a = __ffma2_rn(make_float2(A.x, A.y), u1[r], __ffma2_rn(make_float2(A.z, A.w), u2[r], nou2[r]));
+        const float2 d = __ffma2_rn(a, a, B);
+        m[r] = __funnelshift_l(__float_as_uint(d.x), m[r], 1);
+        m[r] = __funnelshift_l(__float_as_uint(d.y), m[r], 1);
+    }
+}
+
+/* Level 1 over `n_pairs` primitive pairs (a multiple of RT3_PAD_PRIMS / 2; at most
+ * RT3_CHUNK_WORDS words of 32 primitives) starting at pair index `first_pair` of
+ * `xy` / `w` (constant bank or a shared-memory tile). Bit 31 - k of a mask word
+ * belongs to its k-th primitive. Words go to shared memory; `nz` gets one bit per
+ * non-empty word. */
 template <bool CONST_BANK>
-__device__ __forceinline__ void sweep_chunk(const float4* __restrict__ xy, const float2* __restrict__ w, uint32_t first_pair, uint32_t n_words,
+__device__ __forceinline__ void sweep_chunk(const float4* __restrict__ xy, const float2* __restrict__ w, uint32_t first_pair, uint32_t n_pairs,
                                             const rt3_ray_filter (&f)[RT3_RAYS], uint32_t* __restrict__ masks, uint32_t (&nz)[RT3_RAYS]) {
+    constexpr uint32_t WORD_PAIRS = RT3_WORD_PRIMS / 2, PAD_PAIRS = RT3_PAD_PRIMS / 2;
     float2 nou2[RT3_RAYS], u1[RT3_RAYS], u2[RT3_RAYS];
 #pragma unroll
     for (int r = 0; r < RT3_RAYS; r++) {
         nou2[r] = make_float2(f[r].nou, f[r].nou); u1[r] = make_float2(f[r].u1, f[r].u1); u2[r] = make_float2(f[r].u2, f[r].u2);
         nz[r] = 0u;
     }
-    for (uint32_t wd = 0; wd < n_words; wd++) {
+    uint32_t wd = 0;
+    for (uint32_t done = 0; done < n_pairs; done += WORD_PAIRS, wd++) {
         uint32_t m[RT3_RAYS];
 #pragma unroll
         for (int r = 0; r < RT3_RAYS; r++) { m[r] = 0u; }
-        const uint32_t base = first_pair + wd * (RT3_WORD_PRIMS / 2);
-#pragma unroll
-        for (int j = 0; j < RT3_WORD_PRIMS / 2; j++) {
-            const float4 A = CONST_BANK ? c_pair_xy[base + j] : xy[base + j];
-            const float2 B = CONST_BANK ? c_pair_w[base + j] : w[base + j];
-#pragma unroll
-            for (int r = 0; r < RT3_RAYS; r++) {
-                const float2 a = __ffma2_rn(make_float2(A.x, A.y), u1[r], __ffma2_rn(make_float2(A.z, A.w), u2[r], nou2[r]));
-                const float2 d = __ffma2_rn(a, a, B);
-                m[r] = __funnelshift_l(__float_as_uint(d.x), m[r], 1);
-                m[r] = __funnelshift_l(__float_as_uint(d.y), m[r], 1);
+        const uint32_t base = first_pair + done;
+        if (n_pairs - done >= WORD_PAIRS) {
+RT3_PRAGMA_UNROLL(RT3_UNROLL_PAIRS)
+            for (int j = 0; j < (int) WORD_PAIRS; j++) {
+                slab_pair(CONST_BANK ? c_pair_xy[base + j] : xy[base + j], CONST_BANK ? c_pair_w[base + j] : w[base + j], u1, u2, nou2, m);
             }
+        } else {
+            /* last, partial word of the scene */
+            const uint32_t left = n_pairs - done;
+            for (uint32_t g = 0; g < left; g += PAD_PAIRS) {
+#pragma unroll
+                for (int j = 0; j < (int) PAD_PAIRS; j++) {
+                    slab_pair(CONST_BANK ? c_pair_xy[base + g + j] : xy[base + g + j], CONST_BANK ? c_pair_w[base + g + j] : w[base + g + j], u1, u2, nou2, m);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RT3_RAYS; r++) { m[r] <<= 32u - 2u * left; }
         }
 #pragma unroll
         for (int r = 0; r < RT3_RAYS; r++) {
@@ -281,18 +312,18 @@ __device__ __forceinline__ void drain_chunk(const rt3_scene_view& S, uint32_t fi
 }
 
 /* Closest hit of the thread's rays against `n_prims` primitives (a multiple of
- * 32) whose records start at pair index `first_pair`; `first_prim` is the
- * global id of the first one. */
+ * RT3_PAD_PRIMS) whose records start at pair index `first_pair`; `first_prim` is
+ * the global id of the first one. */
 template <bool PATH_MODE, bool CONST_BANK, bool SPHERES_ONLY>
 __device__ __forceinline__ void sweep_range(const rt3_scene_view& S, const float4* __restrict__ xy, const float2* __restrict__ w, uint32_t first_pair,
                                             uint32_t first_prim, uint32_t n_prims, const rt3_ray_filter (&f)[RT3_RAYS],
                                             const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&d)[RT3_RAYS], const bool (&live)[RT3_RAYS],
                                             uint32_t* __restrict__ masks, rt3_hit (&best)[RT3_RAYS]) {
-    const uint32_t n_words = n_prims / RT3_WORD_PRIMS;
-    for (uint32_t w0 = 0; w0 < n_words; w0 += RT3_CHUNK_WORDS) {
-        const uint32_t nw = n_words - w0 < RT3_CHUNK_WORDS ? n_words - w0 : RT3_CHUNK_WORDS;
+    constexpr uint32_t CHUNK_PAIRS = RT3_CHUNK_WORDS * RT3_WORD_PRIMS / 2;
+    const uint32_t n_pairs = n_prims / 2;
+    for (uint32_t p0 = 0, w0 = 0; p0 < n_pairs; p0 += CHUNK_PAIRS, w0 += RT3_CHUNK_WORDS) {
         uint32_t nz[RT3_RAYS];
-        sweep_chunk<CONST_BANK>(xy, w, first_pair + w0 * (RT3_WORD_PRIMS / 2), nw, f, masks, nz);
+        sweep_chunk<CONST_BANK>(xy, w, first_pair + p0, n_pairs - p0 < CHUNK_PAIRS ? n_pairs - p0 : CHUNK_PAIRS, f, masks, nz);
 #pragma unroll
         for (int r = 0; r < RT3_RAYS; r++) {
             if (!live[r]) { nz[r] = 0u; }
