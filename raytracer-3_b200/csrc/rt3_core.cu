@@ -244,9 +244,9 @@ template <class T> int upload(DeviceBuffer<T>& buf, const std::vector<T>& host, 
     return RT3_OK;
 }
 
-size_t render_smem_bytes(const rt3_scene_view& v, bool* resident) {
+size_t render_smem_bytes(const rt3_scene_view& v, bool path_slots, bool* resident) {
     *resident = v.n_prims_padded <= RT3_CONST_PRIMS;
-    return rt3_smem_bytes(*resident);
+    return rt3_smem_bytes(*resident, path_slots);
 }
 
 template <class K> int configure(K kernel, size_t smem, int* blocks_per_sm) {
@@ -306,7 +306,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
                    uint32_t* prim, uint32_t* ent, float* t, cudaStream_t stream) {
     rt3_kparams kp = kp_in;
     bool resident = false;
-    size_t smem = render_smem_bytes(ctx->view, &resident);
+    size_t smem = render_smem_bytes(ctx->view, params->mode == RT3_MODE_PATHTRACE, &resident);
     kp.resident = resident ? 1u : 0u;
     ctx->stats.kernel_launches = 0;
     ctx->stats.rows_rendered = kp.owned_rows;

@@ -35,21 +35,29 @@ __device__ __forceinline__ uint32_t owned_row_to_global(const rt3_kparams& P, ui
 }
 
 /* Shared-memory layout.
- *   resident (constant-bank) scenes: [survivor masks]
- *   streamed scenes:                 [mbarriers (64 B)] [2 stages x (pair_xy tile, pair_w tile)] [survivor masks] */
+ *   resident (constant-bank) scenes: [survivor masks] [path slots]
+ *   streamed scenes:                 [mbarriers (64 B)] [2 stages x (pair_xy tile, pair_w tile)] [survivor masks] [path slots]
+ * The path slots (path tracer only) hold the state of every ray of every thread, one 32-bit word per
+ * field, laid out [slot][field][thread] so that a warp's accesses to a field are conflict-free. */
 struct rt3_smem_view {
     uint64_t* bars;   /* streamed: one "tile landed" mbarrier per stage */
     float4* tile_xy;  /* streamed: 2 stages of RT3_TILE_PRIMS / 2 pair records */
     float2* tile_w;
     uint32_t* masks;  /* RT3_RAYS * RT3_CHUNK_WORDS * RT3_CTA_THREADS words */
+    uint32_t* slots;  /* RT3_RAYS * RT3_SLOT_FIELDS * RT3_CTA_THREADS words */
 };
+
+enum { RT3_F_OX, RT3_F_OY, RT3_F_OZ, RT3_F_DX, RT3_F_DY, RT3_F_DZ, RT3_F_TX, RT3_F_TY, RT3_F_TZ, RT3_F_KEY, RT3_F_PIX,
+       RT3_F_BOUNCE /* RT3_NO_HIT: the slot is free */, RT3_F_BEST_T, RT3_F_BEST_PRIM, RT3_SLOT_FIELDS };
+#define RT3_SLOT_BYTES (RT3_RAYS * RT3_SLOT_FIELDS * RT3_CTA_THREADS * 4)
 
 #define RT3_TILE_PAIRS (RT3_TILE_PRIMS / 2)
 #define RT3_TILE_XY_BYTES (RT3_TILE_PAIRS * 16)
 #define RT3_TILE_W_BYTES (RT3_TILE_PAIRS * 8)
 
-__host__ __device__ inline size_t rt3_smem_bytes(bool resident) {
-    return resident ? (size_t) RT3_MASK_BYTES : (size_t) 64 + 2 * (RT3_TILE_XY_BYTES + RT3_TILE_W_BYTES) + RT3_MASK_BYTES;
+__host__ __device__ inline size_t rt3_smem_bytes(bool resident, bool path_slots) {
+    return (resident ? (size_t) RT3_MASK_BYTES : (size_t) 64 + 2 * (RT3_TILE_XY_BYTES + RT3_TILE_W_BYTES) + RT3_MASK_BYTES) +
+           (path_slots ? (size_t) RT3_SLOT_BYTES : 0);
 }
 
 template <bool RESIDENT>
@@ -58,11 +66,13 @@ __device__ __forceinline__ rt3_smem_view smem_view(unsigned char* base) {
     if (RESIDENT) {
         v.bars = nullptr; v.tile_xy = nullptr; v.tile_w = nullptr;
         v.masks = reinterpret_cast<uint32_t*>(base);
+        v.slots = reinterpret_cast<uint32_t*>(base + RT3_MASK_BYTES);
     } else {
         v.bars = reinterpret_cast<uint64_t*>(base);
         v.tile_xy = reinterpret_cast<float4*>(base + 64);
         v.tile_w = reinterpret_cast<float2*>(base + 64 + 2 * RT3_TILE_XY_BYTES);
         v.masks = reinterpret_cast<uint32_t*>(base + 64 + 2 * (RT3_TILE_XY_BYTES + RT3_TILE_W_BYTES));
+        v.slots = reinterpret_cast<uint32_t*>(base + 64 + 2 * (RT3_TILE_XY_BYTES + RT3_TILE_W_BYTES) + RT3_MASK_BYTES);
     }
     return v;
 }
@@ -118,6 +128,86 @@ __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_s
         const uint32_t n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
         sweep_range<PATH_MODE, false, SPHERES_ONLY>(S, sm.tile_xy + (size_t) stage * RT3_TILE_PAIRS, sm.tile_w + (size_t) stage * RT3_TILE_PAIRS, 0u, first, n,
                                       f, o, d, live, sm.masks, best);
+        __syncthreads();
+    }
+}
+
+/* ---- path slots in shared memory ------------------------------------------ */
+
+__device__ __forceinline__ uint32_t& slot_word(const rt3_smem_view& sm, int r, int field) {
+    return sm.slots[(r * RT3_SLOT_FIELDS + field) * RT3_CTA_THREADS + threadIdx.x];
+}
+__device__ __forceinline__ float slot_float(const rt3_smem_view& sm, int r, int field) { return __uint_as_float(slot_word(sm, r, field)); }
+__device__ __forceinline__ rt3_vec3 slot_vec(const rt3_smem_view& sm, int r, int field) {
+    return v3(slot_float(sm, r, field), slot_float(sm, r, field + 1), slot_float(sm, r, field + 2));
+}
+__device__ __forceinline__ void slot_store_vec(const rt3_smem_view& sm, int r, int field, rt3_vec3 v) {
+    slot_word(sm, r, field) = __float_as_uint(v.x); slot_word(sm, r, field + 1) = __float_as_uint(v.y); slot_word(sm, r, field + 2) = __float_as_uint(v.z);
+}
+
+/* Level-1 constants of every slot's ray; a free slot gets a filter nothing survives (a = +inf). */
+__device__ __forceinline__ void slot_filters(const rt3_scene_view& S, const rt3_smem_view& sm, rt3_ray_filter (&f)[RT3_RAYS]) {
+#pragma unroll
+    for (int r = 0; r < RT3_RAYS; r++) {
+        f[r] = make_ray_filter(S, slot_vec(sm, r, RT3_F_OX), slot_vec(sm, r, RT3_F_DX));
+        if (slot_word(sm, r, RT3_F_BOUNCE) == RT3_NO_HIT) { f[r].u1 = 0.0f; f[r].u2 = 0.0f; f[r].nou = __int_as_float(0x7f800000); }
+    }
+}
+
+/* Drains one chunk for every slot, one slot at a time from a single copy of the code. */
+template <bool SPHERES_ONLY>
+__device__ __forceinline__ void drain_slots(const rt3_scene_view& S, const rt3_smem_view& sm, uint32_t first_prim,
+                                            const rt3_ray_filter (&f)[RT3_RAYS], const uint32_t (&nz)[RT3_RAYS]) {
+    static_assert(RT3_RAYS * RT3_CHUNK_WORDS <= 64, "survivor summaries are packed into 64 bits");
+    unsigned long long packed = 0ull;
+#pragma unroll
+    for (int r = 0; r < RT3_RAYS; r++) { packed |= (unsigned long long) nz[r] << (r * RT3_CHUNK_WORDS); }
+#pragma unroll 1
+    for (int r = 0; r < RT3_RAYS; r++) {
+        const uint32_t mine = (uint32_t) (packed >> (r * RT3_CHUNK_WORDS)) & ((1u << RT3_CHUNK_WORDS) - 1u);
+        rt3_hit best;
+        best.t = slot_float(sm, r, RT3_F_BEST_T); best.prim = slot_word(sm, r, RT3_F_BEST_PRIM);
+        rt3_ray_filter fr = f[0]; /* level 2 is only needed for faces; rebuilt below for the slot at hand */
+        const rt3_vec3 o = slot_vec(sm, r, RT3_F_OX), d = slot_vec(sm, r, RT3_F_DX);
+        if (!SPHERES_ONLY) { fr = make_ray_filter(S, o, d); }
+        drain_chunk<true, SPHERES_ONLY>(S, first_prim, fr, o, d, sm.masks + r * RT3_CHUNK_WORDS * RT3_CTA_THREADS + threadIdx.x, mine, best);
+        slot_word(sm, r, RT3_F_BEST_T) = __float_as_uint(best.t); slot_word(sm, r, RT3_F_BEST_PRIM) = best.prim;
+    }
+}
+
+/* Closest hit of every slot's ray against the whole scene (results in the slots' BEST fields). */
+template <bool RESIDENT, bool SPHERES_ONLY>
+__device__ __forceinline__ void sweep_slots(const rt3_scene_view& S, const rt3_smem_view& sm, uint32_t& phase) {
+    constexpr uint32_t CHUNK_PAIRS = RT3_CHUNK_WORDS * RT3_WORD_PRIMS / 2;
+    rt3_ray_filter f[RT3_RAYS];
+    slot_filters(S, sm, f);
+#pragma unroll
+    for (int r = 0; r < RT3_RAYS; r++) { slot_word(sm, r, RT3_F_BEST_T) = 0x7f800000u; slot_word(sm, r, RT3_F_BEST_PRIM) = RT3_NO_HIT; }
+    if (RESIDENT) {
+        const uint32_t n_pairs = S.n_prims_padded / 2;
+        for (uint32_t p0 = 0; p0 < n_pairs; p0 += CHUNK_PAIRS) {
+            uint32_t nz[RT3_RAYS];
+            sweep_chunk<true>(nullptr, nullptr, p0, n_pairs - p0 < CHUNK_PAIRS ? n_pairs - p0 : CHUNK_PAIRS, f, sm.masks, nz);
+            drain_slots<SPHERES_ONLY>(S, sm, 2u * p0, f, nz);
+        }
+        return;
+    }
+    const uint32_t n_tiles = (S.n_prims_padded + RT3_TILE_PRIMS - 1) / RT3_TILE_PRIMS;
+    if (threadIdx.x == 0 && n_tiles > 0) { fetch_tile(S, sm, 0u, 0u); }
+    for (uint32_t t = 0; t < n_tiles; t++) {
+        const uint32_t stage = t & 1u;
+        if (threadIdx.x == 0 && t + 1 < n_tiles) { fetch_tile(S, sm, t + 1, stage ^ 1u); }
+        mbar_wait(&sm.bars[stage], (phase >> stage) & 1u);
+        phase ^= 1u << stage;
+        const uint32_t first = t * RT3_TILE_PRIMS;
+        const uint32_t n_pairs = (S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS) / 2;
+        const float4* xy = sm.tile_xy + (size_t) stage * RT3_TILE_PAIRS;
+        const float2* w = sm.tile_w + (size_t) stage * RT3_TILE_PAIRS;
+        for (uint32_t p0 = 0; p0 < n_pairs; p0 += CHUNK_PAIRS) {
+            uint32_t nz[RT3_RAYS];
+            sweep_chunk<false>(xy, w, p0, n_pairs - p0 < CHUNK_PAIRS ? n_pairs - p0 : CHUNK_PAIRS, f, sm.masks, nz);
+            drain_slots<SPHERES_ONLY>(S, sm, first + 2u * p0, f, nz);
+        }
         __syncthreads();
     }
 }
@@ -194,8 +284,15 @@ reference_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, uint32_t* __re
  * Path tracer
  * ------------------------------------------------------------------------ */
 
+#ifdef RT3_NOINLINE_RNG
+__device__ __noinline__ float draw_ni(uint32_t k, uint32_t dim) { return rt3_draw(k, dim); }
+#define rt3_draw draw_ni
+#define RT3_UV_INLINE __noinline__
+#else
+#define RT3_UV_INLINE __forceinline__
+#endif
 /* Uniform point on the unit sphere: z = 1 - 2 xi1, phi = 2 pi xi2. */
-__device__ __forceinline__ rt3_vec3 unit_vector(float xi1, float xi2) {
+__device__ RT3_UV_INLINE rt3_vec3 unit_vector(float xi1, float xi2) {
     float z = 1.0f - 2.0f * xi1;
     float rr = 1.0f - z * z;
     rr = sqrtf(rr < 0.0f ? 0.0f : rr);
@@ -256,6 +353,150 @@ __device__ __forceinline__ bool claim_item(bool want, rt3_chunk& c, const rt3_kp
     return got;
 }
 
+/* One path slot while it is in registers: the ray being traced, its throughput and its RNG key. */
+struct rt3_path {
+    rt3_vec3 o, d, thr;
+    uint32_t key, bounce, pix; /* bounce == RT3_NO_HIT: the slot is free */
+};
+
+struct rt3_cam_view {
+    rt3_vec3 origin, hor, ver, llc, lens_u, lens_v;
+    float lens_radius, wm1, hm1;
+};
+
+/* Primary ray of path item (compact pixel p, sample): pixel jitter, thin lens. */
+__device__ __forceinline__ void start_path(rt3_path& s, const rt3_cam_view& C, const rt3_kparams& P, uint32_t p, uint32_t sample) {
+    uint32_t local_row = p / P.width, x = p - local_row * P.width;
+    uint32_t y = owned_row_to_global(P, local_row);
+    uint32_t pixel_index = y * P.width + x;
+    s.pix = pixel_index;
+    uint32_t k = rt3_path_key(pixel_index, sample, P.seed);
+    s.key = k;
+    float jx = 0.0f, jy = 0.0f;
+    if (!(P.flags & RT3_FLAG_NO_JITTER)) { jx = rt3_draw(k, RT3_DIM_JITTER_X); jy = rt3_draw(k, RT3_DIM_JITTER_Y); }
+    float u = ((float) x + jx) / C.wm1;
+    float v = ((float) (P.height - 1 - y) + jy) / C.hm1;
+    rt3_vec3 org = C.origin;
+    rt3_vec3 dir = ((C.llc + u * C.hor) + v * C.ver) - org;
+    if (C.lens_radius > 0.0f) {
+        float rad = sqrtf(rt3_draw(k, RT3_DIM_LENS_R));
+        float sn, cs;
+        rt3_sincos_2pi(rt3_draw(k, RT3_DIM_LENS_PHI), &sn, &cs);
+        float lx = C.lens_radius * (rad * cs), ly = C.lens_radius * (rad * sn);
+        rt3_vec3 off = lx * C.lens_u + ly * C.lens_v;
+        org = org + off;
+        dir = dir - off;
+    }
+    s.o = org;
+    s.d = normalize3(dir);
+    s.thr = v3(1.0f, 1.0f, 1.0f);
+    s.bounce = 0;
+}
+
+/* Shades the closest hit `best` of a live path: miss -> sky * throughput, hit -> scatter
+ * (Lambertian, metal, dielectric). A finished path adds its radiance to the
+ * pixel's fixed-point accumulators and frees the slot. */
+__device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, const rt3_scene_view& S, const rt3_kparams& P,
+                                           unsigned long long* __restrict__ accum) {
+    bool done = false;
+    rt3_vec3 L = v3(0.0f, 0.0f, 0.0f);
+    const rt3_vec3 dr = s.d;
+    if (best.prim == RT3_NO_HIT) {
+        float t = 0.5f * (dr.y + 1.0f);
+        float a = 1.0f - t;
+        L = s.thr * v3(a * 1.0f + t * 0.5f, a * 1.0f + t * 0.7f, a * 1.0f + t * 1.0f);
+        done = true;
+    } else {
+        const uint32_t prim = best.prim;
+        rt3_vec3 hp = s.o + best.t * dr;
+        rt3_vec3 outward;
+        if (prim < S.n_faces) {
+            float4 fn = __ldg(&S.face_n[prim]);
+            outward = v3(fn.x, fn.y, fn.z);
+        } else {
+            float4 sp = __ldg(&S.spheres[prim - S.n_faces]);
+            rt3_vec3 pc = hp - v3(sp.x, sp.y, sp.z);
+            outward = v3(pc.x / sp.w, pc.y / sp.w, pc.z / sp.w);
+        }
+        const bool front = dot3(dr, outward) < 0.0f;
+        const rt3_vec3 n = front ? outward : -outward;
+        uint32_t kind = RT3_MAT_LAMBERTIAN;
+        rt3_vec3 albedo;
+        float fuzz = 0.0f, ior = 1.0f;
+        const uint32_t mi = __ldg(&S.prim_material[prim]);
+        if (mi == RT3_NO_HIT) {
+            float4 c = __ldg(&S.prim_color[prim]);
+            albedo = v3(c.x, c.y, c.z);
+        } else {
+            float4 m0 = __ldg(&S.materials[2 * mi]), m1 = __ldg(&S.materials[2 * mi + 1]);
+            kind = __float_as_uint(m0.x);
+            albedo = v3(m0.y, m0.z, m0.w);
+            fuzz = m1.x; ior = m1.y;
+        }
+        const uint32_t dim = RT3_DIM_BOUNCE0 + RT3_DIMS_PER_BOUNCE * s.bounce;
+        const uint32_t k = s.key;
+        rt3_vec3 nd;
+        if (kind == RT3_MAT_LAMBERTIAN) {
+            rt3_vec3 uv = unit_vector(rt3_draw(k, dim + 0), rt3_draw(k, dim + 1));
+            nd = n + uv;
+            if (fabsf(nd.x) < 1e-8f && fabsf(nd.y) < 1e-8f && fabsf(nd.z) < 1e-8f) { nd = n; }
+            s.thr = s.thr * albedo;
+        } else if (kind == RT3_MAT_METAL) {
+            float dnn = dot3(dr, n);
+            nd = dr - (2.0f * dnn) * n;
+            float fz = fuzz < 1.0f ? fuzz : 1.0f;
+            if (fz > 0.0f) {
+                rt3_vec3 uv = unit_vector(rt3_draw(k, dim + 0), rt3_draw(k, dim + 1));
+                float a = rt3_draw(k, dim + 2), b = rt3_draw(k, dim + 3), c = rt3_draw(k, dim + 4);
+                float mx = a < b ? b : a;
+                mx = mx < c ? c : mx;
+                nd = nd + (fz * mx) * uv;
+            }
+            if (!(dot3(nd, n) > 0.0f)) { done = true; }
+            s.thr = s.thr * albedo;
+        } else {
+            float ratio = front ? (1.0f / ior) : ior;
+            float cs = -dot3(dr, n);
+            cs = cs < 1.0f ? cs : 1.0f;
+            float s2 = 1.0f - cs * cs;
+            float sn = sqrtf(s2 < 0.0f ? 0.0f : s2);
+            bool cannot_refract = ratio * sn > 1.0f;
+            float r0 = (1.0f - ratio) / (1.0f + ratio);
+            r0 = r0 * r0;
+            float w = 1.0f - cs;
+            float w2 = w * w;
+            float schlick = r0 + (1.0f - r0) * ((w2 * w2) * w);
+            if (cannot_refract || schlick > rt3_draw(k, dim + 0)) {
+                float dnn = dot3(dr, n);
+                nd = dr - (2.0f * dnn) * n;
+            } else {
+                rt3_vec3 perp = ratio * (dr + cs * n);
+                float kk = 1.0f - dot3(perp, perp);
+                rt3_vec3 par = (-sqrtf(fabsf(kk))) * n;
+                nd = perp + par;
+            }
+        }
+        if (!done) {
+            s.o = hp;
+            s.d = normalize3(nd);
+            s.bounce++;
+            if (s.bounce >= P.max_depth) { done = true; } /* depth exhausted: radiance 0 */
+        }
+    }
+    if (done) {
+        unsigned long long qx = to_fixed(L.x), qy = to_fixed(L.y), qz = to_fixed(L.z);
+        unsigned long long* acc = accum + 3 * (size_t) s.pix;
+        if (qx) { atomicAdd(acc + 0, qx); }
+        if (qy) { atomicAdd(acc + 1, qy); }
+        if (qz) { atomicAdd(acc + 2, qz); }
+        s.bounce = RT3_NO_HIT;
+    }
+}
+
+/* Persistent multi-bounce path tracer. Every thread owns RT3_RAYS path slots whose state lives in
+ * shared memory; a loop iteration (1) takes the slots in turn through one copy of the shading and
+ * regeneration code -- shade the hit the last sweep found, then start the next (pixel, sample) item
+ * if the slot is free, so that all lanes sweep live rays -- and (2) sweeps the scene for all slots. */
 template <bool RESIDENT, bool SPHERES_ONLY>
 __global__ void __launch_bounds__(RT3_CTA_THREADS, RT3_CTAS_PER_SM)
 pathtrace_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, unsigned long long* __restrict__ accum,
@@ -266,164 +507,53 @@ pathtrace_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, unsigned long 
     scene_prologue<RESIDENT>(sm);
     uint32_t phase = 0u;
 
-    const rt3_vec3 cam_o = v3(cam.origin[0], cam.origin[1], cam.origin[2]);
-    const rt3_vec3 hor = v3(cam.horizontal[0], cam.horizontal[1], cam.horizontal[2]);
-    const rt3_vec3 ver = v3(cam.vertical[0], cam.vertical[1], cam.vertical[2]);
-    const rt3_vec3 llc = v3(cam.lower_left_corner[0], cam.lower_left_corner[1], cam.lower_left_corner[2]);
-    const float inv_w = (float) P.width - 1.0f, inv_h = (float) P.height - 1.0f;
+    rt3_cam_view C;
+    C.origin = v3(cam.origin[0], cam.origin[1], cam.origin[2]);
+    C.hor = v3(cam.horizontal[0], cam.horizontal[1], cam.horizontal[2]);
+    C.ver = v3(cam.vertical[0], cam.vertical[1], cam.vertical[2]);
+    C.llc = v3(cam.lower_left_corner[0], cam.lower_left_corner[1], cam.lower_left_corner[2]);
+    C.lens_u = v3(cam.lens_u[0], cam.lens_u[1], cam.lens_u[2]);
+    C.lens_v = v3(cam.lens_v[0], cam.lens_v[1], cam.lens_v[2]);
+    C.lens_radius = cam.lens_radius;
+    C.wm1 = (float) P.width - 1.0f; C.hm1 = (float) P.height - 1.0f;
 
-    rt3_vec3 o[R], d[R], thr[R];
-    uint32_t key[R], bounce[R];
-    size_t pix[R];
-    bool live[R];
-    rt3_hit best[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) { live[r] = false; bounce[r] = 0; key[r] = 0; pix[r] = 0; o[r] = d[r] = thr[r] = v3(0.f, 0.f, 0.f); }
+    for (int r = 0; r < R; r++) {
+#pragma unroll
+        for (int fld = 0; fld < RT3_SLOT_FIELDS; fld++) { slot_word(sm, r, fld) = 0u; }
+        slot_word(sm, r, RT3_F_BOUNCE) = RT3_NO_HIT;
+        slot_word(sm, r, RT3_F_BEST_PRIM) = RT3_NO_HIT;
+    }
     unsigned long long rays = 0;
     rt3_chunk chunk;
     chunk.cur = chunk.end = chunk.start = 0; chunk.pixel0 = chunk.sample0 = 0; chunk.dry = false;
 
     for (;;) {
-        /* (1) regenerate: every free slot starts the next (pixel, sample) item */
         bool any = false;
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < R; r++) {
-            uint32_t p = 0, sample = 0;
-            if (claim_item(!live[r], chunk, P, &counters[0], p, sample)) {
-                uint32_t local_row = p / P.width, x = p - local_row * P.width;
-                uint32_t y = owned_row_to_global(P, local_row);
-                uint32_t pixel_index = y * P.width + x;
-                pix[r] = (size_t) pixel_index;
-                uint32_t k = rt3_path_key(pixel_index, sample, P.seed);
-                key[r] = k;
-                float jx = 0.0f, jy = 0.0f;
-                if (!(P.flags & RT3_FLAG_NO_JITTER)) { jx = rt3_draw(k, RT3_DIM_JITTER_X); jy = rt3_draw(k, RT3_DIM_JITTER_Y); }
-                float u = ((float) x + jx) / inv_w;
-                float v = ((float) (P.height - 1 - y) + jy) / inv_h;
-                rt3_vec3 org = cam_o;
-                rt3_vec3 dir = ((llc + u * hor) + v * ver) - org;
-                if (cam.lens_radius > 0.0f) {
-                    float rad = sqrtf(rt3_draw(k, RT3_DIM_LENS_R));
-                    float sn, cs;
-                    rt3_sincos_2pi(rt3_draw(k, RT3_DIM_LENS_PHI), &sn, &cs);
-                    float lx = cam.lens_radius * (rad * cs), ly = cam.lens_radius * (rad * sn);
-                    rt3_vec3 off = lx * v3(cam.lens_u[0], cam.lens_u[1], cam.lens_u[2]) + ly * v3(cam.lens_v[0], cam.lens_v[1], cam.lens_v[2]);
-                    org = org + off;
-                    dir = dir - off;
-                }
-                o[r] = org;
-                d[r] = normalize3(dir);
-                thr[r] = v3(1.0f, 1.0f, 1.0f);
-                bounce[r] = 0;
-                live[r] = true;
+            rt3_path s;
+            s.bounce = slot_word(sm, r, RT3_F_BOUNCE);
+            if (s.bounce != RT3_NO_HIT) {
+                s.o = slot_vec(sm, r, RT3_F_OX); s.d = slot_vec(sm, r, RT3_F_DX); s.thr = slot_vec(sm, r, RT3_F_TX);
+                s.key = slot_word(sm, r, RT3_F_KEY); s.pix = slot_word(sm, r, RT3_F_PIX);
+                rt3_hit best;
+                best.t = slot_float(sm, r, RT3_F_BEST_T); best.prim = slot_word(sm, r, RT3_F_BEST_PRIM);
+                rays++;
+                shade_path(s, best, S, P, accum);
             }
-            any = any || live[r];
+            uint32_t p = 0, sample = 0;
+            if (claim_item(s.bounce == RT3_NO_HIT, chunk, P, &counters[0], p, sample)) { start_path(s, C, P, p, sample); }
+            slot_word(sm, r, RT3_F_BOUNCE) = s.bounce;
+            if (s.bounce != RT3_NO_HIT) {
+                slot_store_vec(sm, r, RT3_F_OX, s.o); slot_store_vec(sm, r, RT3_F_DX, s.d); slot_store_vec(sm, r, RT3_F_TX, s.thr);
+                slot_word(sm, r, RT3_F_KEY) = s.key; slot_word(sm, r, RT3_F_PIX) = s.pix;
+                any = true;
+            }
         }
         if (RESIDENT) { if (!__any_sync(0xffffffffu, any)) { break; } }   /* warps run independently */
         else { if (!__syncthreads_or(any ? 1 : 0)) { break; } }           /* tiles are CTA-wide */
-
-        /* (2) closest hit of every live ray against the whole scene */
-        sweep_scene<true, RESIDENT, SPHERES_ONLY>(S, sm, phase, o, d, d, live, best);
-
-        /* (3) shade: miss -> sky * throughput; hit -> scatter */
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            if (!live[r]) { continue; }
-            rays++;
-            bool done = false;
-            rt3_vec3 L = v3(0.0f, 0.0f, 0.0f);
-            const rt3_vec3 dr = d[r];
-            if (best[r].prim == RT3_NO_HIT) {
-                float t = 0.5f * (dr.y + 1.0f);
-                float a = 1.0f - t;
-                L = thr[r] * v3(a * 1.0f + t * 0.5f, a * 1.0f + t * 0.7f, a * 1.0f + t * 1.0f);
-                done = true;
-            } else {
-                const uint32_t prim = best[r].prim;
-                rt3_vec3 hp = o[r] + best[r].t * dr;
-                rt3_vec3 outward;
-                if (prim < S.n_faces) {
-                    float4 fn = __ldg(&S.face_n[prim]);
-                    outward = v3(fn.x, fn.y, fn.z);
-                } else {
-                    float4 sp = __ldg(&S.spheres[prim - S.n_faces]);
-                    rt3_vec3 pc = hp - v3(sp.x, sp.y, sp.z);
-                    outward = v3(pc.x / sp.w, pc.y / sp.w, pc.z / sp.w);
-                }
-                const bool front = dot3(dr, outward) < 0.0f;
-                const rt3_vec3 n = front ? outward : -outward;
-                uint32_t kind = RT3_MAT_LAMBERTIAN;
-                rt3_vec3 albedo;
-                float fuzz = 0.0f, ior = 1.0f;
-                const uint32_t mi = __ldg(&S.prim_material[prim]);
-                if (mi == RT3_NO_HIT) {
-                    float4 c = __ldg(&S.prim_color[prim]);
-                    albedo = v3(c.x, c.y, c.z);
-                } else {
-                    float4 m0 = __ldg(&S.materials[2 * mi]), m1 = __ldg(&S.materials[2 * mi + 1]);
-                    kind = __float_as_uint(m0.x);
-                    albedo = v3(m0.y, m0.z, m0.w);
-                    fuzz = m1.x; ior = m1.y;
-                }
-                const uint32_t dim = RT3_DIM_BOUNCE0 + RT3_DIMS_PER_BOUNCE * bounce[r];
-                const uint32_t k = key[r];
-                rt3_vec3 nd;
-                if (kind == RT3_MAT_LAMBERTIAN) {
-                    rt3_vec3 uv = unit_vector(rt3_draw(k, dim + 0), rt3_draw(k, dim + 1));
-                    nd = n + uv;
-                    if (fabsf(nd.x) < 1e-8f && fabsf(nd.y) < 1e-8f && fabsf(nd.z) < 1e-8f) { nd = n; }
-                    thr[r] = thr[r] * albedo;
-                } else if (kind == RT3_MAT_METAL) {
-                    float dnn = dot3(dr, n);
-                    nd = dr - (2.0f * dnn) * n;
-                    float fz = fuzz < 1.0f ? fuzz : 1.0f;
-                    if (fz > 0.0f) {
-                        rt3_vec3 uv = unit_vector(rt3_draw(k, dim + 0), rt3_draw(k, dim + 1));
-                        float a = rt3_draw(k, dim + 2), b = rt3_draw(k, dim + 3), c = rt3_draw(k, dim + 4);
-                        float mx = a < b ? b : a;
-                        mx = mx < c ? c : mx;
-                        nd = nd + (fz * mx) * uv;
-                    }
-                    if (!(dot3(nd, n) > 0.0f)) { done = true; }
-                    thr[r] = thr[r] * albedo;
-                } else {
-                    float ratio = front ? (1.0f / ior) : ior;
-                    float cs = -dot3(dr, n);
-                    cs = cs < 1.0f ? cs : 1.0f;
-                    float s2 = 1.0f - cs * cs;
-                    float sn = sqrtf(s2 < 0.0f ? 0.0f : s2);
-                    bool cannot_refract = ratio * sn > 1.0f;
-                    float r0 = (1.0f - ratio) / (1.0f + ratio);
-                    r0 = r0 * r0;
-                    float w = 1.0f - cs;
-                    float w2 = w * w;
-                    float schlick = r0 + (1.0f - r0) * ((w2 * w2) * w);
-                    if (cannot_refract || schlick > rt3_draw(k, dim + 0)) {
-                        float dnn = dot3(dr, n);
-                        nd = dr - (2.0f * dnn) * n;
-                    } else {
-                        rt3_vec3 perp = ratio * (dr + cs * n);
-                        float kk = 1.0f - dot3(perp, perp);
-                        rt3_vec3 par = (-sqrtf(fabsf(kk))) * n;
-                        nd = perp + par;
-                    }
-                }
-                if (!done) {
-                    o[r] = hp;
-                    d[r] = normalize3(nd);
-                    bounce[r]++;
-                    if (bounce[r] >= P.max_depth) { done = true; } /* depth exhausted: radiance 0 */
-                }
-            }
-            if (done) {
-                unsigned long long qx = to_fixed(L.x), qy = to_fixed(L.y), qz = to_fixed(L.z);
-                unsigned long long* acc = accum + 3 * pix[r];
-                if (qx) { atomicAdd(acc + 0, qx); }
-                if (qy) { atomicAdd(acc + 1, qy); }
-                if (qz) { atomicAdd(acc + 2, qz); }
-                live[r] = false;
-            }
-        }
+        sweep_slots<RESIDENT, SPHERES_ONLY>(S, sm, phase);
     }
     for (int off = 16; off > 0; off >>= 1) { rays += __shfl_down_sync(0xffffffffu, rays, off); }
     if ((threadIdx.x & 31) == 0 && rays) { atomicAdd(&counters[1], rays); }
