@@ -191,7 +191,8 @@ __device__ __forceinline__ void exact_sphere_v4(uint32_t prim, float4 sp, rt3_ve
     float b = 2.0f * dot3(oc, d);
     float c = dot3(oc, oc) - sp.w * sp.w;
     float D = b * b - (4.0f * a) * c;
-    float t = (-b - sqrtf(fmaxf(D, 0.0f))) / (2.0f * a);
+    /* a miss takes the root of 1 instead: sqrtf of zero or a negative leaves the fast path of its implementation */
+    float t = (-b - sqrtf(D < 0.0f ? 1.0f : D)) / (2.0f * a);
     if (D >= 0 && t >= 0.0f && t < best.t) { best.prim = prim; best.t = t; }
 }
 
@@ -202,7 +203,7 @@ __device__ __forceinline__ void exact_sphere_path(uint32_t prim, float4 sp, rt3_
     float h = dot3(oc, d);
     float c = dot3(oc, oc) - sp.w * sp.w;
     float disc = h * h - c;
-    float sq = sqrtf(fmaxf(disc, 0.0f));
+    float sq = sqrtf(disc < 0.0f ? 1.0f : disc); /* a miss takes the root of 1: see exact_sphere_v4 */
     float t1 = -h - sq, t2 = -h + sq;
     bool ok1 = t1 >= RT3_TMIN && t1 < best.t;
     bool ok2 = t2 >= RT3_TMIN && t2 < best.t;
