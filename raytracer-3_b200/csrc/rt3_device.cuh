@@ -40,7 +40,7 @@
 #ifndef RT3_CTAS_PER_SM
 #define RT3_CTAS_PER_SM 5       /* register budget: 65536 / (128 * 5) = 102 per thread */
 #endif
-#define RT3_ITEM_CHUNK 1024u    /* path items a warp claims per global atomic */
+#define RT3_ITEM_CHUNK 256u     /* path items a warp claims per global atomic (short tail when the frame is split 8 ways) */
 
 /* Relative slack of the prefilter (64 units of 2^-24), applied to |c|^2 + r^2
  * per primitive (host, folded into R^2) and to |o|^2 per ray (folded into the
@@ -106,6 +106,8 @@ struct rt3_scene_view {
 };
 
 struct rt3_hit { float t; uint32_t prim; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
 /* Two-level conservative prefilter.
  *
@@ -239,7 +241,8 @@ __device__ __forceinline__ void slab_pair(const float4 A, const float2 B, const 
  * RT3_CHUNK_WORDS words of 32 primitives) starting at pair index `first_pair` of
  * `xy` / `w` (constant bank or a shared-memory tile). Bit 31 - k of a mask word
  * belongs to its k-th primitive. Words go to shared memory; `nz` gets one bit per
- * non-empty word. */
+ * word, set when the word is not empty, the first word of the chunk in the highest
+ * of the bits used (bit n_words - 1). */
 template <bool CONST_BANK>
 __device__ __forceinline__ void sweep_chunk(const float4* __restrict__ xy, const float2* __restrict__ w, uint32_t first_pair, uint32_t n_pairs,
                                             const rt3_ray_filter (&f)[RT3_RAYS], uint32_t* __restrict__ masks, uint32_t (&nz)[RT3_RAYS]) {
@@ -250,8 +253,8 @@ __device__ __forceinline__ void sweep_chunk(const float4* __restrict__ xy, const
         nou2[r] = make_float2(f[r].nou, f[r].nou); u1[r] = make_float2(f[r].u1, f[r].u1); u2[r] = make_float2(f[r].u2, f[r].u2);
         nz[r] = 0u;
     }
-    uint32_t wd = 0;
-    for (uint32_t done = 0; done < n_pairs; done += WORD_PAIRS, wd++) {
+    uint32_t waddr = smem_u32(masks) + threadIdx.x * 4u; /* this thread's word 0 of ray 0 */
+    for (uint32_t done = 0; done < n_pairs; done += WORD_PAIRS, waddr += RT3_CTA_THREADS * 4u) {
         uint32_t m[RT3_RAYS];
 #pragma unroll
         for (int r = 0; r < RT3_RAYS; r++) { m[r] = 0u; }
@@ -275,8 +278,8 @@ RT3_PRAGMA_UNROLL(RT3_UNROLL_PAIRS)
         }
 #pragma unroll
         for (int r = 0; r < RT3_RAYS; r++) {
-            masks[(r * RT3_CHUNK_WORDS + wd) * RT3_CTA_THREADS + threadIdx.x] = m[r];
-            nz[r] |= (m[r] != 0u ? 1u : 0u) << wd;
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(waddr + (uint32_t) (r * RT3_CHUNK_WORDS * RT3_CTA_THREADS * 4)), "r"(m[r]) : "memory");
+            nz[r] = (nz[r] << 1) + (m[r] < 1u ? m[r] : 1u);
         }
     }
 }
@@ -288,15 +291,17 @@ RT3_PRAGMA_UNROLL(RT3_UNROLL_PAIRS)
  * points at this thread's first word of the ray. Padding records never survive
  * level 1, so every bit is a real primitive. */
 template <bool PATH_MODE, bool SPHERES_ONLY>
-__device__ __forceinline__ void drain_chunk(const rt3_scene_view& S, uint32_t first_prim, const rt3_ray_filter& f, rt3_vec3 o, rt3_vec3 d,
-                                            const uint32_t* __restrict__ masks, uint32_t nz, rt3_hit& best) {
+__device__ __forceinline__ void drain_chunk(const rt3_scene_view& S, uint32_t first_prim, uint32_t n_words, const rt3_ray_filter& f, rt3_vec3 o,
+                                            rt3_vec3 d, const uint32_t* __restrict__ masks, uint32_t nz, rt3_hit& best) {
     uint32_t m = 0u, word_prim = 0u;
+    const uint32_t maddr = smem_u32(masks);
     for (;;) {
         if (m == 0u) {
             if (nz == 0u) { break; }
-            const uint32_t wd = (uint32_t) __ffs((int) nz) - 1u;
-            nz &= nz - 1u;
-            m = masks[wd * RT3_CTA_THREADS];
+            const uint32_t b = 31u - (uint32_t) __clz((int) nz); /* highest bit = first non-empty word */
+            nz ^= 1u << b;
+            const uint32_t wd = n_words - 1u - b;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(maddr + wd * (RT3_CTA_THREADS * 4u)));
             word_prim = first_prim + wd * RT3_WORD_PRIMS;
         }
         const uint32_t k = (uint32_t) __clz((int) m);
@@ -324,11 +329,12 @@ __device__ __forceinline__ void sweep_range(const rt3_scene_view& S, const float
     const uint32_t n_pairs = n_prims / 2;
     for (uint32_t p0 = 0, w0 = 0; p0 < n_pairs; p0 += CHUNK_PAIRS, w0 += RT3_CHUNK_WORDS) {
         uint32_t nz[RT3_RAYS];
-        sweep_chunk<CONST_BANK>(xy, w, first_pair + p0, n_pairs - p0 < CHUNK_PAIRS ? n_pairs - p0 : CHUNK_PAIRS, f, masks, nz);
+        const uint32_t np = n_pairs - p0 < CHUNK_PAIRS ? n_pairs - p0 : CHUNK_PAIRS;
+        sweep_chunk<CONST_BANK>(xy, w, first_pair + p0, np, f, masks, nz);
 #pragma unroll
         for (int r = 0; r < RT3_RAYS; r++) {
             if (!live[r]) { nz[r] = 0u; }
-            drain_chunk<PATH_MODE, SPHERES_ONLY>(S, first_prim + w0 * RT3_WORD_PRIMS, f[r], o[r], d[r],
+            drain_chunk<PATH_MODE, SPHERES_ONLY>(S, first_prim + w0 * RT3_WORD_PRIMS, (np + RT3_WORD_PRIMS / 2 - 1) / (RT3_WORD_PRIMS / 2), f[r], o[r], d[r],
                                                  masks + r * RT3_CHUNK_WORDS * RT3_CTA_THREADS + threadIdx.x, nz[r], best[r]);
         }
     }
@@ -336,7 +342,6 @@ __device__ __forceinline__ void sweep_range(const rt3_scene_view& S, const float
 
 /* ---- mbarrier / bulk-copy (TMA) helpers for streamed tiles ---------------- */
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

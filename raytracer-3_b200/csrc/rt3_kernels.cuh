@@ -156,8 +156,9 @@ __device__ __forceinline__ void slot_filters(const rt3_scene_view& S, const rt3_
 
 /* Drains one chunk for every slot, one slot at a time from a single copy of the code. */
 template <bool SPHERES_ONLY>
-__device__ __forceinline__ void drain_slots(const rt3_scene_view& S, const rt3_smem_view& sm, uint32_t first_prim,
+__device__ __forceinline__ void drain_slots(const rt3_scene_view& S, const rt3_smem_view& sm, uint32_t first_prim, uint32_t n_pairs,
                                             const rt3_ray_filter (&f)[RT3_RAYS], const uint32_t (&nz)[RT3_RAYS]) {
+    const uint32_t n_words = (n_pairs + RT3_WORD_PRIMS / 2 - 1) / (RT3_WORD_PRIMS / 2);
     static_assert(RT3_RAYS * RT3_CHUNK_WORDS <= 64, "survivor summaries are packed into 64 bits");
     unsigned long long packed = 0ull;
 #pragma unroll
@@ -170,7 +171,7 @@ __device__ __forceinline__ void drain_slots(const rt3_scene_view& S, const rt3_s
         rt3_ray_filter fr = f[0]; /* level 2 is only needed for faces; rebuilt below for the slot at hand */
         const rt3_vec3 o = slot_vec(sm, r, RT3_F_OX), d = slot_vec(sm, r, RT3_F_DX);
         if (!SPHERES_ONLY) { fr = make_ray_filter(S, o, d); }
-        drain_chunk<true, SPHERES_ONLY>(S, first_prim, fr, o, d, sm.masks + r * RT3_CHUNK_WORDS * RT3_CTA_THREADS + threadIdx.x, mine, best);
+        drain_chunk<true, SPHERES_ONLY>(S, first_prim, n_words, fr, o, d, sm.masks + r * RT3_CHUNK_WORDS * RT3_CTA_THREADS + threadIdx.x, mine, best);
         slot_word(sm, r, RT3_F_BEST_T) = __float_as_uint(best.t); slot_word(sm, r, RT3_F_BEST_PRIM) = best.prim;
     }
 }
@@ -187,8 +188,9 @@ __device__ __forceinline__ void sweep_slots(const rt3_scene_view& S, const rt3_s
         const uint32_t n_pairs = S.n_prims_padded / 2;
         for (uint32_t p0 = 0; p0 < n_pairs; p0 += CHUNK_PAIRS) {
             uint32_t nz[RT3_RAYS];
-            sweep_chunk<true>(nullptr, nullptr, p0, n_pairs - p0 < CHUNK_PAIRS ? n_pairs - p0 : CHUNK_PAIRS, f, sm.masks, nz);
-            drain_slots<SPHERES_ONLY>(S, sm, 2u * p0, f, nz);
+            const uint32_t np = n_pairs - p0 < CHUNK_PAIRS ? n_pairs - p0 : CHUNK_PAIRS;
+            sweep_chunk<true>(nullptr, nullptr, p0, np, f, sm.masks, nz);
+            drain_slots<SPHERES_ONLY>(S, sm, 2u * p0, np, f, nz);
         }
         return;
     }
@@ -205,8 +207,9 @@ __device__ __forceinline__ void sweep_slots(const rt3_scene_view& S, const rt3_s
         const float2* w = sm.tile_w + (size_t) stage * RT3_TILE_PAIRS;
         for (uint32_t p0 = 0; p0 < n_pairs; p0 += CHUNK_PAIRS) {
             uint32_t nz[RT3_RAYS];
-            sweep_chunk<false>(xy, w, p0, n_pairs - p0 < CHUNK_PAIRS ? n_pairs - p0 : CHUNK_PAIRS, f, sm.masks, nz);
-            drain_slots<SPHERES_ONLY>(S, sm, first + 2u * p0, f, nz);
+            const uint32_t np = n_pairs - p0 < CHUNK_PAIRS ? n_pairs - p0 : CHUNK_PAIRS;
+            sweep_chunk<false>(xy, w, p0, np, f, sm.masks, nz);
+            drain_slots<SPHERES_ONLY>(S, sm, first + 2u * p0, np, f, nz);
         }
         __syncthreads();
     }
@@ -284,15 +287,8 @@ reference_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, uint32_t* __re
  * Path tracer
  * ------------------------------------------------------------------------ */
 
-#ifdef RT3_NOINLINE_RNG
-__device__ __noinline__ float draw_ni(uint32_t k, uint32_t dim) { return rt3_draw(k, dim); }
-#define rt3_draw draw_ni
-#define RT3_UV_INLINE __noinline__
-#else
-#define RT3_UV_INLINE __forceinline__
-#endif
 /* Uniform point on the unit sphere: z = 1 - 2 xi1, phi = 2 pi xi2. */
-__device__ RT3_UV_INLINE rt3_vec3 unit_vector(float xi1, float xi2) {
+__device__ __forceinline__ rt3_vec3 unit_vector(float xi1, float xi2) {
     float z = 1.0f - 2.0f * xi1;
     float rr = 1.0f - z * z;
     rr = sqrtf(rr < 0.0f ? 0.0f : rr);
