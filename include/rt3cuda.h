@@ -131,6 +131,9 @@ typedef struct rt3_camera {
 
 #define RT3_FLAG_NO_JITTER 0x1u /* pathtrace: sample pixel centres (deterministic primary rays) */
 #define RT3_FLAG_NO_GAMMA 0x2u  /* pathtrace: resolve the linear mean instead of its square root */
+#define RT3_FLAG_BVH 0x4u       /* closest hits through a bounding-volume hierarchy built on the device at the first such render
+                                 * after rt3_scene_upload, instead of the reference's brute-force loop over every primitive
+                                 * (SequentialRenderer.cpp:55-95). The frame and the AOVs are identical, bit for bit. */
 
 typedef struct rt3_params {
     uint32_t width;
@@ -160,6 +163,12 @@ typedef struct rt3_stats {
     uint64_t face_tests;    /* ray-triangle tests = rays * n_faces */
     uint32_t kernel_launches;
     uint32_t rows_rendered; /* rows owned by this partition */
+    /* RT3_FLAG_BVH renders: sphere_tests / face_tests are 0 (no brute-force sweep) and these count the traversal */
+    uint64_t accel_node_visits; /* hierarchy nodes read */
+    uint64_t accel_prim_tests;  /* exact ray-primitive tests run in leaves */
+    double accel_build_ms;      /* device time of the hierarchy build for the current scene */
+    uint32_t accel;             /* 1 if the most recent render used the hierarchy */
+    uint32_t _pad;
 } rt3_stats;
 
 typedef struct rt3_ctx rt3_ctx;

@@ -16,7 +16,7 @@ CORE_LIB_PATH = os.path.join(_HERE, "csrc", "librt3cuda.so")
 
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 MODE_REFERENCE, MODE_PATHTRACE = 0, 1
-FLAG_NO_JITTER, FLAG_NO_GAMMA = 0x1, 0x2
+FLAG_NO_JITTER, FLAG_NO_GAMMA, FLAG_BVH = 0x1, 0x2, 0x4
 NO_HIT = 0xFFFFFFFF
 
 # numpy record layouts that mirror rt3_face (GFace, reference Vertex.hpp:39-51),
@@ -74,6 +74,8 @@ class Stats(C.Structure):
         ("device_ms", C.c_double), ("trace_kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("rays", C.c_uint64), ("sphere_tests", C.c_uint64), ("face_tests", C.c_uint64),
         ("kernel_launches", C.c_uint32), ("rows_rendered", C.c_uint32),
+        ("accel_node_visits", C.c_uint64), ("accel_prim_tests", C.c_uint64), ("accel_build_ms", C.c_double),
+        ("accel", C.c_uint32), ("_pad", C.c_uint32),
     ]
 
 

@@ -22,6 +22,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "rt3_kernels.cuh"
 
 namespace {
@@ -75,6 +77,13 @@ struct rt3_ctx {
     DeviceBuffer<float2> pair_w;
     DeviceBuffer<uint32_t> prim_material, prim_entity;
 
+    /* hierarchy (RT3_FLAG_BVH): primitive boxes are uploaded with the scene, the tree is built on first use */
+    DeviceBuffer<float4> prim_lo, prim_hi, bvh_nodes;
+    float centroid_min[3] = { 0, 0, 0 }, centroid_max[3] = { 0, 0, 0 };
+    bool bvh_ready = false;
+    rt3_bvh_view bvh{};
+    double bvh_build_ms = 0.0;
+
     DeviceBuffer<uint32_t> frame, aov_prim, aov_entity;
     DeviceBuffer<float> aov_t;
     DeviceBuffer<unsigned long long> accum, counters;
@@ -120,6 +129,11 @@ int make_kparams(const rt3_params* p, rt3_kparams* k) {
 float round_down(double v) {
     float f = (float) v;
     if ((double) f > v) { f = std::nextafterf(f, -std::numeric_limits<float>::infinity()); }
+    return f;
+}
+float round_up(double v) {
+    float f = (float) v;
+    if ((double) f < v) { f = std::nextafterf(f, std::numeric_limits<float>::infinity()); }
     return f;
 }
 
@@ -255,22 +269,22 @@ template <class K> int configure(K kernel, size_t smem, int* blocks_per_sm) {
     return RT3_OK;
 }
 
-template <bool RESIDENT, bool SPHERES_ONLY>
+template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL>
 int launch_reference(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp, size_t smem, uint32_t* frame, uint32_t* prim,
                      uint32_t* ent, float* t, cudaStream_t stream) {
-    int rc = configure(reference_kernel<RESIDENT, SPHERES_ONLY>, smem, nullptr);
+    int rc = configure(reference_kernel<RESIDENT, SPHERES_ONLY, ACCEL>, smem, nullptr);
     if (rc != RT3_OK) { return rc; }
     unsigned long long per_cta = (unsigned long long) RT3_CTA_THREADS * RT3_RAYS;
     unsigned grid = (unsigned) ((kp.n_pixels + per_cta - 1) / per_cta);
-    reference_kernel<RESIDENT, SPHERES_ONLY><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, cam, kp, frame, prim, ent, t, ctx->counters.ptr);
+    reference_kernel<RESIDENT, SPHERES_ONLY, ACCEL><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, ctx->bvh, cam, kp, frame, prim, ent, t, ctx->counters.ptr);
     RT3_CUDA(cudaGetLastError());
     return RT3_OK;
 }
 
-template <bool RESIDENT, bool SPHERES_ONLY>
+template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL>
 int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp, size_t smem, cudaStream_t stream) {
     int per_sm = 0;
-    int rc = configure(pathtrace_kernel<RESIDENT, SPHERES_ONLY>, smem, &per_sm);
+    int rc = configure(pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL>, smem, &per_sm);
     if (rc != RT3_OK) { return rc; }
     if (per_sm < 1) { return fail(RT3_ERR_CUDA, "pathtrace kernel does not fit on an SM (smem %zu)", smem); }
     /* persistent grid: every SM full, no more CTAs than there are CTAs' worth of paths */
@@ -278,8 +292,68 @@ int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
     unsigned long long want = (kp.n_items + per_cta - 1) / per_cta;
     unsigned grid = (unsigned) ctx->sm_count * (unsigned) per_sm;
     if (want < grid) { grid = want ? (unsigned) want : 1u; }
-    pathtrace_kernel<RESIDENT, SPHERES_ONLY><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, cam, kp, ctx->accum.ptr, ctx->counters.ptr);
+    pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, ctx->bvh, cam, kp, ctx->accum.ptr, ctx->counters.ptr);
     RT3_CUDA(cudaGetLastError());
+    return RT3_OK;
+}
+
+/* Builds the hierarchy over the uploaded primitive boxes (first RT3_FLAG_BVH render after an upload):
+ * Morton codes of the box centres, radix sort (CUB), Karras' radix tree, bottom-up refit. All on the
+ * device; the scratch arrays are released when the node array is complete. */
+int build_bvh(rt3_ctx* ctx, cudaStream_t stream) {
+    if (ctx->bvh_ready) { return RT3_OK; }
+    const uint32_t n = ctx->view.n_prims;
+    ctx->bvh.n_prims = n;
+    ctx->bvh.nodes = nullptr;
+    ctx->bvh.root = n == 1 ? ~0 : 0;
+    ctx->bvh.ray_margin = sqrtf(RT3_FILTER_SLACK) * 1.000001f;
+    ctx->bvh_build_ms = 0.0;
+    if (n < 2) { ctx->bvh_ready = true; return RT3_OK; }
+    DeviceBuffer<unsigned long long> keys_in, keys_out;
+    DeviceBuffer<uint32_t> vals_in, vals_out, arrived;
+    DeviceBuffer<int> child, node_parent, leaf_parent;
+    DeviceBuffer<float4> box_lo, box_hi;
+    DeviceBuffer<unsigned char> temp;
+    int rc;
+    if ((rc = keys_in.reserve(n)) != RT3_OK || (rc = keys_out.reserve(n)) != RT3_OK || (rc = vals_in.reserve(n)) != RT3_OK ||
+        (rc = vals_out.reserve(n)) != RT3_OK || (rc = arrived.reserve(n)) != RT3_OK || (rc = child.reserve(2 * (size_t) n)) != RT3_OK ||
+        (rc = node_parent.reserve(n)) != RT3_OK || (rc = leaf_parent.reserve(n)) != RT3_OK || (rc = box_lo.reserve(n)) != RT3_OK ||
+        (rc = box_hi.reserve(n)) != RT3_OK || (rc = ctx->bvh_nodes.reserve(4 * (size_t) (n - 1))) != RT3_OK) {
+        return rc;
+    }
+    size_t temp_bytes = 0;
+    RT3_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in.ptr, keys_out.ptr, vals_in.ptr, vals_out.ptr, (int) n, 0, 63, stream));
+    if ((rc = temp.reserve(temp_bytes ? temp_bytes : 1)) != RT3_OK) { return rc; }
+    float3 cmin = make_float3(ctx->centroid_min[0], ctx->centroid_min[1], ctx->centroid_min[2]), cscale;
+    {
+        const float ex[3] = { ctx->centroid_max[0] - ctx->centroid_min[0], ctx->centroid_max[1] - ctx->centroid_min[1],
+                              ctx->centroid_max[2] - ctx->centroid_min[2] };
+        cscale = make_float3(ex[0] > 0 ? 1.0f / ex[0] : 0.0f, ex[1] > 0 ? 1.0f / ex[1] : 0.0f, ex[2] > 0 ? 1.0f / ex[2] : 0.0f);
+    }
+    cudaEvent_t e0, e1;
+    RT3_CUDA(cudaEventCreate(&e0));
+    RT3_CUDA(cudaEventCreate(&e1));
+    RT3_CUDA(cudaEventRecord(e0, stream));
+    const unsigned grid = (n + 255u) / 256u;
+    bvh_morton_kernel<<<grid, 256, 0, stream>>>(n, ctx->prim_lo.ptr, ctx->prim_hi.ptr, cmin, cscale, keys_in.ptr, vals_in.ptr);
+    RT3_CUDA(cudaGetLastError());
+    RT3_CUDA(cub::DeviceRadixSort::SortPairs(temp.ptr, temp_bytes, keys_in.ptr, keys_out.ptr, vals_in.ptr, vals_out.ptr, (int) n, 0, 63, stream));
+    RT3_CUDA(cudaMemsetAsync(arrived.ptr, 0, (size_t) n * sizeof(uint32_t), stream));
+    bvh_tree_kernel<<<grid, 256, 0, stream>>>((int) n, keys_out.ptr, child.ptr, node_parent.ptr, leaf_parent.ptr);
+    RT3_CUDA(cudaGetLastError());
+    bvh_refit_kernel<<<grid, 256, 0, stream>>>((int) n, vals_out.ptr, ctx->prim_lo.ptr, ctx->prim_hi.ptr, child.ptr, node_parent.ptr, leaf_parent.ptr,
+                                              box_lo.ptr, box_hi.ptr, arrived.ptr, ctx->bvh_nodes.ptr);
+    RT3_CUDA(cudaGetLastError());
+    RT3_CUDA(cudaEventRecord(e1, stream));
+    RT3_CUDA(cudaStreamSynchronize(stream)); /* the scratch arrays go out of scope */
+    float ms = 0.f;
+    RT3_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    keys_in.release(); keys_out.release(); vals_in.release(); vals_out.release(); arrived.release(); child.release();
+    node_parent.release(); leaf_parent.release(); box_lo.release(); box_hi.release(); temp.release();
+    ctx->bvh_build_ms = ms;
+    ctx->bvh.nodes = ctx->bvh_nodes.ptr;
+    ctx->bvh_ready = true;
     return RT3_OK;
 }
 
@@ -307,6 +381,14 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     rt3_kparams kp = kp_in;
     bool resident = false;
     size_t smem = render_smem_bytes(ctx->view, params->mode == RT3_MODE_PATHTRACE, &resident);
+    const bool accel = (params->flags & RT3_FLAG_BVH) != 0;
+    if (accel) {
+        int brc = build_bvh(ctx, stream);
+        if (brc != RT3_OK) { return brc; }
+        resident = false; /* no constant-bank records needed */
+        smem = rt3_smem_bytes(true, params->mode == RT3_MODE_PATHTRACE);
+    }
+    ctx->stats.accel = accel ? 1u : 0u;
     kp.resident = resident ? 1u : 0u;
     ctx->stats.kernel_launches = 0;
     ctx->stats.rows_rendered = kp.owned_rows;
@@ -316,7 +398,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     int rc = RT3_OK;
     if (resident && kp.n_pixels != 0 && (rc = claim_constant_bank(ctx, stream)) != RT3_OK) { return rc; }
     RT3_CUDA(cudaEventRecord(ctx->ev_begin, stream));
-    RT3_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 2 * sizeof(unsigned long long), stream));
+    RT3_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 4 * sizeof(unsigned long long), stream));
     if (kp.n_pixels == 0) {
         RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
         RT3_CUDA(cudaEventRecord(ctx->ev_k1, stream));
@@ -326,10 +408,11 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     if (params->mode == RT3_MODE_REFERENCE) {
         RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
         const bool so = ctx->view.n_faces == 0;
-        rc = resident ? (so ? launch_reference<true, true>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream)
-                            : launch_reference<true, false>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream))
-                      : (so ? launch_reference<false, true>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream)
-                            : launch_reference<false, false>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream));
+        rc = accel ? launch_reference<true, false, true>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream)
+           : resident ? (so ? launch_reference<true, true, false>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream)
+                            : launch_reference<true, false, false>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream))
+                      : (so ? launch_reference<false, true, false>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream)
+                            : launch_reference<false, false, false>(ctx, *cam, kp, smem, device_frame, prim, ent, t, stream));
         if (rc != RT3_OK) { return rc; }
         RT3_CUDA(cudaEventRecord(ctx->ev_k1, stream));
         RT3_CUDA(cudaEventRecord(ctx->ev_end, stream));
@@ -344,8 +427,9 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     RT3_CUDA(cudaGetLastError());
     RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
     const bool spheres_only = ctx->view.n_faces == 0;
-    rc = resident ? (spheres_only ? launch_pathtrace<true, true>(ctx, *cam, kp, smem, stream) : launch_pathtrace<true, false>(ctx, *cam, kp, smem, stream))
-                  : (spheres_only ? launch_pathtrace<false, true>(ctx, *cam, kp, smem, stream) : launch_pathtrace<false, false>(ctx, *cam, kp, smem, stream));
+    rc = accel ? launch_pathtrace<true, false, true>(ctx, *cam, kp, smem, stream)
+       : resident ? (spheres_only ? launch_pathtrace<true, true, false>(ctx, *cam, kp, smem, stream) : launch_pathtrace<true, false, false>(ctx, *cam, kp, smem, stream))
+                  : (spheres_only ? launch_pathtrace<false, true, false>(ctx, *cam, kp, smem, stream) : launch_pathtrace<false, false, false>(ctx, *cam, kp, smem, stream));
     if (rc != RT3_OK) { return rc; }
     RT3_CUDA(cudaEventRecord(ctx->ev_k1, stream));
     unsigned resolve_grid = (unsigned) ((kp.n_pixels + 255ull) / 256ull);
@@ -416,7 +500,7 @@ int collect_stats(rt3_ctx* ctx) {
     if (!ctx->stats_pending) { return RT3_OK; }
     RT3_CUDA(cudaSetDevice(ctx->device));
     RT3_CUDA(cudaStreamSynchronize(ctx->last_stream));
-    unsigned long long counters[2] = { 0, 0 };
+    unsigned long long counters[4] = { 0, 0, 0, 0 };
     RT3_CUDA(cudaMemcpy(counters, ctx->counters.ptr, sizeof counters, cudaMemcpyDeviceToHost));
     float ms = 0.0f, ms_k = 0.0f, ms_copy = 0.0f;
     RT3_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
@@ -429,6 +513,13 @@ int collect_stats(rt3_ctx* ctx) {
     ctx->stats.rays = counters[1];
     ctx->stats.sphere_tests = counters[1] * ctx->view.n_spheres;
     ctx->stats.face_tests = counters[1] * ctx->view.n_faces;
+    if (ctx->stats.accel) {
+        /* through the hierarchy only the leaves reached are tested */
+        ctx->stats.sphere_tests = 0; ctx->stats.face_tests = 0;
+    }
+    ctx->stats.accel_node_visits = counters[2];
+    ctx->stats.accel_prim_tests = counters[3];
+    ctx->stats.accel_build_ms = ctx->bvh_build_ms;
     ctx->stats_pending = false;
     return RT3_OK;
 }
@@ -462,7 +553,7 @@ int rt3_create(rt3_ctx** out, int device) {
     if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_copy); }
     if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_k0); }
     if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_k1); }
-    if (err == cudaSuccess && ctx->counters.reserve(2) != RT3_OK) { err = cudaErrorMemoryAllocation; }
+    if (err == cudaSuccess && ctx->counters.reserve(4) != RT3_OK) { err = cudaErrorMemoryAllocation; }
     if (err != cudaSuccess) {
         rt3_destroy(ctx);
         return fail(RT3_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(err));
@@ -475,6 +566,7 @@ int rt3_destroy(rt3_ctx* ctx) {
     if (!ctx) { return RT3_OK; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
+    ctx->prim_lo.release(); ctx->prim_hi.release(); ctx->bvh_nodes.release();
     ctx->pair_xy.release(); ctx->pair_w.release(); ctx->filt3.release(); ctx->face_n.release(); ctx->face_p1.release(); ctx->face_p2.release(); ctx->face_p3.release();
     ctx->spheres.release(); ctx->prim_color.release(); ctx->materials.release(); ctx->prim_material.release(); ctx->prim_entity.release();
     ctx->frame.release(); ctx->aov_prim.release(); ctx->aov_entity.release(); ctx->aov_t.release(); ctx->accum.release(); ctx->counters.release();
@@ -500,6 +592,8 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     const uint32_t nf = s->n_faces, ns = s->n_spheres, np = nf + ns;
     const uint32_t np_pad = (np + RT3_PAD_PRIMS - 1) / RT3_PAD_PRIMS * RT3_PAD_PRIMS;
     std::vector<Bound> bounds(np);
+    std::vector<float4> box_lo(np ? np : 1), box_hi(np ? np : 1); /* hierarchy leaves: the primitive's box, widened like its bounding sphere */
+    const float finf = std::numeric_limits<float>::infinity();
     std::vector<float4> fn(nf), p1(nf), p2(nf), p3(nf), sph(ns), color(np), mats((size_t) s->n_materials * 2);
     std::vector<uint32_t> pmat(np, RT3_NO_HIT), pent(np, 0u);
 
@@ -520,10 +614,20 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
         p3[i] = make_float4(c.x, c.y, c.z, 0.f);
         double da[3] = { a.x, a.y, a.z }, db[3] = { b.x, b.y, b.z }, dc[3] = { c.x, c.y, c.z }, centre[3], radius;
         triangle_bound(da, db, dc, centre, &radius);
+        const double r_geom = radius;
         /* faces: the exact test accepts hit points up to a few ulps of the coordinates outside the triangle;
          * widen the bounding sphere by 2^-10 relative and 2^-16 (|c| + r) absolute on top of the common slack */
         radius = radius * (1.0 + 1.0 / 1024.0) + (std::sqrt(centre[0] * centre[0] + centre[1] * centre[1] + centre[2] * centre[2]) + radius) / 65536.0;
         bounds[i] = make_bound(centre, radius);
+        if (bounds[i].R2 >= 0) {
+            const double m = std::sqrt(bounds[i].R2) - r_geom; /* the same widening around the triangle's own box */
+            box_lo[i] = make_float4(round_down(std::min({ da[0], db[0], dc[0] }) - m), round_down(std::min({ da[1], db[1], dc[1] }) - m),
+                                    round_down(std::min({ da[2], db[2], dc[2] }) - m), 0.f);
+            box_hi[i] = make_float4(round_up(std::max({ da[0], db[0], dc[0] }) + m), round_up(std::max({ da[1], db[1], dc[1] }) + m),
+                                    round_up(std::max({ da[2], db[2], dc[2] }) + m), 0.f);
+        } else {
+            box_lo[i] = make_float4(finf, finf, finf, 0.f); box_hi[i] = make_float4(-finf, -finf, -finf, 0.f); /* empty */
+        }
         color[i] = make_float4(f.color[0], f.color[1], f.color[2], 0.f);
         if (s->face_material) {
             if (s->face_material[i] >= s->n_materials) { return fail(RT3_ERR_INVALID, "face %u: material %u out of range", i, s->face_material[i]); }
@@ -536,6 +640,13 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
         sph[i] = make_float4(sp.cx, sp.cy, sp.cz, sp.r);
         double c[3] = { sp.cx, sp.cy, sp.cz };
         bounds[nf + i] = make_bound(c, std::fabs((double) sp.r));
+        if (bounds[nf + i].R2 >= 0) {
+            const double R = std::sqrt(bounds[nf + i].R2);
+            box_lo[nf + i] = make_float4(round_down(c[0] - R), round_down(c[1] - R), round_down(c[2] - R), 0.f);
+            box_hi[nf + i] = make_float4(round_up(c[0] + R), round_up(c[1] + R), round_up(c[2] + R), 0.f);
+        } else {
+            box_lo[nf + i] = make_float4(finf, finf, finf, 0.f); box_hi[nf + i] = make_float4(-finf, -finf, -finf, 0.f);
+        }
         if (s->sphere_color) { color[nf + i] = make_float4(s->sphere_color[3 * i], s->sphere_color[3 * i + 1], s->sphere_color[3 * i + 2], 0.f); }
         else { color[nf + i] = make_float4(1.f, 1.f, 1.f, 0.f); }
         if (s->sphere_material) {
@@ -590,6 +701,22 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     }
 
     int rc;
+    {
+        /* box of the finite box centres: the Morton grid of the hierarchy build */
+        float cmin[3] = { finf, finf, finf }, cmax[3] = { -finf, -finf, -finf };
+        for (uint32_t i = 0; i < np; i++) {
+            if (!(box_lo[i].x <= box_hi[i].x)) { continue; }
+            const float cx[3] = { 0.5f * box_lo[i].x + 0.5f * box_hi[i].x, 0.5f * box_lo[i].y + 0.5f * box_hi[i].y, 0.5f * box_lo[i].z + 0.5f * box_hi[i].z };
+            for (int k = 0; k < 3; k++) { if (std::isfinite(cx[k])) { cmin[k] = std::min(cmin[k], cx[k]); cmax[k] = std::max(cmax[k], cx[k]); } }
+        }
+        for (int k = 0; k < 3; k++) {
+            if (!(cmin[k] <= cmax[k])) { cmin[k] = cmax[k] = 0.0f; }
+            ctx->centroid_min[k] = cmin[k]; ctx->centroid_max[k] = cmax[k];
+        }
+    }
+    ctx->bvh_ready = false;
+    if ((rc = upload(ctx->prim_lo, box_lo, ctx->stream)) != RT3_OK) { return rc; }
+    if ((rc = upload(ctx->prim_hi, box_hi, ctx->stream)) != RT3_OK) { return rc; }
     if ((rc = upload(ctx->pair_xy, pair_xy, ctx->stream)) != RT3_OK) { return rc; }
     if ((rc = upload(ctx->pair_w, pair_w, ctx->stream)) != RT3_OK) { return rc; }
     if ((rc = upload(ctx->filt3, filt3, ctx->stream)) != RT3_OK) { return rc; }

@@ -163,9 +163,19 @@ __device__ __forceinline__ bool line_test(const float4 rec, const rt3_ray_filter
     return !(d2 > 0.0f);
 }
 
+/* Does a hit (t, prim) replace `best`? The reference walks the primitives in ascending order and
+ * rejects t >= min_t (SequentialRenderer.cpp:71), so among equal distances the lowest id wins.
+ * ORDERED callers visit primitives in ascending order themselves and need only the strict compare;
+ * the others (hierarchy traversal) break ties on the id explicitly. */
+template <bool ORDERED>
+__device__ __forceinline__ bool closer(float t, uint32_t prim, const rt3_hit& best) {
+    return ORDERED ? t < best.t : (t < best.t || (t == best.t && prim < best.prim));
+}
+
 /* Exact ray-triangle test: the body of the reference's face loop,
  * SequentialRenderer.cpp:55-95, for one candidate face. tmin = 0 reproduces
  * the reference (`t < 0` rejected); the bounce loop passes 0.001. */
+template <bool ORDERED>
 __device__ __forceinline__ void exact_face(const rt3_scene_view& S, uint32_t i, rt3_vec3 o, rt3_vec3 d, float tmin, rt3_hit& best) {
     float4 fn = __ldg(&S.face_n[i]);
     rt3_vec3 n = v3(fn.x, fn.y, fn.z);
@@ -175,7 +185,7 @@ __device__ __forceinline__ void exact_face(const rt3_scene_view& S, uint32_t i, 
     rt3_vec3 p1 = v3(a1.x, a1.y, a1.z), p2 = v3(a2.x, a2.y, a2.z), p3 = v3(a3.x, a3.y, a3.z);
     float pd = fn.w; /* dot3(n, p1), evaluated once at upload in the same order */
     float t = (pd - dot3(n, o)) / dot3(n, d);
-    if (t < tmin || t >= best.t) { return; }
+    if (t < tmin || !closer<ORDERED>(t, i, best)) { return; } /* a NaN t ends here too; the reference's falls through to the inside tests, which fail */
     rt3_vec3 hp = o + t * d;
     rt3_vec3 a = cross3(p2 - p1, hp - p1);
     rt3_vec3 b = cross3(p3 - p2, hp - p2);
@@ -187,6 +197,7 @@ __device__ __forceinline__ void exact_face(const rt3_scene_view& S, uint32_t i, 
  * (abc form, near root, t >= 0), un-normalised direction. Written without
  * branches: the lanes of a warp walk different survivor lists, and some lane
  * hits in nearly every step. */
+template <bool ORDERED>
 __device__ __forceinline__ void exact_sphere_v4(uint32_t prim, float4 sp, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
     rt3_vec3 oc = o - v3(sp.x, sp.y, sp.z);
     float a = dot3(d, d);
@@ -195,11 +206,12 @@ __device__ __forceinline__ void exact_sphere_v4(uint32_t prim, float4 sp, rt3_ve
     float D = b * b - (4.0f * a) * c;
     /* a miss takes the root of 1 instead: sqrtf of zero or a negative leaves the fast path of its implementation */
     float t = (-b - sqrtf(D < 0.0f ? 1.0f : D)) / (2.0f * a);
-    if (D >= 0 && t >= 0.0f && t < best.t) { best.prim = prim; best.t = t; }
+    if (D >= 0 && t >= 0.0f && closer<ORDERED>(t, prim, best)) { best.prim = prim; best.t = t; }
 }
 
 /* Exact ray-sphere test, bounce loop: half-b form with a unit direction, near
  * then far root, accepted iff tmin <= t < best. */
+template <bool ORDERED>
 __device__ __forceinline__ void exact_sphere_path(uint32_t prim, float4 sp, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
     rt3_vec3 oc = o - v3(sp.x, sp.y, sp.z);
     float h = dot3(oc, d);
@@ -207,8 +219,8 @@ __device__ __forceinline__ void exact_sphere_path(uint32_t prim, float4 sp, rt3_
     float disc = h * h - c;
     float sq = sqrtf(disc < 0.0f ? 1.0f : disc); /* a miss takes the root of 1: see exact_sphere_v4 */
     float t1 = -h - sq, t2 = -h + sq;
-    bool ok1 = t1 >= RT3_TMIN && t1 < best.t;
-    bool ok2 = t2 >= RT3_TMIN && t2 < best.t;
+    bool ok1 = t1 >= RT3_TMIN && closer<ORDERED>(t1, prim, best);
+    bool ok2 = t2 >= RT3_TMIN && closer<ORDERED>(t2, prim, best);
     if (disc >= 0.0f && (ok1 || ok2)) { best.prim = prim; best.t = ok1 ? t1 : t2; }
 }
 
@@ -309,10 +321,10 @@ __device__ __forceinline__ void drain_chunk(const rt3_scene_view& S, uint32_t fi
         const uint32_t prim = word_prim + k;
         if (SPHERES_ONLY || prim >= S.n_faces) {
             const float4 sp = __ldg(&S.spheres[SPHERES_ONLY ? prim : prim - S.n_faces]);
-            if (PATH_MODE) { exact_sphere_path(prim, sp, o, d, best); }
-            else { exact_sphere_v4(prim, sp, o, d, best); }
+            if (PATH_MODE) { exact_sphere_path<true>(prim, sp, o, d, best); }
+            else { exact_sphere_v4<true>(prim, sp, o, d, best); }
         } else {
-            if (line_test(__ldg(&S.filt3[prim]), f)) { exact_face(S, prim, o, d, PATH_MODE ? RT3_TMIN : 0.0f, best); }
+            if (line_test(__ldg(&S.filt3[prim]), f)) { exact_face<true>(S, prim, o, d, PATH_MODE ? RT3_TMIN : 0.0f, best); }
         }
     }
 }

@@ -17,6 +17,7 @@
 #pragma once
 
 #include "rt3_device.cuh"
+#include "rt3_bvh.cuh"
 
 struct rt3_kparams {
     uint32_t width, height;
@@ -215,12 +216,30 @@ __device__ __forceinline__ void sweep_slots(const rt3_scene_view& S, const rt3_s
     }
 }
 
+/* Hierarchy traversal for every live slot (results in the slots' BEST fields). */
+__device__ __forceinline__ void traverse_slots(const rt3_scene_view& S, const rt3_bvh_view& B, const rt3_smem_view& sm, uint32_t& visits, uint32_t& tests) {
+#pragma unroll 1
+    for (int r = 0; r < RT3_RAYS; r++) {
+        if (slot_word(sm, r, RT3_F_BOUNCE) == RT3_NO_HIT) { continue; }
+        rt3_hit best;
+        bvh_closest_hit<true>(S, B, slot_vec(sm, r, RT3_F_OX), slot_vec(sm, r, RT3_F_DX), best, visits, tests);
+        slot_word(sm, r, RT3_F_BEST_T) = __float_as_uint(best.t); slot_word(sm, r, RT3_F_BEST_PRIM) = best.prim;
+    }
+}
+
+/* Adds a thread's traversal counters to the context's (one atomic pair per warp). */
+__device__ __forceinline__ void count_accel(uint32_t visits, uint32_t tests, unsigned long long* __restrict__ counters) {
+    unsigned long long v = visits, t = tests;
+    for (int off = 16; off > 0; off >>= 1) { v += __shfl_down_sync(0xffffffffu, v, off); t += __shfl_down_sync(0xffffffffu, t, off); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&counters[2], v); atomicAdd(&counters[3], t); }
+}
+
 /* ------------------------------------------------------------------------ *
  * Reference mode: SequentialRenderer.cpp:269-308 (+ AOVs)
  * ------------------------------------------------------------------------ */
-template <bool RESIDENT, bool SPHERES_ONLY>
+template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL>
 __global__ void __launch_bounds__(RT3_CTA_THREADS, RT3_CTAS_PER_SM)
-reference_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, uint32_t* __restrict__ frame, uint32_t* __restrict__ hit_prim,
+reference_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P, uint32_t* __restrict__ frame, uint32_t* __restrict__ hit_prim,
                  uint32_t* __restrict__ hit_entity, float* __restrict__ hit_t, unsigned long long* __restrict__ counters) {
     constexpr int R = RT3_RAYS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -253,7 +272,16 @@ reference_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, uint32_t* __re
         d[r] = ((llc + u * hor) + v * ver) - origin;
         dn[r] = normalize3(d[r]);
     }
-    sweep_scene<false, RESIDENT, SPHERES_ONLY>(S, sm, phase, o, d, dn, live, best);
+    uint32_t visits = 0, tests = 0;
+    if (ACCEL) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            best[r].t = __int_as_float(0x7f800000); best[r].prim = RT3_NO_HIT;
+            if (live[r]) { bvh_closest_hit<false>(S, B, o[r], d[r], best[r], visits, tests); }
+        }
+    } else {
+        sweep_scene<false, RESIDENT, SPHERES_ONLY>(S, sm, phase, o, d, dn, live, best);
+    }
     unsigned long long rays = 0;
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -281,6 +309,7 @@ reference_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, uint32_t* __re
     /* ray count: one atomic per warp */
     for (int off = 16; off > 0; off >>= 1) { rays += __shfl_down_sync(0xffffffffu, rays, off); }
     if ((threadIdx.x & 31) == 0 && rays) { atomicAdd(&counters[1], rays); }
+    if (ACCEL) { count_accel(visits, tests, counters); }
 }
 
 /* ------------------------------------------------------------------------ *
@@ -493,9 +522,9 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
  * shared memory; a loop iteration (1) takes the slots in turn through one copy of the shading and
  * regeneration code -- shade the hit the last sweep found, then start the next (pixel, sample) item
  * if the slot is free, so that all lanes sweep live rays -- and (2) sweeps the scene for all slots. */
-template <bool RESIDENT, bool SPHERES_ONLY>
+template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL>
 __global__ void __launch_bounds__(RT3_CTA_THREADS, RT3_CTAS_PER_SM)
-pathtrace_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, unsigned long long* __restrict__ accum,
+pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P, unsigned long long* __restrict__ accum,
                  unsigned long long* __restrict__ counters) {
     constexpr int R = RT3_RAYS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -521,6 +550,7 @@ pathtrace_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, unsigned long 
         slot_word(sm, r, RT3_F_BEST_PRIM) = RT3_NO_HIT;
     }
     unsigned long long rays = 0;
+    uint32_t visits = 0, tests = 0;
     rt3_chunk chunk;
     chunk.cur = chunk.end = chunk.start = 0; chunk.pixel0 = chunk.sample0 = 0; chunk.dry = false;
 
@@ -549,10 +579,12 @@ pathtrace_kernel(rt3_scene_view S, rt3_camera cam, rt3_kparams P, unsigned long 
         }
         if (RESIDENT) { if (!__any_sync(0xffffffffu, any)) { break; } }   /* warps run independently */
         else { if (!__syncthreads_or(any ? 1 : 0)) { break; } }           /* tiles are CTA-wide */
-        sweep_slots<RESIDENT, SPHERES_ONLY>(S, sm, phase);
+        if (ACCEL) { traverse_slots(S, B, sm, visits, tests); }
+        else { sweep_slots<RESIDENT, SPHERES_ONLY>(S, sm, phase); }
     }
     for (int off = 16; off > 0; off >>= 1) { rays += __shfl_down_sync(0xffffffffu, rays, off); }
     if ((threadIdx.x & 31) == 0 && rays) { atomicAdd(&counters[1], rays); }
+    if (ACCEL) { count_accel(visits, tests, counters); }
 }
 
 /* Mean over samples, gamma 2, reference packing (SequentialRenderer.cpp:297). */
