@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--impl", default="rt3", choices=["rt3", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="override samples per pixel (non-default values are not the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bvh", action="store_true", help="time the hierarchy path (RT3_FLAG_BVH) instead of the brute-force sweep: not the headline configuration")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -173,7 +174,7 @@ def main():
     scene, cam = scenes.rtiow_cover(W, H)
     ctx = abi.Context(local_rank)
     ctx.upload(scene)
-    params = abi.make_params(W, H, mode=abi.MODE_PATHTRACE, spp=spp, max_depth=DEPTH, seed=SEED,
+    params = abi.make_params(W, H, mode=abi.MODE_PATHTRACE, spp=spp, max_depth=DEPTH, seed=SEED, flags=abi.FLAG_BVH if args.bvh else 0,
                              tile_rows=TILE_ROWS, part_index=rank, part_count=world)
     lib = ctx.lib
     stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream: kernels, NCCL and the timing events all go here
@@ -278,6 +279,9 @@ def main():
                          "peak_source": "FFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
                          "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS},
         }
+        if args.bvh:
+            line["config"]["workload"] += " [--bvh: hierarchy traversal instead of the brute-force sweep; roofline figures do not apply]"
+            line["accel"] = {"node_visits": st.accel_node_visits, "prim_tests": st.accel_prim_tests, "build_ms": st.accel_build_ms}
         if spp != SPP:
             line["config"]["workload"] += f" [OVERRIDE spp={spp}: not the BASELINE config]"
             line["config"]["spp"] = spp

@@ -34,7 +34,10 @@
 #ifndef RT3_CHUNK_WORDS
 #define RT3_CHUNK_WORDS 16      /* mask words swept before the survivors are drained (512 primitives) */
 #endif
-#define RT3_CONST_PRIMS 4096    /* scenes up to this size are swept out of the constant bank (48 KB of records) */
+#ifndef RT3_CONST_PRIMS
+#define RT3_CONST_PRIMS 768     /* scenes up to this size are swept out of the constant bank: 9 KB of records, about what stays
+                                 * resident in an SM's constant cache (measured crossover with the streamed path, profiles/crossover.py) */
+#endif
 #define RT3_TILE_PRIMS 1024     /* larger scenes: primitives per streamed shared-memory tile (12 KB per stage) */
 #define RT3_CTA_THREADS 128
 #ifndef RT3_CTAS_PER_SM

@@ -79,7 +79,9 @@ def random_soup(rng, n_faces, n_spheres, degenerate=False):
     (31, 1, 64, 36, False),       # exactly one prefilter block
     (33, 31, 64, 36, False),      # ragged second block
     (700, 300, 160, 90, False),
-    (4000, 96, 128, 72, False),   # largest shared-memory-resident scene
+    (700, 68, 128, 72, False),    # largest constant-bank scene (768 primitives)
+    (700, 69, 128, 72, False),    # smallest streamed scene
+    (4000, 96, 128, 72, False),   # exactly four full streamed tiles
     (5000, 1500, 128, 72, False), # streamed tiles (TMA bulk copies), several tiles, ragged tail
 ])
 def test_random_scenes_match_oracle(gpu_ctx, n_faces, n_spheres, w, h, degenerate):
