@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 W, H, SPP, DEPTH, SEED, TILE_ROWS = 1200, 800, 500, 50, 1, 2
 FLOP_PER_SPHERE_TEST, FLOP_PER_FACE_TEST = 17, 45
-CPU_SAMPLE = dict(width=240, height=160, spp=16)    # bounded sample of the same workload for the CPU legs
+CPU_SAMPLE = dict(width=480, height=320, spp=48)    # bounded sample of the same workload for the CPU legs (~20 M ray segments)
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 
 

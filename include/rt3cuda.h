@@ -215,6 +215,13 @@ int rt3_pack_partition(rt3_ctx* ctx, const uint32_t* device_frame, uint32_t* dev
 int rt3_unpack_partition(rt3_ctx* ctx, const uint32_t* device_slab, uint32_t* device_frame, uint32_t width, uint32_t height,
                          uint32_t tile_rows, uint32_t part_index, uint32_t part_count, void* cuda_stream);
 
+/* Output side (the step after the path, reference camera/Frame.cpp:88-96,131-142): unpacks a device frame of
+ * width*height packed pixels into interleaved 8-bit RGB (channels = 3) or RGBA (channels = 4, alpha 255) bytes,
+ * the layout PPM / PNG writers take, on the device and asynchronously on `cuda_stream`. Both pointers are
+ * device pointers, 16-byte aligned. */
+int rt3_frame_bytes(rt3_ctx* ctx, const uint32_t* device_frame, unsigned char* device_out, uint32_t width, uint32_t height, uint32_t channels,
+                    void* cuda_stream);
+
 int rt3_get_stats(rt3_ctx* ctx, rt3_stats* out);
 
 /* Achieved FP32 FMA throughput of a dependent-chain-free FFMA micro-kernel on

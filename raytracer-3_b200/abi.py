@@ -188,6 +188,7 @@ def load_core():
     lib.rt3_partition_rows.restype = u32
     lib.rt3_pack_partition.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, vp]
     lib.rt3_unpack_partition.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, vp]
+    lib.rt3_frame_bytes.argtypes = [vp, vp, vp, u32, u32, u32, vp]
     lib.rt3_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.rt3_measure_fma_peak.argtypes = [vp, C.POINTER(C.c_double)]
     _core = lib
@@ -196,7 +197,7 @@ def load_core():
 
 EXPORTED_SYMBOLS = [
     "rt3_last_error", "rt3_create", "rt3_destroy", "rt3_scene_upload", "rt3_render", "rt3_render_aov",
-    "rt3_render_device", "rt3_partition_rows", "rt3_pack_partition", "rt3_unpack_partition",
+    "rt3_render_device", "rt3_partition_rows", "rt3_pack_partition", "rt3_unpack_partition", "rt3_frame_bytes",
     "rt3_get_stats", "rt3_measure_fma_peak",
 ]
 
@@ -257,6 +258,11 @@ class Context:
     def unpack_partition(self, slab_ptr, frame_ptr, width, height, tile_rows, part_index, part_count, stream_ptr=None):
         self._check(self.lib.rt3_unpack_partition(self.handle, C.c_void_p(slab_ptr), C.c_void_p(frame_ptr), width, height,
                                                   tile_rows, part_index, part_count, C.c_void_p(stream_ptr or 0)))
+
+    def frame_bytes(self, frame_ptr, out_ptr, width, height, channels, stream_ptr=None):
+        """rt3_frame_bytes: packed device frame -> interleaved RGB (3) / RGBA (4) bytes on the device."""
+        self._check(self.lib.rt3_frame_bytes(self.handle, C.c_void_p(frame_ptr), C.c_void_p(out_ptr), width, height, channels,
+                                             C.c_void_p(stream_ptr or 0)))
 
     def stats(self):
         st = Stats()

@@ -801,6 +801,22 @@ int rt3_unpack_partition(rt3_ctx* ctx, const uint32_t* device_slab, uint32_t* de
     return RT3_OK;
 }
 
+int rt3_frame_bytes(rt3_ctx* ctx, const uint32_t* device_frame, unsigned char* device_out, uint32_t width, uint32_t height, uint32_t channels,
+                    void* cuda_stream) {
+    if (!ctx || !device_frame || !device_out) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    if (channels != 3 && channels != 4) { return fail(RT3_ERR_INVALID, "channels must be 3 (RGB) or 4 (RGBA), got %u", channels); }
+    if (((uintptr_t) device_frame & 15u) || ((uintptr_t) device_out & 15u)) { return fail(RT3_ERR_INVALID, "device buffers must be 16-byte aligned"); }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    const unsigned long long n = (unsigned long long) width * height;
+    if (n == 0) { return RT3_OK; }
+    cudaStream_t stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
+    const unsigned grid = (unsigned) (((n + 3ull) / 4ull + 255ull) / 256ull);
+    if (channels == 4) { frame_bytes_kernel<4><<<grid, 256, 0, stream>>>(device_frame, device_out, n); }
+    else { frame_bytes_kernel<3><<<grid, 256, 0, stream>>>(device_frame, device_out, n); }
+    RT3_CUDA(cudaGetLastError());
+    return RT3_OK;
+}
+
 int rt3_get_stats(rt3_ctx* ctx, rt3_stats* out) {
     if (!ctx || !out) { return fail(RT3_ERR_INVALID, "NULL argument"); }
     int rc = collect_stats(ctx);

@@ -629,6 +629,36 @@ __global__ void unpack_partition_kernel(rt3_kparams P, const uint32_t* __restric
     frame[(size_t) owned_row_to_global(P, local_row) * P.width + x] = slab[p];
 }
 
+/* Packed frame (r<<24 | g<<16 | b<<8 | a) -> interleaved 8-bit RGB or RGBA bytes, the layout image writers take
+ * (reference Frame.cpp:88-96, 131-142 do this per pixel on the host). Four pixels per thread: one 16-byte
+ * load, three (RGB) or four (RGBA) 4-byte stores; the tail is done per pixel. */
+template <int CHANNELS>
+__global__ void frame_bytes_kernel(const uint32_t* __restrict__ frame, unsigned char* __restrict__ out, unsigned long long n_pixels) {
+    const unsigned long long q = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long first = 4ull * q;
+    if (first >= n_pixels) { return; }
+    if (first + 4ull <= n_pixels) {
+        const uint4 px = *reinterpret_cast<const uint4*>(frame + first);
+        /* memory order r, g, b, a = the packed word with its bytes reversed */
+        const uint32_t p0 = __byte_perm(px.x, 0u, 0x0123), p1 = __byte_perm(px.y, 0u, 0x0123), p2 = __byte_perm(px.z, 0u, 0x0123),
+                       p3 = __byte_perm(px.w, 0u, 0x0123);
+        if (CHANNELS == 4) {
+            *reinterpret_cast<uint4*>(out + 4ull * first) = make_uint4(p0 | 0xFF000000u, p1 | 0xFF000000u, p2 | 0xFF000000u, p3 | 0xFF000000u);
+        } else {
+            uint32_t* o = reinterpret_cast<uint32_t*>(out + 3ull * first); /* 12 bytes, 4-byte aligned because first % 4 == 0 */
+            o[0] = __byte_perm(p0, p1, 0x4210); /* r0 g0 b0 r1 */
+            o[1] = __byte_perm(p1, p2, 0x5421); /* g1 b1 r2 g2 */
+            o[2] = __byte_perm(p2, p3, 0x6542); /* b2 r3 g3 b3 */
+        }
+        return;
+    }
+    for (unsigned long long i = first; i < n_pixels; i++) {
+        const uint32_t px = frame[i];
+        out[CHANNELS * i + 0] = (unsigned char) (px >> 24); out[CHANNELS * i + 1] = (unsigned char) (px >> 16); out[CHANNELS * i + 2] = (unsigned char) (px >> 8);
+        if (CHANNELS == 4) { out[CHANNELS * i + 3] = 255; }
+    }
+}
+
 /* FFMA throughput probe: 16 independent three-register FMA chains per thread. */
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, float a, float b, int iters) {
     float acc[16];

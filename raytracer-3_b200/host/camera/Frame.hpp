@@ -19,8 +19,11 @@ namespace RayTracer {
         ~Frame();
         Frame& operator=(const Frame& other) = delete;
 
-        /* Binary PPM (P6); the reference's PNG writer depends on the vendored LodePNG and stays out of scope. */
+        /* Binary PPM (P6), reference Frame.cpp:110-148 (without its per-pixel log line, Frame.cpp:137). */
         void to_ppm(const std::string& path) const;
+        /* 8-bit RGBA PNG like reference Frame.cpp:82-106, written by a small encoder of its own (zlib "stored"
+         * blocks: valid for every PNG reader, no compression) instead of the reference's vendored LodePNG. */
+        void to_png(const std::string& path) const;
 
         inline uint32_t w() const { return this->width; }
         inline uint32_t h() const { return this->height; }

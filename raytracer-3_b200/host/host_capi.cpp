@@ -136,4 +136,13 @@ int rt3host_camera_vectors(uint32_t width, uint32_t height, const float* look, f
     });
 }
 
+/* Frame::to_png / Frame::to_ppm on a caller-supplied frame (format: 0 = PPM, 1 = PNG). */
+int rt3host_write_image(const uint32_t* frame, uint32_t width, uint32_t height, const char* path, int format) {
+    return guarded([&] {
+        Frame f(width, height);
+        std::memcpy(f.d(), frame, sizeof(uint32_t) * (size_t) width * height);
+        if (format == 1) { f.to_png(path); } else { f.to_ppm(path); }
+    });
+}
+
 }  // extern "C"

@@ -1,7 +1,7 @@
 /* rt3_main.cpp — command-line driver of the host backend: the shape of reference src/Main.cpp:246-315
  * (create renderer, camera, entities; prerender; render; save), with the scene chosen by name.
  *
- *   rt3_render [-W width] [-H height] [-s scene] [-o out.ppm] [--teddy path/to/teddy.obj]
+ *   rt3_render [-W width] [-H height] [-s scene] [-o out.ppm|out.png] [--teddy path/to/teddy.obj]
  *   scenes: default (reference Main.cpp:280-283, needs --teddy), triangle, sphere, rtiow (path traced, C1)
  */
 #include <cstdio>
@@ -65,7 +65,8 @@ int main(int argc, const char** argv) {
             else if (entities[i]->type == ECS::et_sphere) { delete (ECS::Sphere*) entities[i]; }
             else { delete (ECS::Triangle*) entities[i]; }
         }
-        cam.get_frame().to_ppm(out);
+        if (out.size() > 4 && out.compare(out.size() - 4, 4, ".png") == 0) { cam.get_frame().to_png(out); }
+        else { cam.get_frame().to_ppm(out); }
         std::printf("%s: %ux%u, %.3f ms on the device, %llu rays -> %s\n", scene.c_str(), width, height, cuda->stats().device_ms,
                     (unsigned long long) cuda->stats().rays, out.c_str());
         delete renderer;

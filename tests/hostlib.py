@@ -28,6 +28,7 @@ def lib():
         L.rt3host_prerender.argtypes = [vp]
         L.rt3host_render.argtypes = [vp, u32, u32, C.c_float, C.c_float, C.c_float, fp, vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.rt3host_camera_vectors.argtypes = [u32, u32, fp, fp]
+        L.rt3host_write_image.argtypes = [vp, u32, u32, C.c_char_p, C.c_int]
         _lib = L
     return _lib
 
@@ -38,6 +39,13 @@ def _f(v):
 
 class HostError(RuntimeError):
     pass
+
+
+def write_image(frame, path, fmt):
+    """Frame::to_ppm (fmt 'ppm') / Frame::to_png (fmt 'png') of the host backend on a [H, W] uint32 frame."""
+    frame = np.ascontiguousarray(frame, np.uint32)
+    if lib().rt3host_write_image(frame.ctypes.data, frame.shape[1], frame.shape[0], str(path).encode(), 1 if fmt == "png" else 0) != 0:
+        raise HostError(lib().rt3host_last_error().decode())
 
 
 class HostScene:

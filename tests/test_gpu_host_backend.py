@@ -59,3 +59,21 @@ def test_reference_main_with_cuda_backend_renders_the_golden_image(tmp_path):
     assert rgb.shape == (225, 400, 3)
     frame = (rgb[..., 0] << 24) | (rgb[..., 1] << 16) | (rgb[..., 2] << 8) | 0xFF
     assert np.array_equal(frame[:224], g["frame"])
+
+
+@pytest.mark.parametrize("channels", [3, 4])
+def test_device_frame_to_bytes(gpu_ctx, channels):
+    """rt3_frame_bytes (output side, reference Frame.cpp:88-96,131-142) against the same unpacking in numpy."""
+    import torch
+    rng = np.random.default_rng(channels)
+    for w, h in ((1, 1), (5, 3), (64, 36), (401, 227)):   # pixel counts with every remainder modulo 4
+        frame = rng.integers(0, 1 << 32, (h, w), dtype=np.uint32)
+        d_frame = torch.from_numpy(frame.view(np.int32)).cuda()
+        d_out = torch.zeros(w * h * channels + 16, dtype=torch.uint8, device="cuda")
+        gpu_ctx.frame_bytes(d_frame.data_ptr(), d_out.data_ptr(), w, h, channels)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        want = np.stack([(frame >> s) & 0xFF for s in (24, 16, 8)] + ([np.full_like(frame, 255)] if channels == 4 else []), -1).astype(np.uint8)
+        assert np.array_equal(got[: w * h * channels], want.ravel()) and not got[w * h * channels:].any()
+    with pytest.raises(abi.Rt3Error, match="channels"):
+        gpu_ctx.frame_bytes(d_frame.data_ptr(), d_out.data_ptr(), w, h, 2)

@@ -86,3 +86,23 @@ def test_look_at_camera_matches_python_builder(built):
     want = np.array(list(cam.origin) + list(cam.horizontal) + list(cam.vertical) + list(cam.lower_left_corner) + [cam.lens_radius] +
                     list(cam.lens_u) + list(cam.lens_v), np.float32)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("fmt", ["ppm", "png"])
+def test_frame_writers_round_trip(built, tmp_path, fmt):
+    """Frame::to_ppm / Frame::to_png (reference Frame.cpp:82-148): what an image reader gets back is the frame."""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    for w, h in ((1, 1), (37, 11), (400, 225)):      # the last one needs several 64 KiB deflate blocks
+        frame = (rng.integers(0, 1 << 24, (h, w), dtype=np.uint32) << 8) | 0xFF
+        path = tmp_path / f"f{w}x{h}.{fmt}"
+        hostlib.write_image(frame, path, fmt)
+        img = Image.open(path)
+        assert img.size == (w, h) and img.mode == ("RGBA" if fmt == "png" else "RGB")
+        px = np.array(img).astype(np.uint32)
+        back = (px[..., 0] << 24) | (px[..., 1] << 16) | (px[..., 2] << 8) | 0xFF
+        assert np.array_equal(back, frame)
+        if fmt == "png":
+            assert np.all(px[..., 3] == 255)
+    with pytest.raises(hostlib.HostError, match="Could not open"):
+        hostlib.write_image(frame, tmp_path / "no_such_dir" / "x.png", fmt)
