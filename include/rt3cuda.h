@@ -100,6 +100,16 @@ typedef struct rt3_scene {
     const rt3_material* materials;
 } rt3_scene;
 
+/* UV sphere to be tessellated (the fields of ECS::Sphere, reference src/lib/entities/Sphere.hpp:33-45). */
+typedef struct rt3_uv_sphere {
+    float center[3];
+    float radius;
+    uint32_t n_meridians; /* >= 1 */
+    uint32_t n_parallels; /* >= 3 (Sphere.cpp:101) */
+    float color[3];
+    uint32_t entity;      /* entity id recorded for its faces */
+} rt3_uv_sphere;
+
 /* ---- camera ------------------------------------------------------------- */
 
 /* The four public vectors of the reference Camera (camera/Camera.hpp:27-34;
@@ -214,6 +224,17 @@ int rt3_pack_partition(rt3_ctx* ctx, const uint32_t* device_frame, uint32_t* dev
                        uint32_t tile_rows, uint32_t part_index, uint32_t part_count, void* cuda_stream);
 int rt3_unpack_partition(rt3_ctx* ctx, const uint32_t* device_slab, uint32_t* device_frame, uint32_t width, uint32_t height,
                          uint32_t tile_rows, uint32_t part_index, uint32_t part_count, void* cuda_stream);
+
+/* Scene construction on the device (the step before the path): tessellates `n` UV spheres with the arithmetic of
+ * the reference's CPU pre-render (src/lib/entities/Sphere.cpp:69-79,120-351; GPU twins
+ * shaders/pre_render_sphere_v2_{vertices,faces}.glsl) and returns them flattened like
+ * SequentialRenderer.cpp:174-195: sphere k's vertices follow sphere k-1's, face indices are absolute,
+ * shifted by `first_vertex` (where the caller appends the batch in its own vertex array). The host arrays must
+ * hold the sums of rt3_uv_sphere_faces / rt3_uv_sphere_vertices; host_face_entity may be NULL. */
+uint32_t rt3_uv_sphere_faces(uint32_t n_meridians, uint32_t n_parallels);
+uint32_t rt3_uv_sphere_vertices(uint32_t n_meridians, uint32_t n_parallels);
+int rt3_tessellate_spheres(rt3_ctx* ctx, const rt3_uv_sphere* spheres, uint32_t n, uint32_t first_vertex, rt3_face* host_faces,
+                           rt3_vertex* host_vertices, uint32_t* host_face_entity);
 
 /* Output side (the step after the path, reference camera/Frame.cpp:88-96,131-142): unpacks a device frame of
  * width*height packed pixels into interleaved 8-bit RGB (channels = 3) or RGBA (channels = 4, alpha 255) bytes,

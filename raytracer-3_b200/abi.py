@@ -60,6 +60,11 @@ class Camera(C.Structure):
     ]
 
 
+class UvSphere(C.Structure):
+    _fields_ = [("center", C.c_float * 3), ("radius", C.c_float), ("n_meridians", C.c_uint32), ("n_parallels", C.c_uint32),
+                ("color", C.c_float * 3), ("entity", C.c_uint32)]
+
+
 class Params(C.Structure):
     _fields_ = [
         ("width", C.c_uint32), ("height", C.c_uint32), ("mode", C.c_uint32),
@@ -189,6 +194,11 @@ def load_core():
     lib.rt3_pack_partition.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, vp]
     lib.rt3_unpack_partition.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, vp]
     lib.rt3_frame_bytes.argtypes = [vp, vp, vp, u32, u32, u32, vp]
+    lib.rt3_uv_sphere_faces.argtypes = [u32, u32]
+    lib.rt3_uv_sphere_faces.restype = u32
+    lib.rt3_uv_sphere_vertices.argtypes = [u32, u32]
+    lib.rt3_uv_sphere_vertices.restype = u32
+    lib.rt3_tessellate_spheres.argtypes = [vp, C.POINTER(UvSphere), u32, u32, vp, vp, vp]
     lib.rt3_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.rt3_measure_fma_peak.argtypes = [vp, C.POINTER(C.c_double)]
     _core = lib
@@ -198,6 +208,7 @@ def load_core():
 EXPORTED_SYMBOLS = [
     "rt3_last_error", "rt3_create", "rt3_destroy", "rt3_scene_upload", "rt3_render", "rt3_render_aov",
     "rt3_render_device", "rt3_partition_rows", "rt3_pack_partition", "rt3_unpack_partition", "rt3_frame_bytes",
+    "rt3_uv_sphere_faces", "rt3_uv_sphere_vertices", "rt3_tessellate_spheres",
     "rt3_get_stats", "rt3_measure_fma_peak",
 ]
 
@@ -258,6 +269,18 @@ class Context:
     def unpack_partition(self, slab_ptr, frame_ptr, width, height, tile_rows, part_index, part_count, stream_ptr=None):
         self._check(self.lib.rt3_unpack_partition(self.handle, C.c_void_p(slab_ptr), C.c_void_p(frame_ptr), width, height,
                                                   tile_rows, part_index, part_count, C.c_void_p(stream_ptr or 0)))
+
+    def tessellate_spheres(self, spheres, first_vertex=0):
+        """rt3_tessellate_spheres: [(center, radius, n_meridians, n_parallels, color, entity), ...] -> SceneArrays (faces, vertices)."""
+        arr = (UvSphere * len(spheres))()
+        for dst, (center, radius, m, p, color, entity) in zip(arr, spheres):
+            dst.center = (C.c_float * 3)(*center); dst.radius = radius; dst.n_meridians = m; dst.n_parallels = p
+            dst.color = (C.c_float * 3)(*color); dst.entity = entity
+        nf = sum(self.lib.rt3_uv_sphere_faces(s[2], s[3]) for s in spheres)
+        nv = sum(self.lib.rt3_uv_sphere_vertices(s[2], s[3]) for s in spheres)
+        faces, verts, ent = np.zeros(nf, FACE_DTYPE), np.zeros(nv, VERTEX_DTYPE), np.zeros(nf, np.uint32)
+        self._check(self.lib.rt3_tessellate_spheres(self.handle, arr, len(spheres), first_vertex, _ptr(faces), _ptr(verts), _ptr(ent)))
+        return SceneArrays(faces=faces, vertices=verts, face_entity=ent)
 
     def frame_bytes(self, frame_ptr, out_ptr, width, height, channels, stream_ptr=None):
         """rt3_frame_bytes: packed device frame -> interleaved RGB (3) / RGBA (4) bytes on the device."""

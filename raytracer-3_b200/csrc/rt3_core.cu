@@ -25,6 +25,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "rt3_kernels.cuh"
+#include "rt3_scene.cuh"
 
 namespace {
 
@@ -287,6 +288,10 @@ int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
     int rc = configure(pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL>, smem, &per_sm);
     if (rc != RT3_OK) { return rc; }
     if (per_sm < 1) { return fail(RT3_ERR_CUDA, "pathtrace kernel does not fit on an SM (smem %zu)", smem); }
+    if (const char* cap = getenv("RT3_MAX_CTAS_PER_SM")) { /* tuning knob: fewer persistent CTAs per SM than fit */
+        const int c = atoi(cap);
+        if (c >= 1 && c < per_sm) { per_sm = c; }
+    }
     /* persistent grid: every SM full, no more CTAs than there are CTAs' worth of paths */
     unsigned long long per_cta = (unsigned long long) RT3_CTA_THREADS * RT3_RAYS;
     unsigned long long want = (kp.n_items + per_cta - 1) / per_cta;
@@ -798,6 +803,50 @@ int rt3_unpack_partition(rt3_ctx* ctx, const uint32_t* device_slab, uint32_t* de
     cudaStream_t stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
     unpack_partition_kernel<<<(unsigned) ((kp.n_pixels + 255ull) / 256ull), 256, 0, stream>>>(kp, device_slab, device_frame);
     RT3_CUDA(cudaGetLastError());
+    return RT3_OK;
+}
+
+uint32_t rt3_uv_sphere_faces(uint32_t n_meridians, uint32_t n_parallels) { return n_parallels >= 3 ? uv_sphere_faces(n_meridians, n_parallels) : 0u; }
+uint32_t rt3_uv_sphere_vertices(uint32_t n_meridians, uint32_t n_parallels) { return n_parallels >= 3 ? uv_sphere_vertices(n_meridians, n_parallels) : 0u; }
+
+int rt3_tessellate_spheres(rt3_ctx* ctx, const rt3_uv_sphere* spheres, uint32_t n, uint32_t first_vertex, rt3_face* host_faces,
+                           rt3_vertex* host_vertices, uint32_t* host_face_entity) {
+    if (!ctx || (n && (!spheres || !host_faces || !host_vertices))) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    static_assert(sizeof(rt3_face) == 48 && sizeof(rt3_vertex) == 16, "flattened records must match the reference's GFace / glm::vec4");
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long n_faces = 0, n_vertices = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (spheres[i].n_parallels < 3 || spheres[i].n_meridians < 1) {
+            return fail(RT3_ERR_INVALID, "sphere %u: needs n_parallels >= 3 and n_meridians >= 1 (got %u, %u)", i, spheres[i].n_parallels, spheres[i].n_meridians);
+        }
+        n_faces += uv_sphere_faces(spheres[i].n_meridians, spheres[i].n_parallels);
+        n_vertices += uv_sphere_vertices(spheres[i].n_meridians, spheres[i].n_parallels);
+    }
+    if (n_faces > 0x7FFFFFFFull || n_vertices + first_vertex > 0xFFFFFFFFull) { return fail(RT3_ERR_INVALID, "too many faces or vertices"); }
+    if (n_faces == 0) { return RT3_OK; }
+    DeviceBuffer<float4> d_vertices;
+    DeviceBuffer<uint4> d_faces;
+    DeviceBuffer<uint32_t> d_entity;
+    int rc;
+    if ((rc = d_vertices.reserve(n_vertices)) != RT3_OK || (rc = d_faces.reserve(3 * n_faces)) != RT3_OK || (rc = d_entity.reserve(n_faces)) != RT3_OK) { return rc; }
+    uint32_t v0 = 0, f0 = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const rt3_uv_sphere& s = spheres[i];
+        rt3_uv_sphere_dev d = { s.center[0], s.center[1], s.center[2], s.radius, s.n_meridians, s.n_parallels, s.color[0], s.color[1], s.color[2],
+                                v0, f0, s.entity };
+        const uint32_t nv = uv_sphere_vertices(d.m, d.p), nf = uv_sphere_faces(d.m, d.p);
+        uv_sphere_vertices_kernel<<<(nv + 255u) / 256u, 256, 0, ctx->stream>>>(d, d_vertices.ptr);
+        RT3_CUDA(cudaGetLastError());
+        uv_sphere_faces_kernel<<<(nf + 255u) / 256u, 256, 0, ctx->stream>>>(d, d_vertices.ptr, d_faces.ptr, d_entity.ptr);
+        RT3_CUDA(cudaGetLastError());
+        v0 += nv; f0 += nf;
+    }
+    RT3_CUDA(cudaMemcpyAsync(host_vertices, d_vertices.ptr, n_vertices * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    RT3_CUDA(cudaMemcpyAsync(host_faces, d_faces.ptr, n_faces * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_face_entity) { RT3_CUDA(cudaMemcpyAsync(host_face_entity, d_entity.ptr, n_faces * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)); }
+    RT3_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (first_vertex) { for (unsigned long long f = 0; f < n_faces; f++) { host_faces[f].v1 += first_vertex; host_faces[f].v2 += first_vertex; host_faces[f].v3 += first_vertex; } }
+    d_vertices.release(); d_faces.release(); d_entity.release();
     return RT3_OK;
 }
 

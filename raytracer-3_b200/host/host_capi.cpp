@@ -94,7 +94,8 @@ int rt3host_renderer_create(void* s, int device, uint32_t mode, uint32_t spp, ui
         hs->renderer = nullptr;
         hs->renderer = new CudaRenderer(device);
         CudaRenderSettings st;
-        st.mode = mode; st.spp = spp; st.max_depth = max_depth; st.seed = seed; st.flags = flags; st.analytic_spheres = analytic_spheres != 0;
+        st.mode = mode; st.spp = spp; st.max_depth = max_depth; st.seed = seed; st.flags = flags;
+        st.analytic_spheres = (analytic_spheres & 1) != 0; st.device_tessellation = (analytic_spheres & 2) != 0; /* bit 0 / bit 1 */
         hs->renderer->set_settings(st);
     });
 }

@@ -37,6 +37,8 @@ CudaRenderSettings CudaRenderSettings::from_environment(int* device) {
     s.max_depth = env_u32("RT3_DEPTH", s.max_depth);
     s.seed = env_u32("RT3_SEED", s.seed);
     s.analytic_spheres = env_u32("RT3_ANALYTIC_SPHERES", 0) != 0;
+    s.device_tessellation = env_u32("RT3_DEVICE_TESSELLATION", 0) != 0;
+    if (env_u32("RT3_BVH", 0) != 0) { s.flags |= RT3_FLAG_BVH; }
     if (device) { *device = (int) env_u32("RT3_DEVICE", 0); }
     return s;
 }
@@ -101,7 +103,19 @@ void CudaRenderer::prerender(const Tools::Array<ECS::RenderEntity*>& entities) {
         vertices.resize(e->pre_render_vertices);
         switch (e->pre_render_operation) {
             case EntityPreRenderOperation::epro_generate_triangle: cpu_pre_render_triangle(faces, vertices, (Triangle*) e); break;
-            case EntityPreRenderOperation::epro_generate_sphere: cpu_pre_render_sphere(faces, vertices, (Sphere*) e); break;
+            case EntityPreRenderOperation::epro_generate_sphere:
+                if (this->settings.device_tessellation) {
+                    /* the reference's GPU pre-render (VulkanRenderer.cpp:310-336) as a CUDA kernel, CPU-path arithmetic */
+                    const Sphere* sp = (const Sphere*) e;
+                    rt3_uv_sphere d = { { sp->center.x, sp->center.y, sp->center.z }, sp->radius, sp->n_meridians, sp->n_parallels,
+                                        { sp->color.x, sp->color.y, sp->color.z }, (uint32_t) i };
+                    static_assert(sizeof(GFace) == sizeof(rt3_face) && sizeof(glm::vec4) == sizeof(rt3_vertex), "flattened records differ");
+                    check(rt3_tessellate_spheres(this->ctx, &d, 1, 0, (rt3_face*) &faces[0], (rt3_vertex*) &vertices[0], nullptr),
+                          "Could not tessellate a sphere on the device");
+                } else {
+                    cpu_pre_render_sphere(faces, vertices, (Sphere*) e);
+                }
+                break;
             case EntityPreRenderOperation::epro_load_object_file: cpu_pre_render_object(faces, vertices, (Object*) e); break;
             default:
                 DLOG(fatal, "Entity " + std::to_string(i) + " wants to be pre-rendered using unsupported operation '" +

@@ -41,8 +41,9 @@ namespace RayTracer {
         uint32_t seed = 1;
         uint32_t flags = 0;
         bool analytic_spheres = false;      /* keep ECS spheres analytic instead of tessellating them */
+        bool device_tessellation = false;   /* tessellate ECS spheres on the device (rt3_tessellate_spheres) instead of the CPU */
         uint32_t tile_rows = 8, part_index = 0, part_count = 1;
-        /* Reads RT3_MODE (reference|pathtrace), RT3_SPP, RT3_DEPTH, RT3_SEED, RT3_ANALYTIC_SPHERES, RT3_DEVICE. */
+        /* Reads RT3_MODE (reference|pathtrace), RT3_SPP, RT3_DEPTH, RT3_SEED, RT3_ANALYTIC_SPHERES, RT3_DEVICE_TESSELLATION, RT3_BVH, RT3_DEVICE. */
         static CudaRenderSettings from_environment(int* device);
     };
 

@@ -77,8 +77,10 @@ class HostScene:
         self._ok(self.L.rt3host_flatten(self.h, C.byref(nf), C.byref(nv), faces.ctypes.data, verts.ctypes.data, ent.ctypes.data))
         return abi.SceneArrays(faces=faces, vertices=verts, face_entity=ent)
 
-    def create_renderer(self, device=0, mode=abi.MODE_REFERENCE, spp=1, max_depth=1, seed=1, flags=0, analytic_spheres=False):
-        self._ok(self.L.rt3host_renderer_create(self.h, device, mode, spp, max_depth, seed, flags, int(analytic_spheres)))
+    def create_renderer(self, device=0, mode=abi.MODE_REFERENCE, spp=1, max_depth=1, seed=1, flags=0, analytic_spheres=False,
+                        device_tessellation=False):
+        self._ok(self.L.rt3host_renderer_create(self.h, device, mode, spp, max_depth, seed, flags,
+                                                int(analytic_spheres) | (2 if device_tessellation else 0)))
 
     def set_material(self, entity_index, kind, albedo=(1, 1, 1), fuzz=0.0, ior=1.5):
         self._ok(self.L.rt3host_set_material(self.h, entity_index, kind, _f(albedo), fuzz, ior))
