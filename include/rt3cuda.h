@@ -141,6 +141,10 @@ typedef struct rt3_camera {
 
 #define RT3_FLAG_NO_JITTER 0x1u /* pathtrace: sample pixel centres (deterministic primary rays) */
 #define RT3_FLAG_NO_GAMMA 0x2u  /* pathtrace: resolve the linear mean instead of its square root */
+#define RT3_FLAG_ACCUMULATE 0x8u /* pathtrace, progressive refinement: keep the accumulators of the previous render of this context
+                                 * (same frame size and partition) and add this call's samples [first_sample, first_sample + spp)
+                                 * to them; the frame is resolved over first_sample + spp samples. k calls of n spp produce
+                                 * exactly the frame of one call of k*n spp (integer accumulation). */
 #define RT3_FLAG_BVH 0x4u       /* closest hits through a bounding-volume hierarchy built on the device at the first such render
                                  * after rt3_scene_upload, instead of the reference's brute-force loop over every primitive
                                  * (SequentialRenderer.cpp:55-95). The frame and the AOVs are identical, bit for bit. */
@@ -160,6 +164,7 @@ typedef struct rt3_params {
     uint32_t tile_rows;
     uint32_t part_index;
     uint32_t part_count;
+    uint32_t first_sample; /* pathtrace: sample index of the first of this call's spp samples (0 for a one-shot render) */
 } rt3_params;
 
 /* Timings and counters of the most recent render on this context. */

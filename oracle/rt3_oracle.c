@@ -361,7 +361,7 @@ static void pathtrace_row(void* ctx, uint32_t y) {
             uint64_t acc[3] = { 0, 0, 0 };
             uint64_t rays = 0;
             for (uint32_t sidx = 0; sidx < p->spp; sidx++) {
-                v3 L = trace_path(scene, cam, p, x, y, sidx, &rays);
+                v3 L = trace_path(scene, cam, p, x, y, p->first_sample + sidx, &rays); /* a one-shot render of samples [first_sample, first_sample + spp) */
                 acc[0] += to_fixed(L.x); acc[1] += to_fixed(L.y); acc[2] += to_fixed(L.z);
             }
             rays_total += rays;

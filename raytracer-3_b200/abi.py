@@ -16,7 +16,7 @@ CORE_LIB_PATH = os.path.join(_HERE, "csrc", "librt3cuda.so")
 
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 MODE_REFERENCE, MODE_PATHTRACE = 0, 1
-FLAG_NO_JITTER, FLAG_NO_GAMMA, FLAG_BVH = 0x1, 0x2, 0x4
+FLAG_NO_JITTER, FLAG_NO_GAMMA, FLAG_BVH, FLAG_ACCUMULATE = 0x1, 0x2, 0x4, 0x8
 NO_HIT = 0xFFFFFFFF
 
 # numpy record layouts that mirror rt3_face (GFace, reference Vertex.hpp:39-51),
@@ -70,7 +70,7 @@ class Params(C.Structure):
         ("width", C.c_uint32), ("height", C.c_uint32), ("mode", C.c_uint32),
         ("spp", C.c_uint32), ("max_depth", C.c_uint32), ("seed", C.c_uint32),
         ("flags", C.c_uint32), ("tile_rows", C.c_uint32),
-        ("part_index", C.c_uint32), ("part_count", C.c_uint32),
+        ("part_index", C.c_uint32), ("part_count", C.c_uint32), ("first_sample", C.c_uint32),
     ]
 
 
@@ -165,8 +165,8 @@ def reference_camera(width, height, focal_length=2.0, viewport_height=2.0, viewp
 
 
 def make_params(width, height, mode=MODE_REFERENCE, spp=1, max_depth=1, seed=0, flags=0,
-                tile_rows=8, part_index=0, part_count=1):
-    return Params(width, height, mode, spp, max_depth, seed, flags, tile_rows, part_index, part_count)
+                tile_rows=8, part_index=0, part_count=1, first_sample=0):
+    return Params(width, height, mode, spp, max_depth, seed, flags, tile_rows, part_index, part_count, first_sample)
 
 
 _core = None

@@ -88,6 +88,7 @@ struct rt3_ctx {
     DeviceBuffer<uint32_t> frame, aov_prim, aov_entity;
     DeviceBuffer<float> aov_t;
     DeviceBuffer<unsigned long long> accum, counters;
+    uint32_t accum_width = 0, accum_height = 0; /* frame the accumulators were last cleared for */
 
     rt3_stats stats{};
 };
@@ -117,6 +118,9 @@ int make_kparams(const rt3_params* p, rt3_kparams* k) {
     if (p->part_index >= parts) { return fail(RT3_ERR_INVALID, "part_index %u >= part_count %u", p->part_index, parts); }
     k->width = p->width; k->height = p->height;
     k->spp = p->mode == RT3_MODE_PATHTRACE ? p->spp : 1;
+    k->first_sample = p->mode == RT3_MODE_PATHTRACE ? p->first_sample : 0;
+    if ((unsigned long long) k->first_sample + k->spp > 0x7FFFFFFFull) { return fail(RT3_ERR_INVALID, "first_sample + spp must stay below 2^31"); }
+    k->resolve_spp = (p->flags & RT3_FLAG_ACCUMULATE) ? k->first_sample + k->spp : k->spp;
     k->max_depth = p->max_depth; k->seed = p->seed; k->flags = p->flags;
     k->tile_rows = p->tile_rows ? p->tile_rows : 1;
     k->part_index = p->part_index; k->part_count = parts;
@@ -425,11 +429,19 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
         return rc;
     }
     size_t n_acc = (size_t) kp.width * kp.height * 3;
-    rc = ctx->accum.reserve(n_acc);
-    if (rc != RT3_OK) { return rc; }
-    unsigned clear_grid = (unsigned) ((kp.n_pixels * 3ull + 255ull) / 256ull);
-    clear_accum_kernel<<<clear_grid, 256, 0, stream>>>(kp, ctx->accum.ptr);
-    RT3_CUDA(cudaGetLastError());
+    const bool accumulate = (params->flags & RT3_FLAG_ACCUMULATE) != 0;
+    if (accumulate) {
+        if (ctx->accum_width != kp.width || ctx->accum_height != kp.height || !ctx->accum.ptr) {
+            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE needs a previous path-traced render of the same %ux%u frame on this context", kp.width, kp.height);
+        }
+    } else {
+        rc = ctx->accum.reserve(n_acc);
+        if (rc != RT3_OK) { return rc; }
+        ctx->accum_width = kp.width; ctx->accum_height = kp.height;
+        unsigned clear_grid = (unsigned) ((kp.n_pixels * 3ull + 255ull) / 256ull);
+        clear_accum_kernel<<<clear_grid, 256, 0, stream>>>(kp, ctx->accum.ptr);
+        RT3_CUDA(cudaGetLastError());
+    }
     RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
     const bool spheres_only = ctx->view.n_faces == 0;
     rc = accel ? launch_pathtrace<true, false, true>(ctx, *cam, kp, smem, stream)
@@ -441,7 +453,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     resolve_kernel<<<resolve_grid, 256, 0, stream>>>(kp, ctx->accum.ptr, device_frame);
     RT3_CUDA(cudaGetLastError());
     RT3_CUDA(cudaEventRecord(ctx->ev_end, stream));
-    ctx->stats.kernel_launches = 3;
+    ctx->stats.kernel_launches = accumulate ? 2 : 3;
     return RT3_OK;
 }
 

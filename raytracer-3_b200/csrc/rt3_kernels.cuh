@@ -22,6 +22,8 @@
 struct rt3_kparams {
     uint32_t width, height;
     uint32_t spp, max_depth, seed, flags;
+    uint32_t first_sample;        /* this launch renders samples [first_sample, first_sample + spp) of every pixel */
+    uint32_t resolve_spp;         /* samples behind the accumulators when the frame is resolved */
     uint32_t tile_rows, part_index, part_count;
     uint32_t owned_rows;          /* rows this partition renders */
     unsigned long long n_pixels;  /* owned_rows * width */
@@ -395,7 +397,7 @@ __device__ __forceinline__ void start_path(rt3_path& s, const rt3_cam_view& C, c
     uint32_t y = owned_row_to_global(P, local_row);
     uint32_t pixel_index = y * P.width + x;
     s.pix = pixel_index;
-    uint32_t k = rt3_path_key(pixel_index, sample, P.seed);
+    uint32_t k = rt3_path_key(pixel_index, P.first_sample + sample, P.seed);
     s.key = k;
     float jx = 0.0f, jy = 0.0f;
     if (!(P.flags & RT3_FLAG_NO_JITTER)) { jx = rt3_draw(k, RT3_DIM_JITTER_X); jy = rt3_draw(k, RT3_DIM_JITTER_Y); }
@@ -597,7 +599,7 @@ __global__ void resolve_kernel(rt3_kparams P, const unsigned long long* __restri
     uint32_t ch[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        float m = (float) ((double) accum[3 * idx + c] / ((double) P.spp * (double) RT3_ACC_SCALE));
+        float m = (float) ((double) accum[3 * idx + c] / ((double) P.resolve_spp * (double) RT3_ACC_SCALE));
         if (gamma) { m = sqrtf(m); }
         ch[c] = unorm8(m);
     }

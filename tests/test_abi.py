@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(built):
 def test_struct_layouts_match_header():
     assert abi.FACE_DTYPE.itemsize == 48 and abi.VERTEX_DTYPE.itemsize == 16 and abi.MATERIAL_DTYPE.itemsize == 32
     assert C.sizeof(abi.Camera) == 4 * (12 + 1 + 6)
-    assert C.sizeof(abi.Params) == 40
+    assert C.sizeof(abi.Params) == 44
     assert C.sizeof(abi.Scene) == 8 + 4 * 8 + 8 + 5 * 8
     assert C.sizeof(abi.Stats) == 4 * 8 + 3 * 8 + 8 + 3 * 8 + 8
 

@@ -137,3 +137,27 @@ def test_full_size_properties(gpu_ctx):
     strip = abi.make_params(w, h, mode=abi.MODE_PATHTRACE, spp=100, max_depth=50, seed=1, tile_rows=1, part_index=112, part_count=225)
     cpu, _, _ = ol.oracle_pathtrace(scene, cam, strip)
     assert np.array_equal(a[112], cpu[112])
+
+
+def test_progressive_refinement_equals_one_shot(gpu_ctx):
+    """RT3_FLAG_ACCUMULATE (online / progressive mode): k calls of n spp leave exactly the
+    frame of one call of k*n spp -- the accumulators are integers -- and every intermediate frame is the one-shot
+    frame of the samples so far."""
+    w, h = 96, 64
+    scene, cam = scenes.rtiow_cover(w, h)
+    gpu_ctx.upload(scene)
+    base = dict(mode=abi.MODE_PATHTRACE, max_depth=50, seed=5)
+    one_shot = {n: gpu_ctx.render(cam, abi.make_params(w, h, spp=n, **base)) for n in (3, 7, 12)}
+    rays_12 = gpu_ctx.stats().rays
+    rays = 0
+    for first, n in ((0, 3), (3, 4), (7, 5)):
+        frame = gpu_ctx.render(cam, abi.make_params(w, h, spp=n, first_sample=first, flags=abi.FLAG_ACCUMULATE if first else 0, **base))
+        rays += gpu_ctx.stats().rays
+        assert np.array_equal(frame, one_shot[first + n]), f"after {first + n} samples"
+    assert rays == rays_12
+    # a window of samples on its own (no accumulation) is the oracle's frame of those samples
+    params = abi.make_params(w, h, spp=4, first_sample=3, **base)
+    cpu, _, _ = ol.oracle_pathtrace(scene, cam, params)
+    assert np.array_equal(gpu_ctx.render(cam, params), cpu)
+    with pytest.raises(abi.Rt3Error, match="ACCUMULATE"):
+        gpu_ctx.render(cam, abi.make_params(w + 2, h, spp=1, first_sample=12, flags=abi.FLAG_ACCUMULATE, **base))
