@@ -15,6 +15,7 @@
 #include "entities/Sphere.hpp"
 #include "entities/Object.hpp"
 #include "renderer/CudaRenderer.hpp"
+#include "sceneparser/SceneParser.hpp"
 
 using namespace RayTracer;
 
@@ -55,6 +56,20 @@ int rt3host_add_sphere(void* s, const float* center, float radius, uint32_t n_me
 }
 int rt3host_add_object(void* s, const char* path, const float* center, float scale, const float* color) {
     return guarded([&] { ((HostScene*) s)->entities.push_back(ECS::create_object(path, v3(center), scale, v3(color))); });
+}
+
+/* SceneLang front end: appends the entities of a .scene text to the scene; returns how many were added through *n_added
+ * and the warnings (newline separated) through rt3host_last_error when there are any. */
+int rt3host_add_scene_text(void* s, const char* text, const char* base_dir, uint32_t* n_added) {
+    HostScene* hs = (HostScene*) s;
+    return guarded([&] {
+        ParsedScene parsed;
+        SceneParser::parse_string(text, base_dir ? base_dir : "", parsed);
+        for (size_t i = 0; i < parsed.entities.size(); i++) { hs->entities.push_back(parsed.entities[i]); }
+        if (n_added) { *n_added = (uint32_t) parsed.entities.size(); }
+        g_error.clear();
+        for (const std::string& w : parsed.warnings) { g_error += w + "\n"; }
+    });
 }
 
 /* CPU-only flatten of one entity list (no device needed): the arrays prerender() would upload. */
@@ -124,6 +139,19 @@ int rt3host_render(void* s, uint32_t width, uint32_t height, float focal, float 
         std::memcpy(frame_out, hs->camera.get_frame().d(), sizeof(uint32_t) * (size_t) width * height);
         if (device_ms) { *device_ms = hs->renderer->stats().device_ms; }
         if (rays) { *rays = hs->renderer->stats().rays; }
+    });
+}
+/* CudaRenderer::render_progressive with the reference camera; frames_out receives every pass's frame (passes * W * H words). */
+int rt3host_render_progressive(void* s, uint32_t width, uint32_t height, float focal, float vw, float vh, uint32_t passes, uint32_t* frames_out) {
+    HostScene* hs = (HostScene*) s;
+    if (!hs->renderer) { g_error = "create the renderer first"; return -1; }
+    return guarded([&] {
+        hs->camera.update(width, height, focal, vw, vh);
+        struct Sink { uint32_t* out; size_t n; } sink = { frames_out, (size_t) width * height };
+        hs->renderer->render_progressive(hs->camera, passes, [](uint32_t pass, const Frame& f, void* user) {
+            Sink* k = (Sink*) user;
+            std::memcpy(k->out + (size_t) pass * k->n, f.d(), sizeof(uint32_t) * k->n);
+        }, &sink);
     });
 }
 int rt3host_camera_vectors(uint32_t width, uint32_t height, const float* look, float* out19) {

@@ -156,7 +156,17 @@ void CudaRenderer::prerender(const Tools::Array<ECS::RenderEntity*>& entities) {
     check(rt3_scene_upload(this->ctx, &scene), "Could not upload the scene");
 }
 
-void CudaRenderer::render(Camera& camera) const {
+void CudaRenderer::render(Camera& camera) const { this->render_samples(camera, 0, false); }
+
+void CudaRenderer::render_progressive(Camera& camera, uint32_t passes, FrameCallback on_frame, void* user) const {
+    if (this->settings.mode != RT3_MODE_PATHTRACE) { DLOG(fatal, "Progressive rendering needs the path-tracing mode."); }
+    for (uint32_t pass = 0; pass < passes; pass++) {
+        this->render_samples(camera, pass * this->settings.spp, pass > 0);
+        if (on_frame) { on_frame(pass, camera.get_frame(), user); }
+    }
+}
+
+void CudaRenderer::render_samples(Camera& camera, uint32_t first_sample, bool accumulate) const {
     rt3_camera cam;
     std::memset(&cam, 0, sizeof cam);
     const glm::vec3* src[4] = { &camera.origin, &camera.horizontal, &camera.vertical, &camera.lower_left_corner };
@@ -176,7 +186,8 @@ void CudaRenderer::render(Camera& camera) const {
     params.spp = this->settings.spp;
     params.max_depth = this->settings.max_depth;
     params.seed = this->settings.seed;
-    params.flags = this->settings.flags;
+    params.flags = this->settings.flags | (accumulate ? RT3_FLAG_ACCUMULATE : 0u);
+    params.first_sample = first_sample;
     params.tile_rows = this->settings.tile_rows;
     params.part_index = this->settings.part_index;
     params.part_count = this->settings.part_count;

@@ -52,6 +52,7 @@ namespace RayTracer {
         CudaRenderSettings settings;
         std::map<size_t, Material> materials;
         mutable rt3_stats last_stats;
+        void render_samples(Camera& camera, uint32_t first_sample, bool accumulate) const;
 
     public:
         explicit CudaRenderer(int device = 0);
@@ -66,6 +67,14 @@ namespace RayTracer {
 
         virtual void prerender(const Tools::Array<ECS::RenderEntity*>& entities);
         virtual void render(Camera& camera) const;
+
+        /* Online / progressive mode (the headless counterpart of the reference's VulkanOnlineRenderer frame loop,
+         * VulkanOnlineRenderer.cpp:637-735): `passes` renders of settings.spp samples each into the same accumulators
+         * (RT3_FLAG_ACCUMULATE); after every pass the camera's frame holds the image over all samples so far and
+         * `on_frame(pass, camera.get_frame())` is called if given. The last frame equals one render() of
+         * passes * spp samples bit for bit. Path tracing only. */
+        typedef void (*FrameCallback)(uint32_t pass, const Frame& frame, void* user);
+        void render_progressive(Camera& camera, uint32_t passes, FrameCallback on_frame = nullptr, void* user = nullptr) const;
 
         /* Device timings / ray counters of the last render(). */
         const rt3_stats& stats() const { return this->last_stats; }

@@ -2,7 +2,8 @@
  * (create renderer, camera, entities; prerender; render; save), with the scene chosen by name.
  *
  *   rt3_render [-W width] [-H height] [-s scene] [-o out.ppm|out.png] [--teddy path/to/teddy.obj]
- *   scenes: default (reference Main.cpp:280-283, needs --teddy), triangle, sphere, rtiow (path traced, C1)
+ *   scenes: default (reference Main.cpp:280-283, needs --teddy), triangle, sphere, rtiow (path traced, C1),
+ *           or the path of a SceneLang file (*.scene)
  */
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +16,7 @@
 #include "entities/Sphere.hpp"
 #include "entities/Object.hpp"
 #include "renderer/CudaRenderer.hpp"
+#include "sceneparser/SceneParser.hpp"
 
 using namespace RayTracer;
 
@@ -39,6 +41,11 @@ int main(int argc, const char** argv) {
         if (scene == "default") {
             entities.push_back(ECS::create_object(teddy, {0.0f, 0.0f, -3.0f}, 1.0f / 17.0f, {1.0f, 0.0f, 0.0f}));
             entities.push_back(ECS::create_sphere({-2.0f, 0.0f, -5.0f}, 1.0f, 8, 8, {0.0f, 0.0f, 1.0f}));
+        } else if (scene.size() > 6 && scene.compare(scene.size() - 6, 6, ".scene") == 0) {
+            ParsedScene parsed;                                  /* SceneLang file (reference src/lib/sceneparser/SceneLang.md) */
+            SceneParser::parse_file(scene, parsed);
+            for (const std::string& w : parsed.warnings) { std::fprintf(stderr, "warning: %s\n", w.c_str()); }
+            for (size_t i = 0; i < parsed.entities.size(); i++) { entities.push_back(parsed.entities[i]); }
         } else if (scene == "sphere") {
             entities.push_back(ECS::create_sphere({0.0f, 0.0f, -3.0f}, 1.0f, 8, 8, {1.0f, 0.0f, 0.0f}));
         } else if (scene == "rtiow") {

@@ -28,6 +28,8 @@ def lib():
         L.rt3host_prerender.argtypes = [vp]
         L.rt3host_render.argtypes = [vp, u32, u32, C.c_float, C.c_float, C.c_float, fp, vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.rt3host_camera_vectors.argtypes = [u32, u32, fp, fp]
+        L.rt3host_render_progressive.argtypes = [vp, u32, u32, C.c_float, C.c_float, C.c_float, u32, vp]
+        L.rt3host_add_scene_text.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(u32)]
         L.rt3host_write_image.argtypes = [vp, u32, u32, C.c_char_p, C.c_int]
         _lib = L
     return _lib
@@ -68,6 +70,12 @@ class HostScene:
     def add_object(self, path, center, scale, color):
         self._ok(self.L.rt3host_add_object(self.h, path.encode(), _f(center), scale, _f(color)))
 
+    def add_scene_text(self, text, base_dir=""):
+        """SceneLang (reference src/lib/sceneparser/SceneLang.md): appends the file's entities; returns (count, warnings)."""
+        n = C.c_uint32()
+        self._ok(self.L.rt3host_add_scene_text(self.h, text.encode(), str(base_dir).encode(), C.byref(n)))
+        return n.value, [w for w in self.L.rt3host_last_error().decode().split("\n") if w]
+
     def flatten(self) -> abi.SceneArrays:
         nf, nv = C.c_uint32(), C.c_uint32()
         self._ok(self.L.rt3host_flatten(self.h, C.byref(nf), C.byref(nv), None, None, None))
@@ -95,6 +103,12 @@ class HostScene:
         self._ok(self.L.rt3host_render(self.h, width, height, focal, vw, vh, _f(look) if look is not None else None, frame.ctypes.data,
                                        C.byref(ms), C.byref(rays)))
         return frame, ms.value, rays.value
+
+    def render_progressive(self, width, height, passes, focal=2.0, vh=2.0):
+        frames = np.zeros((passes, height, width), np.uint32)
+        vw = float(np.float32(np.float32(width) / np.float32(height)) * np.float32(2.0))
+        self._ok(self.L.rt3host_render_progressive(self.h, width, height, focal, vw, vh, passes, frames.ctypes.data))
+        return frames
 
     def close(self):
         if self.h:

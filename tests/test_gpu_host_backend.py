@@ -77,3 +77,22 @@ def test_device_frame_to_bytes(gpu_ctx, channels):
         assert np.array_equal(got[: w * h * channels], want.ravel()) and not got[w * h * channels:].any()
     with pytest.raises(abi.Rt3Error, match="channels"):
         gpu_ctx.frame_bytes(d_frame.data_ptr(), d_out.data_ptr(), w, h, 2)
+
+
+def test_progressive_mode_through_the_host_backend(built):
+    """CudaRenderer::render_progressive: pass k's frame is the one-shot frame of (k + 1) * spp samples."""
+    w, h = 80, 45
+    def scene(spp):
+        hs = hostlib.HostScene()
+        n, _ = hs.add_scene_text('''entities {
+            sphere ground { center: 0.0 -100.5 -1.0; radius: 100.0; n_meridians: 8; n_parallels: 8; color: 0.8 0.8 0.0; }
+            sphere ball   { center: 0.0 0.0 -1.0;    radius: 0.5;   n_meridians: 8; n_parallels: 8; color: 0.1 0.2 0.5; } }''')
+        assert n == 2
+        hs.create_renderer(mode=abi.MODE_PATHTRACE, spp=spp, max_depth=20, seed=4, analytic_spheres=True)
+        hs.prerender()
+        return hs
+    frames = scene(3).render_progressive(w, h, 4, focal=1.0)
+    for k in (0, 1, 3):
+        one_shot, _, _ = scene(3 * (k + 1)).render(w, h, focal=1.0)
+        assert np.array_equal(frames[k], one_shot), f"pass {k}"
+    assert not np.array_equal(frames[0], frames[3])
