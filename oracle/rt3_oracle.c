@@ -195,14 +195,18 @@ int orc_render_reference(const rt3_scene* scene, const rt3_camera* cam, uint32_t
 #define RT3_ACC_SCALE 16777216.0f /* 2^24 fixed-point radiance */
 
 /* Path-mode sphere: half-b form with a unit direction, near root then far
- * root, accepted iff tmin <= t < best (appendix C "Sphere hit"). */
+ * root, accepted iff tmin <= t < best (appendix C "Sphere hit"). The dot
+ * products and the discriminant are chains of fused multiply-adds (fmaf, one
+ * rounding each), written out in a fixed order -- the contraction a GLSL
+ * compiler may apply to raytracer_v4.glsl:157-178, made explicit so that the
+ * CUDA kernel (exact_sphere_path, __fmaf_rn in the same order) agrees bit for bit. */
 static hit_rec closest_sphere_path(const rt3_scene* s, v3 o, v3 d, hit_rec best) {
     for (uint32_t i = 0; i < s->n_spheres; i++) {
         const rt3_sphere* sp = &s->spheres[i];
         v3 oc = vsub(o, V(sp->cx, sp->cy, sp->cz));
-        float h = dot3(oc, d);
-        float c = dot3(oc, oc) - sp->r * sp->r;
-        float disc = h * h - c;
+        float h = fmaf(oc.x, d.x, fmaf(oc.y, d.y, oc.z * d.z));
+        float c = fmaf(oc.x, oc.x, fmaf(oc.y, oc.y, fmaf(oc.z, oc.z, -(sp->r * sp->r))));
+        float disc = fmaf(h, h, -c);
         if (!(disc >= 0.0f)) { continue; }
         float sq = sqrtf(disc);
         float t = -h - sq;

@@ -213,13 +213,16 @@ __device__ __forceinline__ void exact_sphere_v4(uint32_t prim, float4 sp, rt3_ve
 }
 
 /* Exact ray-sphere test, bounce loop: half-b form with a unit direction, near
- * then far root, accepted iff tmin <= t < best. */
+ * then far root, accepted iff tmin <= t < best. This part
+ * of the path has no implementation in the reference; its arithmetic is the
+ * oracle's, which spells the dot products out as fused multiply-adds. */
 template <bool ORDERED>
 __device__ __forceinline__ void exact_sphere_path(uint32_t prim, float4 sp, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
     rt3_vec3 oc = o - v3(sp.x, sp.y, sp.z);
-    float h = dot3(oc, d);
-    float c = dot3(oc, oc) - sp.w * sp.w;
-    float disc = h * h - c;
+    /* explicit fused multiply-adds, in the oracle's order (oracle/rt3_oracle.c closest_sphere_path) */
+    float h = __fmaf_rn(oc.x, d.x, __fmaf_rn(oc.y, d.y, oc.z * d.z));
+    float c = __fmaf_rn(oc.x, oc.x, __fmaf_rn(oc.y, oc.y, __fmaf_rn(oc.z, oc.z, -(sp.w * sp.w))));
+    float disc = __fmaf_rn(h, h, -c);
     float sq = sqrtf(disc < 0.0f ? 1.0f : disc); /* a miss takes the root of 1: see exact_sphere_v4 */
     float t1 = -h - sq, t2 = -h + sq;
     bool ok1 = t1 >= RT3_TMIN && closer<ORDERED>(t1, prim, best);
