@@ -37,7 +37,8 @@ NCU_DRAM_BYTES_PER_LAUNCH = 23154176 + 256          # profiles/r01_v3_ncu_summar
 
 
 def workload_config():
-    return {"workload": f"RTIOW book-1 cover scene, {W}x{H}, {SPP} spp, depth {DEPTH} (BASELINE configs[1])",
+    which = "configs[1]" if (W, H, SPP) == (1200, 800, 500) else "configs[3]: not the configuration the metric is quoted on"
+    return {"workload": f"RTIOW book-1 cover scene, {W}x{H}, {SPP} spp, depth {DEPTH} (BASELINE {which})",
             "width": W, "height": H, "spp": SPP, "max_depth": DEPTH, "tile_rows": TILE_ROWS,
             "l2": "256 MiB buffer written between timed steps (L2 flush); scene+accumulators re-read from HBM"}
 
@@ -136,6 +137,7 @@ def run_reference_arm(args):
 
 
 def main():
+    global W, H, SPP
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -143,8 +145,14 @@ def main():
     ap.add_argument("--impl", default="rt3", choices=["rt3", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="override samples per pixel (non-default values are not the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4"],
+                    help="c2 (default, the metric's configuration) or c4: the same scene at 3840x2160, 1024 spp (BASELINE configs[3], the multi-GPU one)")
     ap.add_argument("--bvh", action="store_true", help="time the hierarchy path (RT3_FLAG_BVH) instead of the brute-force sweep: not the headline configuration")
     args = ap.parse_args()
+    if args.config == "c4":
+        W, H, SPP = 3840, 2160, 1024
+        if args.spp == 500:
+            args.spp = SPP
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -275,7 +283,7 @@ def main():
                     "last_step_device_ms": st_e2e.device_ms, "last_step_d2h_ms": st_e2e.d2h_ms,
                     "path": "rt3_render (C ABI), pinned host frame" if world == 1 else "rt3_render_device + NCCL gather + D2H on rank 0"},
             "roofline": {"bound": "fp32-issue", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and spp == SPP and not args.bvh) else None,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and spp == SPP and args.config == "c2" and not args.bvh) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one pathtrace_kernel launch of this workload, ncu --set full "
                                            "(profiles/r01_v3_ncu_summary.txt); the accumulators, the scene is 13 KB",
                          "kernel": "pathtrace_kernel", "kernel_ms": st.trace_kernel_ms,

@@ -147,15 +147,15 @@ __global__ void bvh_refit_kernel(int n, const uint32_t* __restrict__ vals, const
 #define RT3_BVH_ROBUST 1.00000095367431640625f
 
 struct rt3_bvh_ray {
-    rt3_vec3 o, inv;
-    float grow; /* per-ray widening of every box */
+    rt3_vec3 o_lo, o_hi, inv; /* o + grow, o - grow: the per-ray widening of every box, moved onto the origin */
 };
 
 __device__ __forceinline__ bool bvh_slab(const rt3_bvh_ray& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float limit,
                                          float& t_in) {
-    const float x0 = ((lox - r.grow) - r.o.x) * r.inv.x, x1 = ((hix + r.grow) - r.o.x) * r.inv.x;
-    const float y0 = ((loy - r.grow) - r.o.y) * r.inv.y, y1 = ((hiy + r.grow) - r.o.y) * r.inv.y;
-    const float z0 = ((loz - r.grow) - r.o.z) * r.inv.z, z1 = ((hiz + r.grow) - r.o.z) * r.inv.z;
+    /* (lo - grow) - o == lo - (o + grow) up to one rounding of o + grow, which is 2^-24 |o| against grow = 2^-9 |o| */
+    const float x0 = (lox - r.o_lo.x) * r.inv.x, x1 = (hix - r.o_hi.x) * r.inv.x;
+    const float y0 = (loy - r.o_lo.y) * r.inv.y, y1 = (hiy - r.o_hi.y) * r.inv.y;
+    const float z0 = (loz - r.o_lo.z) * r.inv.z, z1 = (hiz - r.o_hi.z) * r.inv.z;
     /* fminf / fmaxf return the other operand for a NaN (0 * inf: origin on a slab plane of an axis the ray is parallel to) */
     const float tin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
     const float tout = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
@@ -172,9 +172,10 @@ __device__ __forceinline__ void bvh_closest_hit(const rt3_scene_view& S, const r
     best.prim = RT3_NO_HIT;
     if (B.n_prims == 0u) { return; }
     rt3_bvh_ray r;
-    r.o = o;
+    const float grow = B.ray_margin * sqrtf(dot3(o, o));
+    r.o_lo = v3(o.x + grow, o.y + grow, o.z + grow);
+    r.o_hi = v3(o.x - grow, o.y - grow, o.z - grow);
     r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    r.grow = B.ray_margin * sqrtf(dot3(o, o));
     int32_t stack_ref[RT3_BVH_STACK];
     float stack_tin[RT3_BVH_STACK];
     int sp = 0;

@@ -610,7 +610,7 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     const uint32_t np_pad = (np + RT3_PAD_PRIMS - 1) / RT3_PAD_PRIMS * RT3_PAD_PRIMS;
     std::vector<Bound> bounds(np);
     std::vector<float4> box_lo(np ? np : 1), box_hi(np ? np : 1); /* hierarchy leaves: the primitive's box, widened like its bounding sphere */
-    const float finf = std::numeric_limits<float>::infinity();
+    const float finf = std::numeric_limits<float>::infinity(), fnan = std::numeric_limits<float>::quiet_NaN();
     std::vector<float4> fn(nf), p1(nf), p2(nf), p3(nf), sph(ns), color(np), mats((size_t) s->n_materials * 2);
     std::vector<uint32_t> pmat(np, RT3_NO_HIT), pent(np, 0u);
 
@@ -643,7 +643,7 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
             box_hi[i] = make_float4(round_up(std::max({ da[0], db[0], dc[0] }) + m), round_up(std::max({ da[1], db[1], dc[1] }) + m),
                                     round_up(std::max({ da[2], db[2], dc[2] }) + m), 0.f);
         } else {
-            box_lo[i] = make_float4(finf, finf, finf, 0.f); box_hi[i] = make_float4(-finf, -finf, -finf, 0.f); /* empty */
+            box_lo[i] = make_float4(fnan, fnan, fnan, 0.f); box_hi[i] = make_float4(fnan, fnan, fnan, 0.f); /* never entered (every comparison of the slab test fails), ignored by fminf / fmaxf unions */
         }
         color[i] = make_float4(f.color[0], f.color[1], f.color[2], 0.f);
         if (s->face_material) {
@@ -662,7 +662,7 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
             box_lo[nf + i] = make_float4(round_down(c[0] - R), round_down(c[1] - R), round_down(c[2] - R), 0.f);
             box_hi[nf + i] = make_float4(round_up(c[0] + R), round_up(c[1] + R), round_up(c[2] + R), 0.f);
         } else {
-            box_lo[nf + i] = make_float4(finf, finf, finf, 0.f); box_hi[nf + i] = make_float4(-finf, -finf, -finf, 0.f);
+            box_lo[nf + i] = make_float4(fnan, fnan, fnan, 0.f); box_hi[nf + i] = make_float4(fnan, fnan, fnan, 0.f);
         }
         if (s->sphere_color) { color[nf + i] = make_float4(s->sphere_color[3 * i], s->sphere_color[3 * i + 1], s->sphere_color[3 * i + 2], 0.f); }
         else { color[nf + i] = make_float4(1.f, 1.f, 1.f, 0.f); }
