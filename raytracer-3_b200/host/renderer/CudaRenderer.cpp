@@ -38,6 +38,7 @@ CudaRenderSettings CudaRenderSettings::from_environment(int* device) {
     s.seed = env_u32("RT3_SEED", s.seed);
     s.analytic_spheres = env_u32("RT3_ANALYTIC_SPHERES", 0) != 0;
     s.device_tessellation = env_u32("RT3_DEVICE_TESSELLATION", 0) != 0;
+    s.bvh_above = env_u32("RT3_BVH_ABOVE", s.bvh_above);
     if (env_u32("RT3_BVH", 0) != 0) { s.flags |= RT3_FLAG_BVH; }
     if (device) { *device = (int) env_u32("RT3_DEVICE", 0); }
     return s;
@@ -187,6 +188,7 @@ void CudaRenderer::render_samples(Camera& camera, uint32_t first_sample, bool ac
     params.max_depth = this->settings.max_depth;
     params.seed = this->settings.seed;
     params.flags = this->settings.flags | (accumulate ? RT3_FLAG_ACCUMULATE : 0u);
+    if (this->flat_faces.size() + this->flat_spheres.size() > (size_t) this->settings.bvh_above) { params.flags |= RT3_FLAG_BVH; }
     params.first_sample = first_sample;
     params.tile_rows = this->settings.tile_rows;
     params.part_index = this->settings.part_index;

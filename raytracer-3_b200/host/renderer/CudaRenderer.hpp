@@ -40,10 +40,14 @@ namespace RayTracer {
         uint32_t max_depth = 50;
         uint32_t seed = 1;
         uint32_t flags = 0;
+        /* Closest hits through the device-built hierarchy (RT3_FLAG_BVH) when the scene has more primitives than this;
+         * the brute-force sweep below it. The two give identical frames, so this is purely a matter of speed:
+         * the sweep wins while its records stay in the constant cache. 0 = always the hierarchy, UINT32_MAX = never. */
+        uint32_t bvh_above = 768;
         bool analytic_spheres = false;      /* keep ECS spheres analytic instead of tessellating them */
         bool device_tessellation = false;   /* tessellate ECS spheres on the device (rt3_tessellate_spheres) instead of the CPU */
         uint32_t tile_rows = 8, part_index = 0, part_count = 1;
-        /* Reads RT3_MODE (reference|pathtrace), RT3_SPP, RT3_DEPTH, RT3_SEED, RT3_ANALYTIC_SPHERES, RT3_DEVICE_TESSELLATION, RT3_BVH, RT3_DEVICE. */
+        /* Reads RT3_MODE (reference|pathtrace), RT3_SPP, RT3_DEPTH, RT3_SEED, RT3_ANALYTIC_SPHERES, RT3_DEVICE_TESSELLATION, RT3_BVH, RT3_BVH_ABOVE, RT3_DEVICE. */
         static CudaRenderSettings from_environment(int* device);
     };
 
