@@ -36,6 +36,17 @@ NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 NCU_DRAM_BYTES_PER_LAUNCH = 23154176 + 256          # profiles/r01_v3_ncu_summary.txt (N = 1, the BASELINE config)
 
 
+def hbm_line(kernel_ms):
+    """Achieved DRAM bandwidth of the dominant kernel (ncu traffic / event time) against the measured copy bandwidth."""
+    peak, src = 6650.0, "fallback of /opt/skills/guides/B200_PROFILING.md"
+    try:
+        peak, src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        pass
+    achieved = NCU_DRAM_BYTES_PER_LAUNCH / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    return {"achieved_gbs": achieved, "peak_gbs": peak, "frac": achieved / peak, "peak_source": src}
+
+
 def workload_config():
     which = "configs[1]" if (W, H, SPP) == (1200, 800, 500) else "configs[3]: not the configuration the metric is quoted on"
     return {"workload": f"RTIOW book-1 cover scene, {W}x{H}, {SPP} spp, depth {DEPTH} (BASELINE {which})",
@@ -291,7 +302,8 @@ def main():
                          "peak_source": "FFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
                          "note": "the path is neither HBM- nor tensor-bound (DRAM 0.002 % busy): achieved = 17 algorithmic FLOP per ray-sphere test / kernel time; "
                                  "the conservative prefilter executes 3 FMA per test, so the fraction can exceed 1 (DESIGN.md 3.1)",
-                         "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS},
+                         "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
+                         "hbm": hbm_line(st.trace_kernel_ms) if (world == 1 and spp == SPP and args.config == "c2" and not args.bvh) else None},
         }
         if args.bvh:
             line["config"]["workload"] += " [--bvh: hierarchy traversal instead of the brute-force sweep; roofline figures do not apply]"
