@@ -463,8 +463,11 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
         const uint32_t dim = RT3_DIM_BOUNCE0 + RT3_DIMS_PER_BOUNCE * s.bounce;
         const uint32_t k = s.key;
         rt3_vec3 nd;
+        /* every material's first draws are dims +0 and +1 (the oracle's layout); drawn once, ahead of the
+         * material branches, so that a warp with mixed materials runs the hash and the sincos polynomial once */
+        const float xi0 = rt3_draw(k, dim + 0), xi1 = rt3_draw(k, dim + 1);
+        const rt3_vec3 uv = unit_vector(xi0, xi1);
         if (kind == RT3_MAT_LAMBERTIAN) {
-            rt3_vec3 uv = unit_vector(rt3_draw(k, dim + 0), rt3_draw(k, dim + 1));
             nd = n + uv;
             if (fabsf(nd.x) < 1e-8f && fabsf(nd.y) < 1e-8f && fabsf(nd.z) < 1e-8f) { nd = n; }
             s.thr = s.thr * albedo;
@@ -473,7 +476,6 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
             nd = dr - (2.0f * dnn) * n;
             float fz = fuzz < 1.0f ? fuzz : 1.0f;
             if (fz > 0.0f) {
-                rt3_vec3 uv = unit_vector(rt3_draw(k, dim + 0), rt3_draw(k, dim + 1));
                 float a = rt3_draw(k, dim + 2), b = rt3_draw(k, dim + 3), c = rt3_draw(k, dim + 4);
                 float mx = a < b ? b : a;
                 mx = mx < c ? c : mx;
@@ -493,7 +495,7 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
             float w = 1.0f - cs;
             float w2 = w * w;
             float schlick = r0 + (1.0f - r0) * ((w2 * w2) * w);
-            if (cannot_refract || schlick > rt3_draw(k, dim + 0)) {
+            if (cannot_refract || schlick > xi0) {
                 float dnn = dot3(dr, n);
                 nd = dr - (2.0f * dnn) * n;
             } else {
