@@ -523,9 +523,9 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
 }
 
 /* Persistent multi-bounce path tracer. Every thread owns RT3_RAYS path slots whose state lives in
- * shared memory; a loop iteration (1) takes the slots in turn through one copy of the shading and
- * regeneration code -- shade the hit the last sweep found, then start the next (pixel, sample) item
- * if the slot is free, so that all lanes sweep live rays -- and (2) sweeps the scene for all slots. */
+ * shared memory; a loop iteration (1) takes the slots in turn through one copy of the shading code
+ * (the hit the last sweep found), then gives every free slot of the warp the next (pixel, sample) item,
+ * so that all lanes sweep live rays, and (2) sweeps the scene for all slots. */
 template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL>
 __global__ void __launch_bounds__(RT3_CTA_THREADS, RT3_CTAS_PER_SM)
 pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P, unsigned long long* __restrict__ accum,
@@ -555,11 +555,15 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
     }
     unsigned long long rays = 0;
     uint32_t visits = 0, tests = 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned lane_lt = (1u << lane) - 1u;
+    uint32_t* const exchange = sm.masks + (threadIdx.x & ~31u); /* [field][this warp's 32 columns] */
+    static_assert(RT3_RAYS * RT3_CHUNK_WORDS >= 8, "the exchange area needs eight mask words per thread");
     rt3_chunk chunk;
     chunk.cur = chunk.end = chunk.start = 0; chunk.pixel0 = chunk.sample0 = 0; chunk.dry = false;
 
     for (;;) {
-        bool any = false;
+        /* (1a) slot by slot through one copy of the shading code: shade the hit the last sweep found */
 #pragma unroll 1
         for (int r = 0; r < R; r++) {
             rt3_path s;
@@ -571,16 +575,54 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
                 best.t = slot_float(sm, r, RT3_F_BEST_T); best.prim = slot_word(sm, r, RT3_F_BEST_PRIM);
                 rays++;
                 shade_path(s, best, S, P, accum);
-            }
-            uint32_t p = 0, sample = 0;
-            if (claim_item(s.bounce == RT3_NO_HIT, chunk, P, &counters[0], p, sample)) { start_path(s, C, P, p, sample); }
-            slot_word(sm, r, RT3_F_BOUNCE) = s.bounce;
-            if (s.bounce != RT3_NO_HIT) {
-                slot_store_vec(sm, r, RT3_F_OX, s.o); slot_store_vec(sm, r, RT3_F_DX, s.d); slot_store_vec(sm, r, RT3_F_TX, s.thr);
-                slot_word(sm, r, RT3_F_KEY) = s.key; slot_word(sm, r, RT3_F_PIX) = s.pix;
-                any = true;
+                slot_word(sm, r, RT3_F_BOUNCE) = s.bounce;
+                if (s.bounce != RT3_NO_HIT) { slot_store_vec(sm, r, RT3_F_OX, s.o); slot_store_vec(sm, r, RT3_F_DX, s.d); slot_store_vec(sm, r, RT3_F_TX, s.thr); }
             }
         }
+        /* (1b) regeneration for all slots at once: the warp's free slots are numbered, and its first lanes
+         * generate that many primary rays (32 per round) into an exchange area -- this warp's columns of
+         * the survivor masks, which are dead between sweeps -- from where the owners of the free slots pick
+         * them up. The generation code runs with as many lanes as there are free slots in the whole warp
+         * instead of once per slot with a third of the lanes. */
+        uint32_t my_rank[R];
+        uint32_t n_free = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const unsigned free_r = __ballot_sync(0xffffffffu, slot_word(sm, r, RT3_F_BOUNCE) == RT3_NO_HIT);
+            my_rank[r] = ((free_r >> lane) & 1u) ? n_free + (uint32_t) __popc(free_r & lane_lt) : RT3_NO_HIT;
+            n_free += (uint32_t) __popc(free_r);
+        }
+        for (uint32_t base = 0; base < n_free && !chunk.dry; base += 32u) {
+            const uint32_t take = n_free - base < 32u ? n_free - base : 32u;
+            rt3_path fresh;
+            uint32_t p = 0, sample = 0;
+            const bool got = claim_item(lane < take, chunk, P, &counters[0], p, sample);
+            if (got) {
+                start_path(fresh, C, P, p, sample);
+                exchange[0 * RT3_CTA_THREADS + lane] = __float_as_uint(fresh.o.x); exchange[1 * RT3_CTA_THREADS + lane] = __float_as_uint(fresh.o.y);
+                exchange[2 * RT3_CTA_THREADS + lane] = __float_as_uint(fresh.o.z); exchange[3 * RT3_CTA_THREADS + lane] = __float_as_uint(fresh.d.x);
+                exchange[4 * RT3_CTA_THREADS + lane] = __float_as_uint(fresh.d.y); exchange[5 * RT3_CTA_THREADS + lane] = __float_as_uint(fresh.d.z);
+                exchange[6 * RT3_CTA_THREADS + lane] = fresh.key; exchange[7 * RT3_CTA_THREADS + lane] = fresh.pix;
+            }
+            const uint32_t n_made = (uint32_t) __popc(__ballot_sync(0xffffffffu, got)); /* the claim serves the lowest lanes first */
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint32_t e = my_rank[r] - base; /* wraps around for slots that are not free */
+                if (my_rank[r] != RT3_NO_HIT && e < n_made) {
+                    slot_word(sm, r, RT3_F_OX) = exchange[0 * RT3_CTA_THREADS + e]; slot_word(sm, r, RT3_F_OY) = exchange[1 * RT3_CTA_THREADS + e];
+                    slot_word(sm, r, RT3_F_OZ) = exchange[2 * RT3_CTA_THREADS + e]; slot_word(sm, r, RT3_F_DX) = exchange[3 * RT3_CTA_THREADS + e];
+                    slot_word(sm, r, RT3_F_DY) = exchange[4 * RT3_CTA_THREADS + e]; slot_word(sm, r, RT3_F_DZ) = exchange[5 * RT3_CTA_THREADS + e];
+                    slot_word(sm, r, RT3_F_KEY) = exchange[6 * RT3_CTA_THREADS + e]; slot_word(sm, r, RT3_F_PIX) = exchange[7 * RT3_CTA_THREADS + e];
+                    slot_word(sm, r, RT3_F_TX) = 0x3f800000u; slot_word(sm, r, RT3_F_TY) = 0x3f800000u; slot_word(sm, r, RT3_F_TZ) = 0x3f800000u;
+                    slot_word(sm, r, RT3_F_BOUNCE) = 0u;
+                }
+            }
+            __syncwarp();
+        }
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < R; r++) { any = any || slot_word(sm, r, RT3_F_BOUNCE) != RT3_NO_HIT; }
         if (RESIDENT) { if (!__any_sync(0xffffffffu, any)) { break; } }   /* warps run independently */
         else { if (!__syncthreads_or(any ? 1 : 0)) { break; } }           /* tiles are CTA-wide */
         if (ACCEL) { traverse_slots(S, B, sm, visits, tests); }
