@@ -526,8 +526,11 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
  * shared memory; a loop iteration (1) takes the slots in turn through one copy of the shading code
  * (the hit the last sweep found), then gives every free slot of the warp the next (pixel, sample) item,
  * so that all lanes sweep live rays, and (2) sweeps the scene for all slots. */
+#ifndef RT3_ACCEL_CTAS_PER_SM
+#define RT3_ACCEL_CTAS_PER_SM RT3_CTAS_PER_SM
+#endif
 template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL>
-__global__ void __launch_bounds__(RT3_CTA_THREADS, RT3_CTAS_PER_SM)
+__global__ void __launch_bounds__(RT3_CTA_THREADS, ACCEL ? RT3_ACCEL_CTAS_PER_SM : RT3_CTAS_PER_SM)
 pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P, unsigned long long* __restrict__ accum,
                  unsigned long long* __restrict__ counters) {
     constexpr int R = RT3_RAYS;

@@ -128,3 +128,24 @@ def test_errors_are_reported_not_swallowed(gpu_ctx):
     with pytest.raises(abi.Rt3Error, match="spp"):
         ctx.render(abi.reference_camera(8, 8), abi.make_params(8, 8, mode=abi.MODE_PATHTRACE, spp=0))
     ctx.close()
+
+
+def test_two_contexts_share_the_constant_bank_correctly(gpu_ctx):
+    """Scenes up to RT3_CONST_PRIMS are swept out of one constant-memory bank per device; contexts with different
+    scenes rendering in turn must each get their own records back (ownership check in claim_constant_bank)."""
+    w, h = 64, 36
+    cam = abi.reference_camera(w, h)
+    other = abi.Context(0)
+    try:
+        scenes_ab = [random_soup(np.random.default_rng(s), 40, 60) for s in (21, 22)]
+        want = [ol.oracle_reference(sc, cam, w, h)[0] for sc in scenes_ab]
+        gpu_ctx.upload(scenes_ab[0])
+        other.upload(scenes_ab[1])
+        for _ in range(3):
+            assert np.array_equal(gpu_ctx.render(cam, abi.make_params(w, h)), want[0])
+            assert np.array_equal(other.render(cam, abi.make_params(w, h)), want[1])
+            pt = abi.make_params(w, h, mode=abi.MODE_PATHTRACE, spp=2, max_depth=4, seed=1)
+            a, b = gpu_ctx.render(cam, pt), other.render(cam, pt)
+            assert np.array_equal(a, gpu_ctx.render(cam, pt)) and np.array_equal(b, other.render(cam, pt)) and not np.array_equal(a, b)
+    finally:
+        other.close()
