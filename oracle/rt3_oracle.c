@@ -2,7 +2,9 @@
  *
  * TEST INFRASTRUCTURE, not product code: see rt3_oracle.h. Built by
  * oracle/Makefile with -O2 -ffp-contract=off -fno-fast-math: every float
- * operation below is one IEEE-754 binary32 operation, in the order written.
+ * operation below is one IEEE-754 binary32 operation, in the order written
+ * (fused multiply-adds appear only where fmaf() is spelled out: the path-mode
+ * sphere discriminant).
  *
  * Parity status
  *   orc_render_reference : PINNED. tests/test_oracle_pinned.py requires its

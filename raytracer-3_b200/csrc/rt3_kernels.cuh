@@ -12,7 +12,8 @@
  * and ray three packed FMAs of a conservative slab test, the records coming
  * from the constant bank through uniform registers (scenes up to
  * RT3_CONST_PRIMS) or from TMA-streamed shared-memory tiles; the exact tests
- * run only on the survivors.
+ * run only on the survivors. With RT3_FLAG_BVH (template parameter ACCEL) the
+ * sweep is replaced by the hierarchy traversal of rt3_bvh.cuh, same results.
  */
 #pragma once
 
