@@ -1,0 +1,63 @@
+"""The built library contains the instructions the design relies on (no GPU needed: cuobjdump on librt3cuda.so).
+
+The sweep's speed hinges on two code-generation facts that a harmless-looking source change can undo without any
+functional symptom: the level-1 test must be packed FMAs (SASS FFMA2) whose primitive operand
+comes through the uniform datapath (LDCU.64 loads from the constant bank; ptxas falls back to per-thread LDC as soon as
+the control flow around the sweep stops looking convergent to it, which costs 20 %), and large scenes must be staged by
+bulk asynchronous copies (UBLKCP)."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from rt3_b200 import abi
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+
+
+@pytest.fixture(scope="module")
+def sass(built):
+    text = subprocess.run(["cuobjdump", "-sass", abi.CORE_LIB_PATH], check=True, capture_output=True, text=True).stdout
+    kernels = {}
+    for block in text.split("Function : ")[1:]:
+        name, _, body = block.partition("\n")
+        kernels[name.strip()] = re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", body, flags=re.M)
+    return kernels
+
+
+def kernel(sass, *needles):
+    names = [n for n in sass if all(x in n for x in needles)]
+    assert len(names) == 1, names
+    return sass[names[0]]
+
+
+def test_built_for_sm_100a(built):
+    out = subprocess.run(["cuobjdump", "-lelf", abi.CORE_LIB_PATH], check=True, capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+@pytest.mark.parametrize("needles", [("pathtrace_kernelILb1ELb1ELb0",), ("pathtrace_kernelILb1ELb0ELb0",),
+                                     ("reference_kernelILb1ELb1ELb0",), ("reference_kernelILb1ELb0ELb0",)])
+def test_constant_bank_sweep_uses_packed_fma_with_uniform_operands(sass, needles):
+    ops = kernel(sass, *needles)
+    ffma2 = sum(op.startswith("FFMA2") for op in ops)
+    ldcu64 = sum(op == "LDCU.64" for op in ops)
+    ldc64 = sum(op == "LDC.64" for op in ops)
+    assert ffma2 >= 96, f"{ffma2} FFMA2"                      # 16 pairs x 2 rays x 3 in the unrolled word (+ the partial-word loop)
+    assert ldcu64 >= 48, f"only {ldcu64} LDCU.64 ({ldc64} LDC.64): the records are no longer read through uniform registers"
+    assert ldc64 < 16, f"{ldc64} LDC.64: per-thread constant loads in the sweep"
+    assert sum(op.startswith("SHF.L.W") for op in ops) >= 64  # sign bits into the survivor masks
+
+
+@pytest.mark.parametrize("needles", [("pathtrace_kernelILb0ELb1ELb0",), ("reference_kernelILb0ELb0ELb0",)])
+def test_streamed_sweep_stages_tiles_with_bulk_copies(sass, needles):
+    ops = kernel(sass, *needles)
+    assert sum(op.startswith("UBLKCP") for op in ops) >= 2, "no cp.async.bulk (UBLKCP) in the streamed kernel"
+    assert sum(op.startswith("FFMA2") for op in ops) >= 96
+    assert any(op.startswith("SYNCS") for op in ops), "no mbarrier instructions"
+
+
+def test_accumulation_is_a_64_bit_reduction(sass):
+    ops = kernel(sass, "pathtrace_kernelILb1ELb1ELb0")
+    assert any(op.startswith("RED") and "64" in op for op in ops)
