@@ -224,10 +224,11 @@ __device__ __forceinline__ void exact_sphere_path(uint32_t prim, float4 sp, rt3_
     float c = __fmaf_rn(oc.x, oc.x, __fmaf_rn(oc.y, oc.y, __fmaf_rn(oc.z, oc.z, -(sp.w * sp.w))));
     float disc = __fmaf_rn(h, h, -c);
     float sq = sqrtf(disc < 0.0f ? 1.0f : disc); /* a miss takes the root of 1: see exact_sphere_v4 */
-    float t1 = -h - sq, t2 = -h + sq;
-    bool ok1 = t1 >= RT3_TMIN && closer<ORDERED>(t1, prim, best);
-    bool ok2 = t2 >= RT3_TMIN && closer<ORDERED>(t2, prim, best);
-    if (disc >= 0.0f && (ok1 || ok2)) { best.prim = prim; best.t = ok1 ? t1 : t2; }
+    /* near root if it is in front of tmin, else the far one; the oracle's "near, then far" gives the same:
+     * t1 <= t2, so a near root that is in front but not closer than `best` rules the far one out too */
+    const float t1 = -h - sq, t2 = -h + sq;
+    const float t = t1 >= RT3_TMIN ? t1 : t2;
+    if (disc >= 0.0f && t >= RT3_TMIN && closer<ORDERED>(t, prim, best)) { best.prim = prim; best.t = t; }
 }
 
 /* Records of scenes up to RT3_CONST_PRIMS live in the constant bank: the sweep
