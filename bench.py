@@ -89,6 +89,27 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in rows)}
 
 
+def usable_cores():
+    """Host cores this process may actually use: the affinity mask, capped by the cgroup CPU quota when there is one."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            fields = open(path).read().split()
+            if path.endswith("cpu.max"):
+                quota, period = fields[0], float(fields[1])
+            else:
+                quota, period = fields[0], float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota not in ("max", "-1") and period > 0:
+                n = max(1, min(n, int(float(quota) / period + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return n
+
+
 def cpu_port_rate(n_threads, steps=1, warmup=0):
     """Mrays/s of the oracle port on a bounded sample of the workload (all ray segments counted)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -133,7 +154,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_threads = os.cpu_count() or 1
+    n_threads = usable_cores()
     rate, sec_per_step, sample = cpu_port_rate(n_threads, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": rate, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -312,7 +333,7 @@ def main():
             line["config"]["workload"] += f" [OVERRIDE spp={spp}: not the BASELINE config]"
             line["config"]["spp"] = spp
         if world == 1 and not args.no_cpu_baseline:
-            n_threads = os.cpu_count() or 1
+            n_threads = usable_cores()
             rate, _, sample = cpu_port_rate(n_threads)
             line["cpu_baseline"] = {"value": rate, "unit": "Mrays/s", "cores": n_threads, "kind": "port", "sample": sample}
             line["reference_native"] = reference_native_rate()

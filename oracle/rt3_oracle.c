@@ -202,6 +202,12 @@ int orc_render_reference(const rt3_scene* scene, const rt3_camera* cam, uint32_t
  * rounding each), written out in a fixed order -- the contraction a GLSL
  * compiler may apply to raytracer_v4.glsl:157-178, made explicit so that the
  * CUDA kernel (exact_sphere_path, __fmaf_rn in the same order) agrees bit for bit. */
+/* fmaf() through libm is a slow software routine where glibc has no FMA dispatch for it; cloned for FMA hardware
+ * (resolved when the library loads) so that the CPU baseline is not handicapped. The results are the same: one
+ * rounding per fmaf either way. */
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("fma", "default")))
+#endif
 static hit_rec closest_sphere_path(const rt3_scene* s, v3 o, v3 d, hit_rec best) {
     for (uint32_t i = 0; i < s->n_spheres; i++) {
         const rt3_sphere* sp = &s->spheres[i];
