@@ -63,4 +63,13 @@ for name in (sys.argv[1:] or list(CONFIGS)):
         if flag:
             out["bvh_build_ms"] = round(st.accel_build_ms, 3)
     out["frames_identical"] = bool(np.array_equal(frames["sweep"], frames["bvh"]))
+    if c["spp"] != c["full_spp"]:
+        # the configured sample count through the hierarchy (and through the sweep where that takes seconds, not minutes)
+        for path, flag in (("bvh", abi.FLAG_BVH),) + ((("sweep", 0),) if name == "c4" else ()):
+            params = abi.make_params(c["w"], c["h"], mode=abi.MODE_PATHTRACE, spp=c["full_spp"], max_depth=c["depth"], seed=1, flags=c.get("flags", 0) | flag)
+            ctx.render(cam, params)
+            st = ctx.stats()
+            out[path + "_full_spp_device_ms"] = round(st.device_ms, 2)
+            out[path + "_full_spp_mrays_s"] = round(st.rays / st.device_ms / 1e3, 1)
+            out["full_spp_rays"] = st.rays
     print(json.dumps(out), flush=True)
