@@ -12,7 +12,7 @@ spheres = np.array([(0, -101, -3, 100), (2.2, 0, -3, 1), (-2.2, 0, -3, 1)], np.f
 scene = abi.SceneArrays(faces=mesh.faces, vertices=mesh.vertices, face_entity=mesh.face_entity, spheres=spheres, sphere_material=np.arange(3, dtype=np.uint32), sphere_entity=np.arange(1, 4, dtype=np.uint32), materials=mats)
 w, h = 1920, 1080
 ctx = abi.Context(0); ctx.upload(scene)
-p = abi.make_params(w, h, mode=abi.MODE_PATHTRACE, spp=2, max_depth=50, seed=1, flags=abi.FLAG_BVH)
+p = abi.make_params(w, h, mode=abi.MODE_PATHTRACE, spp=32, max_depth=50, seed=1, flags=abi.FLAG_BVH)
 for _ in range(2):
     ctx.render(abi.reference_camera(w, h), p); st = ctx.stats()
     print("ms", st.trace_kernel_ms, "rays", st.rays, "visits/ray", st.accel_node_visits / st.rays, "tests/ray", st.accel_prim_tests / st.rays)
