@@ -24,11 +24,21 @@
 
 #define RT3_BVH_STACK 128 /* >= depth of a radix tree over 63-bit keys + index bits */
 
-struct rt3_bvh_view {
-    const float4* nodes; /* 4 float4 per internal node: (lo0.xyz, hi0.x) (hi0.yz, lo1.xy) (lo1.z, hi1.xyz) (ref0, ref1, -, -) */
-    int32_t root;        /* reference of the root (a leaf when the scene has one primitive) */
+/* Two trees, one over the faces and one over the analytic spheres, walked one after the other with the closest hit
+ * carried over. They differ in how far a box must be widened for a ray starting at o: the exact sphere test's
+ * discriminant is off by ~15 2^-24 |c - o|^2, so it can report a sphere that the ray's line misses by up to
+ * sqrt(2^-18) |o| (what matters for tiny, distant spheres); the exact triangle test only moves the hit point by a few
+ * 2^-24 (|o| + |p|). With one common margin the sphere bound (2^-9 |o|) would swell the boxes of a finely tessellated
+ * mesh by a third of a triangle and make rays that start on it walk hundreds of nodes. */
+struct rt3_bvh_tree {
+    int32_t root;        /* reference of the root (a leaf when the tree has one primitive) */
     uint32_t n_prims;    /* 0: nothing to hit */
     float ray_margin;    /* every box is widened by ray_margin * |o| for a ray starting at o */
+};
+struct rt3_bvh_view {
+    const float4* nodes; /* 4 float4 per internal node: (lo0.xyz, hi0.x) (hi0.yz, lo1.xy) (lo1.z, hi1.xyz) (ref0, ref1, -, -) */
+    rt3_bvh_tree tree[2]; /* faces, spheres */
+    uint32_t n_prims;
 };
 
 /* ---- build ---------------------------------------------------------------- */
@@ -44,11 +54,11 @@ __device__ __forceinline__ unsigned long long bvh_spread21(uint32_t v) {
 }
 
 /* 63-bit Morton code of every primitive's box centre, normalised to the box of all centres. */
-__global__ void bvh_morton_kernel(uint32_t n, const float4* __restrict__ lo, const float4* __restrict__ hi, float3 cmin, float3 cscale,
-                                  unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+__global__ void bvh_morton_kernel(uint32_t n, uint32_t first_prim, const float4* __restrict__ lo, const float4* __restrict__ hi, float3 cmin,
+                                  float3 cscale, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) { return; }
-    const float4 a = lo[i], b = hi[i];
+    const float4 a = lo[first_prim + i], b = hi[first_prim + i];
     float c[3] = { 0.5f * a.x + 0.5f * b.x, 0.5f * a.y + 0.5f * b.y, 0.5f * a.z + 0.5f * b.z };
     const float mn[3] = { cmin.x, cmin.y, cmin.z }, sc[3] = { cscale.x, cscale.y, cscale.z };
     uint32_t q[3];
@@ -60,7 +70,7 @@ __global__ void bvh_morton_kernel(uint32_t n, const float4* __restrict__ lo, con
         q[k] = (uint32_t) x;
     }
     keys[i] = bvh_spread21(q[0]) | (bvh_spread21(q[1]) << 1) | (bvh_spread21(q[2]) << 2);
-    vals[i] = i;
+    vals[i] = first_prim + i;
 }
 
 /* Length of the common prefix of sorted keys i and j (index bits break ties); -1 outside the array. */
@@ -107,7 +117,7 @@ __global__ void bvh_tree_kernel(int n, const unsigned long long* __restrict__ ke
  * children's boxes, writes the node record and climbs on. */
 __global__ void bvh_refit_kernel(int n, const uint32_t* __restrict__ vals, const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi,
                                  const int* __restrict__ child, const int* __restrict__ node_parent, const int* __restrict__ leaf_parent,
-                                 float4* box_lo, float4* box_hi, unsigned int* __restrict__ arrived, float4* __restrict__ nodes) {
+                                 float4* box_lo, float4* box_hi, unsigned int* __restrict__ arrived, float4* __restrict__ nodes, int node_offset) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) { return; }
     int p = leaf_parent[k];
@@ -126,15 +136,16 @@ __global__ void bvh_refit_kernel(int n, const uint32_t* __restrict__ vals, const
                 ref[c] = ~(int) prim;
             } else {
                 lo[c] = __ldcg(&box_lo[ch]); hi[c] = __ldcg(&box_hi[ch]);
-                ref[c] = ch;
+                ref[c] = ch + node_offset; /* node records of all trees share one array */
             }
         }
         box_lo[p] = make_float4(fminf(lo[0].x, lo[1].x), fminf(lo[0].y, lo[1].y), fminf(lo[0].z, lo[1].z), 0.f);
         box_hi[p] = make_float4(fmaxf(hi[0].x, hi[1].x), fmaxf(hi[0].y, hi[1].y), fmaxf(hi[0].z, hi[1].z), 0.f);
-        nodes[4 * p + 0] = make_float4(lo[0].x, lo[0].y, lo[0].z, hi[0].x);
-        nodes[4 * p + 1] = make_float4(hi[0].y, hi[0].z, lo[1].x, lo[1].y);
-        nodes[4 * p + 2] = make_float4(lo[1].z, hi[1].x, hi[1].y, hi[1].z);
-        nodes[4 * p + 3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), 0.f, 0.f);
+        float4* out = nodes + 4 * (size_t) (p + node_offset);
+        out[0] = make_float4(lo[0].x, lo[0].y, lo[0].z, hi[0].x);
+        out[1] = make_float4(hi[0].y, hi[0].z, lo[1].x, lo[1].y);
+        out[2] = make_float4(lo[1].z, hi[1].x, hi[1].y, hi[1].z);
+        out[3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), 0.f, 0.f);
         p = node_parent[p];
     }
 }
@@ -170,51 +181,56 @@ __device__ __forceinline__ void bvh_closest_hit(const rt3_scene_view& S, const r
                                                 uint32_t& visits, uint32_t& tests) {
     best.t = __int_as_float(0x7f800000);
     best.prim = RT3_NO_HIT;
-    if (B.n_prims == 0u) { return; }
-    rt3_bvh_ray r;
-    const float grow = B.ray_margin * sqrtf(dot3(o, o));
-    r.o_lo = v3(o.x + grow, o.y + grow, o.z + grow);
-    r.o_hi = v3(o.x - grow, o.y - grow, o.z - grow);
-    r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     int32_t stack_ref[RT3_BVH_STACK];
     float stack_tin[RT3_BVH_STACK];
-    int sp = 0;
-    int32_t ref = B.root;
-    for (;;) {
-        if (ref < 0) {
-            const uint32_t prim = (uint32_t) ~ref;
-            tests++;
-            if (prim < S.n_faces) {
-                exact_face<false>(S, prim, o, d, PATH_MODE ? RT3_TMIN : 0.0f, best);
+    const float o_len = sqrtf(dot3(o, o));
+    rt3_bvh_ray r;
+    r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
+        const rt3_bvh_tree T = B.tree[which];
+        if (T.n_prims == 0u) { continue; }
+        const float grow = T.ray_margin * o_len;
+        r.o_lo = v3(o.x + grow, o.y + grow, o.z + grow);
+        r.o_hi = v3(o.x - grow, o.y - grow, o.z - grow);
+        int sp = 0;
+        int32_t ref = T.root;
+        for (;;) {
+            if (ref < 0) {
+                const uint32_t prim = (uint32_t) ~ref;
+                tests++;
+                if (prim < S.n_faces) {
+                    exact_face<false>(S, prim, o, d, PATH_MODE ? RT3_TMIN : 0.0f, best);
+                } else {
+                    const float4 sp4 = __ldg(&S.spheres[prim - S.n_faces]);
+                    if (PATH_MODE) { exact_sphere_path<false>(prim, sp4, o, d, best); }
+                    else { exact_sphere_v4<false>(prim, sp4, o, d, best); }
+                }
             } else {
-                const float4 sp4 = __ldg(&S.spheres[prim - S.n_faces]);
-                if (PATH_MODE) { exact_sphere_path<false>(prim, sp4, o, d, best); }
-                else { exact_sphere_v4<false>(prim, sp4, o, d, best); }
+                visits++;
+                const float4 n0 = __ldg(&B.nodes[4 * ref + 0]), n1 = __ldg(&B.nodes[4 * ref + 1]), n2 = __ldg(&B.nodes[4 * ref + 2]),
+                             n3 = __ldg(&B.nodes[4 * ref + 3]);
+                const float limit = best.t * RT3_BVH_ROBUST;
+                float t0, t1;
+                const bool h0 = bvh_slab(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, limit, t0);
+                const bool h1 = bvh_slab(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, limit, t1);
+                const int32_t c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+                if (h0 && h1) {
+                    const bool first0 = t0 <= t1;
+                    if (sp < RT3_BVH_STACK) { stack_ref[sp] = first0 ? c1 : c0; stack_tin[sp] = first0 ? t1 : t0; sp++; }
+                    ref = first0 ? c0 : c1;
+                    continue;
+                }
+                if (h0) { ref = c0; continue; }
+                if (h1) { ref = c1; continue; }
             }
-        } else {
-            visits++;
-            const float4 n0 = __ldg(&B.nodes[4 * ref + 0]), n1 = __ldg(&B.nodes[4 * ref + 1]), n2 = __ldg(&B.nodes[4 * ref + 2]),
-                         n3 = __ldg(&B.nodes[4 * ref + 3]);
-            const float limit = best.t * RT3_BVH_ROBUST;
-            float t0, t1;
-            const bool h0 = bvh_slab(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, limit, t0);
-            const bool h1 = bvh_slab(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, limit, t1);
-            const int32_t c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-            if (h0 && h1) {
-                const bool first0 = t0 <= t1;
-                if (sp < RT3_BVH_STACK) { stack_ref[sp] = first0 ? c1 : c0; stack_tin[sp] = first0 ? t1 : t0; sp++; }
-                ref = first0 ? c0 : c1;
-                continue;
+            /* next subtree still worth entering */
+            bool found = false;
+            while (sp > 0) {
+                sp--;
+                if (stack_tin[sp] <= best.t * RT3_BVH_ROBUST) { ref = stack_ref[sp]; found = true; break; }
             }
-            if (h0) { ref = c0; continue; }
-            if (h1) { ref = c1; continue; }
+            if (!found) { break; }
         }
-        /* next subtree still worth entering */
-        bool found = false;
-        while (sp > 0) {
-            sp--;
-            if (stack_tin[sp] <= best.t * RT3_BVH_ROBUST) { ref = stack_ref[sp]; found = true; break; }
-        }
-        if (!found) { break; }
     }
 }

@@ -308,30 +308,42 @@ int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
 
 /* Builds the hierarchy over the uploaded primitive boxes (first RT3_FLAG_BVH render after an upload):
  * Morton codes of the box centres, radix sort (CUB), Karras' radix tree, bottom-up refit. All on the
- * device; the scratch arrays are released when the node array is complete. */
+ * device; the scratch arrays are released when the node array is complete.
+ * Faces and spheres get a tree each (one node array, the sphere tree's nodes behind the face tree's):
+ * the sphere discriminant needs boxes widened by sqrt(2^-18)|o| per ray, and that much around the
+ * small triangles of a tessellated mesh makes every ray that starts on the mesh walk its whole
+ * neighbourhood. The face tree's per-ray widening only covers the rounding of the slab test itself. */
 int build_bvh(rt3_ctx* ctx, cudaStream_t stream) {
     if (ctx->bvh_ready) { return RT3_OK; }
-    const uint32_t n = ctx->view.n_prims;
-    ctx->bvh.n_prims = n;
+    const uint32_t count[2] = { ctx->view.n_faces, ctx->view.n_spheres }, first[2] = { 0u, ctx->view.n_faces };
+    /* per-ray widening (times |o|): a few 2^-24 for the triangle test's hit point, sqrt(2^-18) for the sphere discriminant */
+    const float margin[2] = { 9.5367431640625e-07f, sqrtf(RT3_FILTER_SLACK) * 1.000001f };
+    ctx->bvh.n_prims = ctx->view.n_prims;
     ctx->bvh.nodes = nullptr;
-    ctx->bvh.root = n == 1 ? ~0 : 0;
-    ctx->bvh.ray_margin = sqrtf(RT3_FILTER_SLACK) * 1.000001f;
     ctx->bvh_build_ms = 0.0;
-    if (n < 2) { ctx->bvh_ready = true; return RT3_OK; }
+    uint32_t node_offset[2] = { 0u, count[0] > 1 ? count[0] - 1 : 0u };
+    const size_t n_nodes = (size_t) node_offset[1] + (count[1] > 1 ? count[1] - 1 : 0u);
+    for (int w = 0; w < 2; w++) {
+        ctx->bvh.tree[w].n_prims = count[w];
+        ctx->bvh.tree[w].root = count[w] == 1 ? ~(int32_t) first[w] : (int32_t) node_offset[w];
+        ctx->bvh.tree[w].ray_margin = margin[w];
+    }
+    const uint32_t nmax = count[0] > count[1] ? count[0] : count[1];
+    if (nmax < 2) { ctx->bvh_ready = true; return RT3_OK; }
     DeviceBuffer<unsigned long long> keys_in, keys_out;
     DeviceBuffer<uint32_t> vals_in, vals_out, arrived;
     DeviceBuffer<int> child, node_parent, leaf_parent;
     DeviceBuffer<float4> box_lo, box_hi;
     DeviceBuffer<unsigned char> temp;
     int rc;
-    if ((rc = keys_in.reserve(n)) != RT3_OK || (rc = keys_out.reserve(n)) != RT3_OK || (rc = vals_in.reserve(n)) != RT3_OK ||
-        (rc = vals_out.reserve(n)) != RT3_OK || (rc = arrived.reserve(n)) != RT3_OK || (rc = child.reserve(2 * (size_t) n)) != RT3_OK ||
-        (rc = node_parent.reserve(n)) != RT3_OK || (rc = leaf_parent.reserve(n)) != RT3_OK || (rc = box_lo.reserve(n)) != RT3_OK ||
-        (rc = box_hi.reserve(n)) != RT3_OK || (rc = ctx->bvh_nodes.reserve(4 * (size_t) (n - 1))) != RT3_OK) {
+    if ((rc = keys_in.reserve(nmax)) != RT3_OK || (rc = keys_out.reserve(nmax)) != RT3_OK || (rc = vals_in.reserve(nmax)) != RT3_OK ||
+        (rc = vals_out.reserve(nmax)) != RT3_OK || (rc = arrived.reserve(nmax)) != RT3_OK || (rc = child.reserve(2 * (size_t) nmax)) != RT3_OK ||
+        (rc = node_parent.reserve(nmax)) != RT3_OK || (rc = leaf_parent.reserve(nmax)) != RT3_OK || (rc = box_lo.reserve(nmax)) != RT3_OK ||
+        (rc = box_hi.reserve(nmax)) != RT3_OK || (rc = ctx->bvh_nodes.reserve(4 * (n_nodes ? n_nodes : 1))) != RT3_OK) {
         return rc;
     }
     size_t temp_bytes = 0;
-    RT3_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in.ptr, keys_out.ptr, vals_in.ptr, vals_out.ptr, (int) n, 0, 63, stream));
+    RT3_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in.ptr, keys_out.ptr, vals_in.ptr, vals_out.ptr, (int) nmax, 0, 63, stream));
     if ((rc = temp.reserve(temp_bytes ? temp_bytes : 1)) != RT3_OK) { return rc; }
     float3 cmin = make_float3(ctx->centroid_min[0], ctx->centroid_min[1], ctx->centroid_min[2]), cscale;
     {
@@ -343,16 +355,21 @@ int build_bvh(rt3_ctx* ctx, cudaStream_t stream) {
     RT3_CUDA(cudaEventCreate(&e0));
     RT3_CUDA(cudaEventCreate(&e1));
     RT3_CUDA(cudaEventRecord(e0, stream));
-    const unsigned grid = (n + 255u) / 256u;
-    bvh_morton_kernel<<<grid, 256, 0, stream>>>(n, ctx->prim_lo.ptr, ctx->prim_hi.ptr, cmin, cscale, keys_in.ptr, vals_in.ptr);
-    RT3_CUDA(cudaGetLastError());
-    RT3_CUDA(cub::DeviceRadixSort::SortPairs(temp.ptr, temp_bytes, keys_in.ptr, keys_out.ptr, vals_in.ptr, vals_out.ptr, (int) n, 0, 63, stream));
-    RT3_CUDA(cudaMemsetAsync(arrived.ptr, 0, (size_t) n * sizeof(uint32_t), stream));
-    bvh_tree_kernel<<<grid, 256, 0, stream>>>((int) n, keys_out.ptr, child.ptr, node_parent.ptr, leaf_parent.ptr);
-    RT3_CUDA(cudaGetLastError());
-    bvh_refit_kernel<<<grid, 256, 0, stream>>>((int) n, vals_out.ptr, ctx->prim_lo.ptr, ctx->prim_hi.ptr, child.ptr, node_parent.ptr, leaf_parent.ptr,
-                                              box_lo.ptr, box_hi.ptr, arrived.ptr, ctx->bvh_nodes.ptr);
-    RT3_CUDA(cudaGetLastError());
+    for (int w = 0; w < 2; w++) {
+        const uint32_t n = count[w];
+        if (n < 2) { continue; }
+        const unsigned grid = (n + 255u) / 256u;
+        bvh_morton_kernel<<<grid, 256, 0, stream>>>(n, first[w], ctx->prim_lo.ptr, ctx->prim_hi.ptr, cmin, cscale, keys_in.ptr, vals_in.ptr);
+        RT3_CUDA(cudaGetLastError());
+        size_t tb = temp_bytes;
+        RT3_CUDA(cub::DeviceRadixSort::SortPairs(temp.ptr, tb, keys_in.ptr, keys_out.ptr, vals_in.ptr, vals_out.ptr, (int) n, 0, 63, stream));
+        RT3_CUDA(cudaMemsetAsync(arrived.ptr, 0, (size_t) n * sizeof(uint32_t), stream));
+        bvh_tree_kernel<<<grid, 256, 0, stream>>>((int) n, keys_out.ptr, child.ptr, node_parent.ptr, leaf_parent.ptr);
+        RT3_CUDA(cudaGetLastError());
+        bvh_refit_kernel<<<grid, 256, 0, stream>>>((int) n, vals_out.ptr, ctx->prim_lo.ptr, ctx->prim_hi.ptr, child.ptr, node_parent.ptr, leaf_parent.ptr,
+                                                  box_lo.ptr, box_hi.ptr, arrived.ptr, ctx->bvh_nodes.ptr, (int) node_offset[w]);
+        RT3_CUDA(cudaGetLastError());
+    }
     RT3_CUDA(cudaEventRecord(e1, stream));
     RT3_CUDA(cudaStreamSynchronize(stream)); /* the scratch arrays go out of scope */
     float ms = 0.f;
@@ -637,7 +654,9 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
         radius = radius * (1.0 + 1.0 / 1024.0) + (std::sqrt(centre[0] * centre[0] + centre[1] * centre[1] + centre[2] * centre[2]) + radius) / 65536.0;
         bounds[i] = make_bound(centre, radius);
         if (bounds[i].R2 >= 0) {
-            const double m = std::sqrt(bounds[i].R2) - r_geom; /* the same widening around the triangle's own box */
+            /* around the triangle's own box: the geometric widening of its bounding sphere, without the slack term of
+             * the sphere discriminant (rt3_bvh.cuh) */
+            const double m = radius - r_geom;
             box_lo[i] = make_float4(round_down(std::min({ da[0], db[0], dc[0] }) - m), round_down(std::min({ da[1], db[1], dc[1] }) - m),
                                     round_down(std::min({ da[2], db[2], dc[2] }) - m), 0.f);
             box_hi[i] = make_float4(round_up(std::max({ da[0], db[0], dc[0] }) + m), round_up(std::max({ da[1], db[1], dc[1] }) + m),
