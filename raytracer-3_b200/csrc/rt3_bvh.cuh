@@ -157,16 +157,37 @@ __global__ void bvh_refit_kernel(int n, const uint32_t* __restrict__ vals, const
  * admit more. A box is entered iff [t_in, t_out] meets [0, limit]. */
 #define RT3_BVH_ROBUST 1.00000095367431640625f
 
+#ifndef RT3_BVH_FMA_SLAB
+#define RT3_BVH_FMA_SLAB 1
+#endif
+
 struct rt3_bvh_ray {
     rt3_vec3 o_lo, o_hi, inv; /* o + grow, o - grow: the per-ray widening of every box, moved onto the origin */
 };
 
+/* 1 / d per axis for the slab test. An axis whose |d| is below 2^-60 (or whose o / d leaves the float
+ * range) gets NaN: both of its slab distances are then NaN, fminf / fmaxf drop them and the axis is
+ * ignored, which can only admit more boxes. */
+__device__ __forceinline__ float bvh_axis_inv(float d, float o_a, float o_b) {
+    const float inv = 1.0f / d;
+    const float big = fmaxf(fabsf(o_a * inv), fabsf(o_b * inv));
+    return (fabsf(d) >= 8.673617379884035e-19f && big < 3.0e38f) ? inv : __int_as_float(0x7fc00000);
+}
+
 __device__ __forceinline__ bool bvh_slab(const rt3_bvh_ray& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float limit,
                                          float& t_in) {
-    /* (lo - grow) - o == lo - (o + grow) up to one rounding of o + grow, which is 2^-24 |o| against grow = 2^-9 |o| */
+#if RT3_BVH_FMA_SLAB
+    /* o_lo / o_hi hold -(o + grow) / d and -(o - grow) / d: one FMA per plane. The rounding of that product is the
+     * distance to a plane moved by at most 2^-24 |o|, a small part of grow (>= 2^-19 |o|); the rest is relative. */
+    const float x0 = __fmaf_rn(lox, r.inv.x, r.o_lo.x), x1 = __fmaf_rn(hix, r.inv.x, r.o_hi.x);
+    const float y0 = __fmaf_rn(loy, r.inv.y, r.o_lo.y), y1 = __fmaf_rn(hiy, r.inv.y, r.o_hi.y);
+    const float z0 = __fmaf_rn(loz, r.inv.z, r.o_lo.z), z1 = __fmaf_rn(hiz, r.inv.z, r.o_hi.z);
+#else
+    /* (lo - grow) - o == lo - (o + grow) up to one rounding of o + grow, which is 2^-24 |o| against grow >= 2^-19 |o| */
     const float x0 = (lox - r.o_lo.x) * r.inv.x, x1 = (hix - r.o_hi.x) * r.inv.x;
     const float y0 = (loy - r.o_lo.y) * r.inv.y, y1 = (hiy - r.o_hi.y) * r.inv.y;
     const float z0 = (loz - r.o_lo.z) * r.inv.z, z1 = (hiz - r.o_hi.z) * r.inv.z;
+#endif
     /* fminf / fmaxf return the other operand for a NaN (0 * inf: origin on a slab plane of an axis the ray is parallel to) */
     const float tin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
     const float tout = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
@@ -185,14 +206,26 @@ __device__ __forceinline__ void bvh_closest_hit(const rt3_scene_view& S, const r
     float stack_tin[RT3_BVH_STACK];
     const float o_len = sqrtf(dot3(o, o));
     rt3_bvh_ray r;
+#if RT3_BVH_FMA_SLAB
+    {
+        const float g = B.tree[1].ray_margin * o_len; /* the larger of the two widenings */
+        r.inv = v3(bvh_axis_inv(d.x, o.x + g, o.x - g), bvh_axis_inv(d.y, o.y + g, o.y - g), bvh_axis_inv(d.z, o.z + g, o.z - g));
+    }
+#else
     r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+#endif
 #pragma unroll 1
     for (int which = 0; which < 2; which++) {
         const rt3_bvh_tree T = B.tree[which];
         if (T.n_prims == 0u) { continue; }
         const float grow = T.ray_margin * o_len;
+#if RT3_BVH_FMA_SLAB
+        r.o_lo = v3(-(o.x + grow) * r.inv.x, -(o.y + grow) * r.inv.y, -(o.z + grow) * r.inv.z);
+        r.o_hi = v3(-(o.x - grow) * r.inv.x, -(o.y - grow) * r.inv.y, -(o.z - grow) * r.inv.z);
+#else
         r.o_lo = v3(o.x + grow, o.y + grow, o.z + grow);
         r.o_hi = v3(o.x - grow, o.y - grow, o.z - grow);
+#endif
         int sp = 0;
         int32_t ref = T.root;
         for (;;) {

@@ -291,6 +291,16 @@ int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
     int per_sm = 0;
     int rc = configure(pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL>, smem, &per_sm);
     if (rc != RT3_OK) { return rc; }
+    if (ACCEL) {
+        /* The traversal reads its node records through L1: ask for the smallest shared-memory carve-out that still
+         * holds the resident CTAs (1 KB of system use each) -- the default rounds up one configuration further. */
+        int sm_bytes = 0;
+        RT3_CUDA(cudaDeviceGetAttribute(&sm_bytes, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
+        const size_t need = (size_t) per_sm * (smem + 1024);
+        int percent = sm_bytes > 0 ? (int) ((need * 100 + (size_t) sm_bytes - 1) / (size_t) sm_bytes) : 100;
+        if (percent > 100) { percent = 100; }
+        RT3_CUDA(cudaFuncSetAttribute(pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL>, cudaFuncAttributePreferredSharedMemoryCarveout, percent));
+    }
     if (per_sm < 1) { return fail(RT3_ERR_CUDA, "pathtrace kernel does not fit on an SM (smem %zu)", smem); }
     if (const char* cap = getenv("RT3_MAX_CTAS_PER_SM")) { /* tuning knob: fewer persistent CTAs per SM than fit */
         const int c = atoi(cap);
@@ -316,8 +326,9 @@ int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
 int build_bvh(rt3_ctx* ctx, cudaStream_t stream) {
     if (ctx->bvh_ready) { return RT3_OK; }
     const uint32_t count[2] = { ctx->view.n_faces, ctx->view.n_spheres }, first[2] = { 0u, ctx->view.n_faces };
-    /* per-ray widening (times |o|): a few 2^-24 for the triangle test's hit point, sqrt(2^-18) for the sphere discriminant */
-    const float margin[2] = { 9.5367431640625e-07f, sqrtf(RT3_FILTER_SLACK) * 1.000001f };
+    /* per-ray widening (times |o|): a few 2^-24 for the triangle test's hit point and the slab test's own o / d
+     * product (2^-19 in all), sqrt(2^-18) for the sphere discriminant */
+    const float margin[2] = { 1.9073486328125e-06f, sqrtf(RT3_FILTER_SLACK) * 1.0001f };
     ctx->bvh.n_prims = ctx->view.n_prims;
     ctx->bvh.nodes = nullptr;
     ctx->bvh_build_ms = 0.0;
@@ -412,7 +423,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
         int brc = build_bvh(ctx, stream);
         if (brc != RT3_OK) { return brc; }
         resident = false; /* no constant-bank records needed */
-        smem = rt3_smem_bytes(true, params->mode == RT3_MODE_PATHTRACE);
+        smem = rt3_accel_smem_bytes(params->mode == RT3_MODE_PATHTRACE);
     }
     ctx->stats.accel = accel ? 1u : 0u;
     kp.resident = resident ? 1u : 0u;

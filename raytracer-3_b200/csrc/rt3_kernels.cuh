@@ -64,10 +64,17 @@ __host__ __device__ inline size_t rt3_smem_bytes(bool resident, bool path_slots)
            (path_slots ? (size_t) RT3_SLOT_BYTES : 0);
 }
 
-template <bool RESIDENT>
+/* Hierarchy kernels keep no survivor masks: their shared memory is the path slots alone, which
+ * leaves the rest of the SM's 256 KB to the L1 the node records are read through. */
+__host__ __device__ inline size_t rt3_accel_smem_bytes(bool path_slots) { return path_slots ? (size_t) RT3_SLOT_BYTES : 0; }
+
+template <bool RESIDENT, bool ACCEL = false>
 __device__ __forceinline__ rt3_smem_view smem_view(unsigned char* base) {
     rt3_smem_view v;
-    if (RESIDENT) {
+    if (ACCEL) {
+        v.bars = nullptr; v.tile_xy = nullptr; v.tile_w = nullptr; v.masks = nullptr;
+        v.slots = reinterpret_cast<uint32_t*>(base);
+    } else if (RESIDENT) {
         v.bars = nullptr; v.tile_xy = nullptr; v.tile_w = nullptr;
         v.masks = reinterpret_cast<uint32_t*>(base);
         v.slots = reinterpret_cast<uint32_t*>(base + RT3_MASK_BYTES);
@@ -246,7 +253,7 @@ reference_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
                  uint32_t* __restrict__ hit_entity, float* __restrict__ hit_t, unsigned long long* __restrict__ counters) {
     constexpr int R = RT3_RAYS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const rt3_smem_view sm = smem_view<RESIDENT>(smem_raw);
+    const rt3_smem_view sm = smem_view<RESIDENT, ACCEL>(smem_raw);
     scene_prologue<RESIDENT>(sm);
     uint32_t phase = 0u;
 
@@ -536,7 +543,7 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
                  unsigned long long* __restrict__ counters) {
     constexpr int R = RT3_RAYS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const rt3_smem_view sm = smem_view<RESIDENT>(smem_raw);
+    const rt3_smem_view sm = smem_view<RESIDENT, ACCEL>(smem_raw);
     scene_prologue<RESIDENT>(sm);
     uint32_t phase = 0u;
 
