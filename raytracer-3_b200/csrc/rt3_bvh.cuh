@@ -160,6 +160,7 @@ __global__ void bvh_refit_kernel(int n, const uint32_t* __restrict__ vals, const
 #ifndef RT3_BVH_FMA_SLAB
 #define RT3_BVH_FMA_SLAB 1
 #endif
+#define RT3_BVH_NONE 0x7fffffff /* neither a node (>= 0) nor a leaf (~primitive < 0) */
 
 struct rt3_bvh_ray {
     rt3_vec3 o_lo, o_hi, inv; /* o + grow, o - grow: the per-ray widening of every box, moved onto the origin */
@@ -202,8 +203,7 @@ __device__ __forceinline__ void bvh_closest_hit(const rt3_scene_view& S, const r
                                                 uint32_t& visits, uint32_t& tests) {
     best.t = __int_as_float(0x7f800000);
     best.prim = RT3_NO_HIT;
-    int32_t stack_ref[RT3_BVH_STACK];
-    float stack_tin[RT3_BVH_STACK];
+    uint2 stack[RT3_BVH_STACK]; /* (subtree reference, its entry distance): one 8-byte local access per push / pop */
     const float o_len = sqrtf(dot3(o, o));
     rt3_bvh_ray r;
 #if RT3_BVH_FMA_SLAB
@@ -228,42 +228,47 @@ __device__ __forceinline__ void bvh_closest_hit(const rt3_scene_view& S, const r
 #endif
         int sp = 0;
         int32_t ref = T.root;
-        for (;;) {
-            if (ref < 0) {
-                const uint32_t prim = (uint32_t) ~ref;
-                tests++;
-                if (prim < S.n_faces) {
-                    exact_face<false>(S, prim, o, d, PATH_MODE ? RT3_TMIN : 0.0f, best);
-                } else {
-                    const float4 sp4 = __ldg(&S.spheres[prim - S.n_faces]);
-                    if (PATH_MODE) { exact_sphere_path<false>(prim, sp4, o, d, best); }
-                    else { exact_sphere_v4<false>(prim, sp4, o, d, best); }
-                }
-            } else {
-                visits++;
-                const float4 n0 = __ldg(&B.nodes[4 * ref + 0]), n1 = __ldg(&B.nodes[4 * ref + 1]), n2 = __ldg(&B.nodes[4 * ref + 2]),
-                             n3 = __ldg(&B.nodes[4 * ref + 3]);
-                const float limit = best.t * RT3_BVH_ROBUST;
-                float t0, t1;
-                const bool h0 = bvh_slab(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, limit, t0);
-                const bool h1 = bvh_slab(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, limit, t1);
-                const int32_t c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-                if (h0 && h1) {
-                    const bool first0 = t0 <= t1;
-                    if (sp < RT3_BVH_STACK) { stack_ref[sp] = first0 ? c1 : c0; stack_tin[sp] = first0 ? t1 : t0; sp++; }
-                    ref = first0 ? c0 : c1;
-                    continue;
-                }
-                if (h0) { ref = c0; continue; }
-                if (h1) { ref = c1; continue; }
-            }
-            /* next subtree still worth entering */
-            bool found = false;
+        /* next stacked subtree still worth entering, or RT3_BVH_NONE */
+        auto pop = [&]() -> int32_t {
             while (sp > 0) {
-                sp--;
-                if (stack_tin[sp] <= best.t * RT3_BVH_ROBUST) { ref = stack_ref[sp]; found = true; break; }
+                const uint2 e = stack[--sp];
+                if (__uint_as_float(e.y) <= best.t * RT3_BVH_ROBUST) { return (int32_t) e.x; }
             }
-            if (!found) { break; }
+            return RT3_BVH_NONE;
+        };
+        /* one node record: both child boxes against the ray; returns the subtree to enter next, stacks the farther one */
+        auto visit = [&](int32_t node) -> int32_t {
+            visits++;
+            const float4 n0 = __ldg(&B.nodes[4 * node + 0]), n1 = __ldg(&B.nodes[4 * node + 1]), n2 = __ldg(&B.nodes[4 * node + 2]),
+                         n3 = __ldg(&B.nodes[4 * node + 3]);
+            const float limit = best.t * RT3_BVH_ROBUST;
+            float t0, t1;
+            const bool h0 = bvh_slab(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, limit, t0);
+            const bool h1 = bvh_slab(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, limit, t1);
+            const int32_t c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            if (h0 && h1) {
+                const bool first0 = t0 <= t1;
+                if (sp < RT3_BVH_STACK) { stack[sp++] = make_uint2((uint32_t) (first0 ? c1 : c0), __float_as_uint(first0 ? t1 : t0)); }
+                return first0 ? c0 : c1;
+            }
+            if (h0) { return c0; }
+            if (h1) { return c1; }
+            return pop();
+        };
+        auto test = [&](int32_t leaf) {
+            const uint32_t prim = (uint32_t) ~leaf;
+            tests++;
+            if (prim < S.n_faces) {
+                exact_face<false>(S, prim, o, d, PATH_MODE ? RT3_TMIN : 0.0f, best);
+            } else {
+                const float4 sp4 = __ldg(&S.spheres[prim - S.n_faces]);
+                if (PATH_MODE) { exact_sphere_path<false>(prim, sp4, o, d, best); }
+                else { exact_sphere_v4<false>(prim, sp4, o, d, best); }
+            }
+        };
+        while (ref != RT3_BVH_NONE) {
+            if (ref < 0) { test(ref); ref = pop(); }
+            else { ref = visit(ref); }
         }
     }
 }
