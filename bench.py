@@ -179,6 +179,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="c2", choices=["c2", "c4"],
                     help="c2 (default, the metric's configuration) or c4: the same scene at 3840x2160, 1024 spp (BASELINE configs[3], the multi-GPU one)")
+    ap.add_argument("--gather", choices=("peer", "nccl"), default="peer",
+                    help="N>1 frame end: 'peer' = every rank's kernels store their rows into rank 0's frame over NVLink (CUDA IPC mapping) "
+                         "and the frame ends with a one-element all-reduce; 'nccl' = pack + NCCL gather + de-interleave")
     ap.add_argument("--bvh", action="store_true", help="time the hierarchy path (RT3_FLAG_BVH) instead of the brute-force sweep: not the headline configuration")
     args = ap.parse_args()
     if args.config == "c4":
@@ -220,7 +223,10 @@ def main():
     lib = ctx.lib
     stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream: kernels, NCCL and the timing events all go here
     torch.cuda.set_stream(stream)
-    frame = torch.zeros(H * W, dtype=torch.int32, device=dev)
+    peer = world > 1 and args.gather == "peer"
+    shared = distributed.SharedFrame(ctx, dist, H * W, rank, world, dev) if peer else None
+    frame = shared.tensor if (peer and rank == 0) else torch.zeros(H * W, dtype=torch.int32, device=dev)
+    frame_ptr = shared.ptr if peer else frame.data_ptr()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     my_rows = lib.rt3_partition_rows(H, TILE_ROWS, rank, world)
     max_rows = max(lib.rt3_partition_rows(H, TILE_ROWS, r, world) for r in range(world))
@@ -230,9 +236,12 @@ def main():
     launches_per_step = 3  # clear_accum + pathtrace + resolve
 
     def device_step():
-        """Render this rank's rows; N>1: gather the packed framebuffer onto rank 0 (NCCL) and de-interleave."""
-        ctx.render_device(cam, params, frame.data_ptr(), stream.cuda_stream)
-        if world > 1:
+        """Render this rank's rows. N>1, peer: the rows land in rank 0's frame as they are resolved, the frame ends with a
+        stream-ordered one-element all-reduce. N>1, nccl: pack, gather onto rank 0 (NCCL), de-interleave."""
+        ctx.render_device(cam, params, frame_ptr, stream.cuda_stream)
+        if peer:
+            shared.finish()
+        elif world > 1:
             ctx.pack_partition(frame.data_ptr(), slab.data_ptr(), W, H, TILE_ROWS, rank, world, stream.cuda_stream)
             gathered = distributed.gather_slabs(dist, slab, rank, world)  # NCCL, frame end only
             if rank == 0:
@@ -288,6 +297,8 @@ def main():
             device_step()
             if rank == 0:
                 host_frame_t.copy_(frame, non_blocking=True)
+            if peer:
+                shared.finish()  # the other ranks' next frame may only overwrite the shared frame once rank 0 has read this one
             torch.cuda.synchronize()
     sync_all()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
@@ -323,11 +334,13 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(),
             "rays_per_step": rays_per_step, "spheres": scene.n_spheres,
-            "clocks": clocks, "gpu_launches": launches_per_step * args.steps + (0 if world == 1 else (1 + (world - 1)) * args.steps),
+            "clocks": clocks, "gpu_launches": launches_per_step * args.steps + (0 if (world == 1 or peer) else (1 + (world - 1)) * args.steps),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": ctypes.sizeof(abi.Camera) + ctypes.sizeof(abi.Params),
                     "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "last_step_device_ms": st_e2e.device_ms, "last_step_d2h_ms": st_e2e.d2h_ms,
-                    "path": "rt3_render (C ABI), pinned host frame" if world == 1 else "rt3_render_device + NCCL gather + D2H on rank 0"},
+                    "path": "rt3_render (C ABI), pinned host frame" if world == 1 else
+                            ("rt3_render_device into rank 0's frame over NVLink (rt3_frame_import) + all-reduce barrier + D2H on rank 0" if peer
+                             else "rt3_render_device + NCCL gather + D2H on rank 0")},
             "roofline": {"bound": "fp32-issue", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and spp == SPP and args.config == "c2" and not args.bvh) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one pathtrace_kernel launch of this workload, ncu --set full "
@@ -342,6 +355,9 @@ def main():
         }
         if hierarchy:
             line["hierarchy"] = hierarchy
+        if world > 1:
+            line["config"]["frame_end"] = ("each rank's kernels store its rows into rank 0's frame over NVLink (CUDA IPC mapping), one-element all-reduce as barrier"
+                                           if peer else "pack + NCCL gather onto rank 0 + de-interleave")
         if args.bvh:
             line["config"]["workload"] += " [--bvh: hierarchy traversal instead of the brute-force sweep; roofline figures do not apply]"
             line["accel"] = {"node_visits": st.accel_node_visits, "prim_tests": st.accel_prim_tests, "build_ms": st.accel_build_ms}
@@ -355,6 +371,10 @@ def main():
             line["reference_native"] = reference_native_rate()
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if shared:
+        torch.cuda.synchronize()
+        frame = None
+        shared.close()
     if world > 1:
         dist.destroy_process_group()
 

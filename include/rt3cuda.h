@@ -230,6 +230,21 @@ int rt3_pack_partition(rt3_ctx* ctx, const uint32_t* device_frame, uint32_t* dev
 int rt3_unpack_partition(rt3_ctx* ctx, const uint32_t* device_slab, uint32_t* device_frame, uint32_t width, uint32_t height,
                          uint32_t tile_rows, uint32_t part_index, uint32_t part_count, void* cuda_stream);
 
+/* Shared frame for the multi-GPU split (the reference's hook is the unused BlockInfo
+ * uniform, src/lib/shaders/raytracer/raytracer_v4.glsl:70-79). One process allocates the full frame on its
+ * GPU (rt3_frame_alloc) and exports it (rt3_frame_export, a CUDA IPC handle of RT3_IPC_HANDLE_BYTES bytes
+ * that travels over any channel); every other process maps it (rt3_frame_import, peer access over NVLink is
+ * enabled on first use) and passes the mapped pointer to rt3_render_device as `device_frame`. Frames use
+ * full-frame indexing, so each partition's kernels store its rows where they belong in the owner's memory:
+ * the frame-end gather is the render kernels' own stores, and all that is left is a barrier. A process that
+ * imported a frame releases it (rt3_frame_release) before the owner frees it (rt3_frame_free). */
+#define RT3_IPC_HANDLE_BYTES 64
+int rt3_frame_alloc(rt3_ctx* ctx, uint64_t n_pixels, uint32_t** device_frame);
+int rt3_frame_free(rt3_ctx* ctx, uint32_t* device_frame);
+int rt3_frame_export(rt3_ctx* ctx, const uint32_t* device_frame, unsigned char* handle_out);
+int rt3_frame_import(rt3_ctx* ctx, const unsigned char* handle, uint32_t** peer_frame);
+int rt3_frame_release(rt3_ctx* ctx, uint32_t* peer_frame);
+
 /* Scene construction on the device (the step before the path): tessellates `n` UV spheres with the arithmetic of
  * the reference's CPU pre-render (src/lib/entities/Sphere.cpp:69-79,120-351; GPU twins
  * shaders/pre_render_sphere_v2_{vertices,faces}.glsl) and returns them flattened like

@@ -18,6 +18,7 @@ MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 MODE_REFERENCE, MODE_PATHTRACE = 0, 1
 FLAG_NO_JITTER, FLAG_NO_GAMMA, FLAG_BVH, FLAG_ACCUMULATE = 0x1, 0x2, 0x4, 0x8
 NO_HIT = 0xFFFFFFFF
+IPC_HANDLE_BYTES = 64  # RT3_IPC_HANDLE_BYTES
 
 # numpy record layouts that mirror rt3_face (GFace, reference Vertex.hpp:39-51),
 # rt3_vertex (glm::vec4) and rt3_material byte for byte.
@@ -194,6 +195,11 @@ def load_core():
     lib.rt3_pack_partition.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, vp]
     lib.rt3_unpack_partition.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, vp]
     lib.rt3_frame_bytes.argtypes = [vp, vp, vp, u32, u32, u32, vp]
+    lib.rt3_frame_alloc.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
+    lib.rt3_frame_free.argtypes = [vp, vp]
+    lib.rt3_frame_export.argtypes = [vp, vp, C.c_char_p]
+    lib.rt3_frame_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    lib.rt3_frame_release.argtypes = [vp, vp]
     lib.rt3_uv_sphere_faces.argtypes = [u32, u32]
     lib.rt3_uv_sphere_faces.restype = u32
     lib.rt3_uv_sphere_vertices.argtypes = [u32, u32]
@@ -208,6 +214,7 @@ def load_core():
 EXPORTED_SYMBOLS = [
     "rt3_last_error", "rt3_create", "rt3_destroy", "rt3_scene_upload", "rt3_render", "rt3_render_aov",
     "rt3_render_device", "rt3_partition_rows", "rt3_pack_partition", "rt3_unpack_partition", "rt3_frame_bytes",
+    "rt3_frame_alloc", "rt3_frame_free", "rt3_frame_export", "rt3_frame_import", "rt3_frame_release",
     "rt3_uv_sphere_faces", "rt3_uv_sphere_vertices", "rt3_tessellate_spheres",
     "rt3_get_stats", "rt3_measure_fma_peak",
 ]
@@ -286,6 +293,32 @@ class Context:
         """rt3_frame_bytes: packed device frame -> interleaved RGB (3) / RGBA (4) bytes on the device."""
         self._check(self.lib.rt3_frame_bytes(self.handle, C.c_void_p(frame_ptr), C.c_void_p(out_ptr), width, height, channels,
                                              C.c_void_p(stream_ptr or 0)))
+
+    def frame_alloc(self, n_pixels):
+        """rt3_frame_alloc: a zeroed frame of n_pixels packed pixels on this context's GPU (exportable); returns the device pointer."""
+        p = C.c_void_p()
+        self._check(self.lib.rt3_frame_alloc(self.handle, n_pixels, C.byref(p)))
+        return p.value
+
+    def frame_free(self, ptr):
+        self._check(self.lib.rt3_frame_free(self.handle, C.c_void_p(ptr)))
+
+    def frame_export(self, ptr):
+        """rt3_frame_export: the IPC handle (bytes) another process maps with frame_import."""
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._check(self.lib.rt3_frame_export(self.handle, C.c_void_p(ptr), buf))
+        return buf.raw
+
+    def frame_import(self, handle):
+        """rt3_frame_import: maps another process's frame; the returned pointer is a valid `device_frame` for render_device."""
+        if len(handle) != IPC_HANDLE_BYTES:
+            raise ValueError(f"an IPC handle is {IPC_HANDLE_BYTES} bytes, got {len(handle)}")
+        p = C.c_void_p()
+        self._check(self.lib.rt3_frame_import(self.handle, handle, C.byref(p)))
+        return p.value
+
+    def frame_release(self, ptr):
+        self._check(self.lib.rt3_frame_release(self.handle, C.c_void_p(ptr)))
 
     def stats(self):
         st = Stats()

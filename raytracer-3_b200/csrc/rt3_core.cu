@@ -44,12 +44,21 @@ int fail(int code, const char* fmt, ...) {
 #define RT3_CUDA(call)                                                                                           \
     do {                                                                                                         \
         cudaError_t e__ = (call);                                                                                \
-        if (e__ != cudaSuccess) { return fail(RT3_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); } \
+        if (e__ != cudaSuccess) {                                                                                \
+            (void) cudaGetLastError(); /* reported here: must not resurface at a later launch check */         \
+            return fail(RT3_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));                        \
+        }                                                                                                        \
     } while (0)
 
+/* Device allocation owned by its holder: context members live as long as the context, scratch
+ * buffers of one call are freed on every way out of it. */
 template <class T> struct DeviceBuffer {
     T* ptr = nullptr;
     size_t count = 0;
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer&) = delete;
+    DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+    ~DeviceBuffer() { release(); }
     int reserve(size_t n) {
         if (n <= count) { return RT3_OK; }
         if (ptr) { cudaFree(ptr); ptr = nullptr; count = 0; }
@@ -58,6 +67,20 @@ template <class T> struct DeviceBuffer {
         return RT3_OK;
     }
     void release() { if (ptr) { cudaFree(ptr); } ptr = nullptr; count = 0; }
+};
+
+/* A pair of timing events that does not outlive the call that made it. */
+struct EventPair {
+    cudaEvent_t begin = nullptr, end = nullptr;
+    EventPair() = default;
+    EventPair(const EventPair&) = delete;
+    EventPair& operator=(const EventPair&) = delete;
+    ~EventPair() { if (begin) { cudaEventDestroy(begin); } if (end) { cudaEventDestroy(end); } }
+    int create() {
+        RT3_CUDA(cudaEventCreate(&begin));
+        RT3_CUDA(cudaEventCreate(&end));
+        return RT3_OK;
+    }
 };
 
 }  // namespace
@@ -222,7 +245,8 @@ void scene_basis(const std::vector<Bound>& b, float e[3][3]) {
 
 /* Which scene owns the constant-bank records of each device (rt3_device.cuh c_pair_xy / c_pair_w). */
 std::mutex g_const_mutex;
-uint64_t g_const_owner[64] = { 0 };
+constexpr int RT3_MAX_DEVICES = 64;
+uint64_t g_const_owner[RT3_MAX_DEVICES] = { 0 };
 std::atomic<uint64_t> g_next_scene_id{ 1 };
 
 /* Smallest sphere through/around a triangle (double precision). */
@@ -362,10 +386,9 @@ int build_bvh(rt3_ctx* ctx, cudaStream_t stream) {
                               ctx->centroid_max[2] - ctx->centroid_min[2] };
         cscale = make_float3(ex[0] > 0 ? 1.0f / ex[0] : 0.0f, ex[1] > 0 ? 1.0f / ex[1] : 0.0f, ex[2] > 0 ? 1.0f / ex[2] : 0.0f);
     }
-    cudaEvent_t e0, e1;
-    RT3_CUDA(cudaEventCreate(&e0));
-    RT3_CUDA(cudaEventCreate(&e1));
-    RT3_CUDA(cudaEventRecord(e0, stream));
+    EventPair ev;
+    if ((rc = ev.create()) != RT3_OK) { return rc; }
+    RT3_CUDA(cudaEventRecord(ev.begin, stream));
     for (int w = 0; w < 2; w++) {
         const uint32_t n = count[w];
         if (n < 2) { continue; }
@@ -381,13 +404,10 @@ int build_bvh(rt3_ctx* ctx, cudaStream_t stream) {
                                                   box_lo.ptr, box_hi.ptr, arrived.ptr, ctx->bvh_nodes.ptr, (int) node_offset[w]);
         RT3_CUDA(cudaGetLastError());
     }
-    RT3_CUDA(cudaEventRecord(e1, stream));
+    RT3_CUDA(cudaEventRecord(ev.end, stream));
     RT3_CUDA(cudaStreamSynchronize(stream)); /* the scratch arrays go out of scope */
     float ms = 0.f;
-    RT3_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    keys_in.release(); keys_out.release(); vals_in.release(); vals_out.release(); arrived.release(); child.release();
-    node_parent.release(); leaf_parent.release(); box_lo.release(); box_hi.release(); temp.release();
+    RT3_CUDA(cudaEventElapsedTime(&ms, ev.begin, ev.end));
     ctx->bvh_build_ms = ms;
     ctx->bvh.nodes = ctx->bvh_nodes.ptr;
     ctx->bvh_ready = true;
@@ -584,7 +604,7 @@ int rt3_create(rt3_ctx** out, int device) {
         return fail(RT3_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     }
-    if (device < 0 || device >= n_dev) { return fail(RT3_ERR_INVALID, "device %d out of range (0..%d)", device, n_dev - 1); }
+    if (device < 0 || device >= n_dev || device >= RT3_MAX_DEVICES) { return fail(RT3_ERR_INVALID, "device %d out of range (0..%d)", device, std::min(n_dev, RT3_MAX_DEVICES) - 1); }
     RT3_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     RT3_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -848,6 +868,58 @@ int rt3_unpack_partition(rt3_ctx* ctx, const uint32_t* device_slab, uint32_t* de
     return RT3_OK;
 }
 
+int rt3_frame_alloc(rt3_ctx* ctx, uint64_t n_pixels, uint32_t** device_frame) {
+    if (!ctx || !device_frame) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    *device_frame = nullptr;
+    if (n_pixels == 0 || n_pixels > 0xFFFFFFFFull) { return fail(RT3_ERR_INVALID, "n_pixels must be in 1 .. 2^32-1"); }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    /* a plain cudaMalloc: the IPC handle names the whole allocation, so the frame must be one */
+    RT3_CUDA(cudaMalloc(&p, (size_t) n_pixels * sizeof(uint32_t)));
+    cudaError_t e = cudaMemset(p, 0, (size_t) n_pixels * sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaFree(p); return fail(RT3_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e)); }
+    *device_frame = (uint32_t*) p;
+    return RT3_OK;
+}
+
+int rt3_frame_free(rt3_ctx* ctx, uint32_t* device_frame) {
+    if (!ctx) { return fail(RT3_ERR_INVALID, "ctx is NULL"); }
+    if (!device_frame) { return RT3_OK; }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    RT3_CUDA(cudaFree(device_frame));
+    return RT3_OK;
+}
+
+int rt3_frame_export(rt3_ctx* ctx, const uint32_t* device_frame, unsigned char* handle_out) {
+    if (!ctx || !device_frame || !handle_out) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == RT3_IPC_HANDLE_BYTES, "RT3_IPC_HANDLE_BYTES must be the size of a CUDA IPC handle");
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    RT3_CUDA(cudaIpcGetMemHandle(&h, const_cast<uint32_t*>(device_frame)));
+    memcpy(handle_out, &h, sizeof h);
+    return RT3_OK;
+}
+
+int rt3_frame_import(rt3_ctx* ctx, const unsigned char* handle, uint32_t** peer_frame) {
+    if (!ctx || !handle || !peer_frame) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    *peer_frame = nullptr;
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    RT3_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *peer_frame = (uint32_t*) p;
+    return RT3_OK;
+}
+
+int rt3_frame_release(rt3_ctx* ctx, uint32_t* peer_frame) {
+    if (!ctx) { return fail(RT3_ERR_INVALID, "ctx is NULL"); }
+    if (!peer_frame) { return RT3_OK; }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    RT3_CUDA(cudaIpcCloseMemHandle(peer_frame));
+    return RT3_OK;
+}
+
 uint32_t rt3_uv_sphere_faces(uint32_t n_meridians, uint32_t n_parallels) { return n_parallels >= 3 ? uv_sphere_faces(n_meridians, n_parallels) : 0u; }
 uint32_t rt3_uv_sphere_vertices(uint32_t n_meridians, uint32_t n_parallels) { return n_parallels >= 3 ? uv_sphere_vertices(n_meridians, n_parallels) : 0u; }
 
@@ -888,7 +960,6 @@ int rt3_tessellate_spheres(rt3_ctx* ctx, const rt3_uv_sphere* spheres, uint32_t 
     if (host_face_entity) { RT3_CUDA(cudaMemcpyAsync(host_face_entity, d_entity.ptr, n_faces * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)); }
     RT3_CUDA(cudaStreamSynchronize(ctx->stream));
     if (first_vertex) { for (unsigned long long f = 0; f < n_faces; f++) { host_faces[f].v1 += first_vertex; host_faces[f].v2 += first_vertex; host_faces[f].v3 += first_vertex; } }
-    d_vertices.release(); d_faces.release(); d_entity.release();
     return RT3_OK;
 }
 
@@ -938,7 +1009,6 @@ int rt3_measure_fma_peak(rt3_ctx* ctx, double* tflops_out) {
         double tf = flops / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) { best = tf; }
     }
-    out.release();
     *tflops_out = best;
     return RT3_OK;
 }

@@ -6,6 +6,11 @@ src/lib/shaders/raytracer/raytracer_v4.glsl:70-79) and every rank renders its ti
 replicated scene. Only the packed uint32 pixels travel, once per frame: each rank packs its
 rows into a compact slab (padded to the largest slab so a plain gather works), rank 0 gathers
 over NCCL (gloo in the CPU tests) and de-interleaves.
+
+``SharedFrame`` removes that gather on a node with NVLink: rank 0's frame is mapped into every
+other rank (CUDA IPC, include/rt3cuda.h rt3_frame_*), each rank's render kernels store their
+rows straight into it (frames use full-frame indexing), and the frame end is one stream-ordered
+barrier.
 """
 import numpy as np
 import torch
@@ -44,3 +49,52 @@ def gather_slabs(dist, slab, rank, world, dst=0):
     bucket = [torch.empty_like(slab) for _ in range(world)] if rank == dst else None
     dist.gather(slab, bucket, dst=dst)
     return bucket
+
+
+class _DevicePointer:
+    """Lets torch view memory the render core allocated (``__cuda_array_interface__``, int32 words)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+
+class SharedFrame:
+    """One frame in rank ``owner``'s HBM that every rank of the node renders into.
+
+    ``ptr`` is what each rank passes to ``Context.render_device`` as the frame (the owner's own
+    allocation there, the IPC mapping elsewhere); ``tensor`` is the owner's torch view of it
+    (None on the other ranks). ``finish()`` is the frame-end barrier: an all-reduce of one
+    element on the current stream, after which the owner's stream has every rank's pixels.
+    """
+
+    def __init__(self, ctx, dist, n_pixels, rank, world, device, owner=0):
+        self.ctx, self.dist, self.rank, self.world, self.owner = ctx, dist, rank, world, owner
+        self.ptr, self.tensor, self._mapped = None, None, False
+        handle = [None]
+        if rank == owner:
+            self.ptr = ctx.frame_alloc(n_pixels)
+            self.tensor = torch.as_tensor(_DevicePointer(self.ptr, n_pixels), device=device)
+            handle[0] = ctx.frame_export(self.ptr) if world > 1 else None
+        if world > 1:
+            dist.broadcast_object_list(handle, src=owner)
+            if rank != owner:
+                self.ptr = ctx.frame_import(handle[0])
+                self._mapped = True
+            self._token = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.all_reduce(self._token)
+
+    def close(self):
+        """Unmaps on the importing ranks, then frees on the owner (collective: every rank calls it)."""
+        if self.ptr is None:
+            return
+        if self._mapped:
+            self.ctx.frame_release(self.ptr)
+        if self.world > 1:
+            self.dist.barrier()
+        if self.rank == self.owner:
+            self.tensor = None
+            self.ctx.frame_free(self.ptr)
+        self.ptr = None
