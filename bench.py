@@ -307,6 +307,21 @@ def main():
     e2e_s = float(e2e_s.item())
     st_e2e = ctx.stats()
 
+    # ---- N>1: the assembled frame must be the one-GPU frame, bit for bit (untimed; rank 0 renders every row itself) ----
+    frame_matches = None
+    if world > 1:
+        device_step()
+        sync_all()
+        if rank == 0:
+            whole = torch.zeros(H * W, dtype=torch.int32, device=dev)
+            one = abi.make_params(W, H, mode=abi.MODE_PATHTRACE, spp=spp, max_depth=DEPTH, seed=SEED, flags=abi.FLAG_BVH if args.bvh else 0, tile_rows=TILE_ROWS)
+            ctx.render_device(cam, one, whole.data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize()
+            frame_matches = bool(torch.equal(whole, frame))
+            if not frame_matches:
+                raise SystemExit(f"the frame assembled from {world} partitions differs from the one-GPU frame")
+        sync_all()
+
     # ---- informational: the same frame through the hierarchy (RT3_FLAG_BVH), device-timed, not part of `value` ----
     hierarchy = None
     if world == 1 and not args.bvh:
@@ -356,6 +371,7 @@ def main():
         if hierarchy:
             line["hierarchy"] = hierarchy
         if world > 1:
+            line["frame_matches_single_gpu"] = frame_matches
             line["config"]["frame_end"] = ("each rank's kernels store its rows into rank 0's frame over NVLink (CUDA IPC mapping), one-element all-reduce as barrier"
                                            if peer else "pack + NCCL gather onto rank 0 + de-interleave")
         if args.bvh:
