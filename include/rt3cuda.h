@@ -244,6 +244,12 @@ int rt3_frame_free(rt3_ctx* ctx, uint32_t* device_frame);
 int rt3_frame_export(rt3_ctx* ctx, const uint32_t* device_frame, unsigned char* handle_out);
 int rt3_frame_import(rt3_ctx* ctx, const unsigned char* handle, uint32_t** peer_frame);
 int rt3_frame_release(rt3_ctx* ctx, uint32_t* peer_frame);
+/* Same sharing inside one process (several contexts, one per GPU): rt3_frame_attach lets `ctx`'s device store into
+ * frames that live on `owner`'s device (peer access; nothing to do when the two are one device), after which a
+ * pointer from rt3_frame_alloc(owner) is a valid `device_frame` for rt3_render_device(ctx). rt3_frame_read copies
+ * n_pixels packed pixels of a device frame into host memory and returns when they are there. */
+int rt3_frame_attach(rt3_ctx* ctx, rt3_ctx* owner);
+int rt3_frame_read(rt3_ctx* ctx, const uint32_t* device_frame, uint32_t* host_frame, uint64_t n_pixels);
 
 /* Scene construction on the device (the step before the path): tessellates `n` UV spheres with the arithmetic of
  * the reference's CPU pre-render (src/lib/entities/Sphere.cpp:69-79,120-351; GPU twins

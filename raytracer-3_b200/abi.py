@@ -200,6 +200,8 @@ def load_core():
     lib.rt3_frame_export.argtypes = [vp, vp, C.c_char_p]
     lib.rt3_frame_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     lib.rt3_frame_release.argtypes = [vp, vp]
+    lib.rt3_frame_attach.argtypes = [vp, vp]
+    lib.rt3_frame_read.argtypes = [vp, vp, vp, C.c_uint64]
     lib.rt3_uv_sphere_faces.argtypes = [u32, u32]
     lib.rt3_uv_sphere_faces.restype = u32
     lib.rt3_uv_sphere_vertices.argtypes = [u32, u32]
@@ -215,6 +217,7 @@ EXPORTED_SYMBOLS = [
     "rt3_last_error", "rt3_create", "rt3_destroy", "rt3_scene_upload", "rt3_render", "rt3_render_aov",
     "rt3_render_device", "rt3_partition_rows", "rt3_pack_partition", "rt3_unpack_partition", "rt3_frame_bytes",
     "rt3_frame_alloc", "rt3_frame_free", "rt3_frame_export", "rt3_frame_import", "rt3_frame_release",
+    "rt3_frame_attach", "rt3_frame_read",
     "rt3_uv_sphere_faces", "rt3_uv_sphere_vertices", "rt3_tessellate_spheres",
     "rt3_get_stats", "rt3_measure_fma_peak",
 ]
@@ -319,6 +322,16 @@ class Context:
 
     def frame_release(self, ptr):
         self._check(self.lib.rt3_frame_release(self.handle, C.c_void_p(ptr)))
+
+    def frame_attach(self, owner):
+        """rt3_frame_attach: this context's GPU may store into frames allocated by ``owner`` (same process)."""
+        self._check(self.lib.rt3_frame_attach(self.handle, owner.handle))
+
+    def frame_read(self, ptr, width, height):
+        """rt3_frame_read: blocking copy of a device frame into a new (height, width) uint32 array."""
+        out = np.zeros((height, width), np.uint32)
+        self._check(self.lib.rt3_frame_read(self.handle, C.c_void_p(ptr), _ptr(out), width * height))
+        return out
 
     def stats(self):
         st = Stats()

@@ -920,6 +920,27 @@ int rt3_frame_release(rt3_ctx* ctx, uint32_t* peer_frame) {
     return RT3_OK;
 }
 
+int rt3_frame_attach(rt3_ctx* ctx, rt3_ctx* owner) {
+    if (!ctx || !owner) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    if (ctx->device == owner->device) { return RT3_OK; }
+    int can = 0;
+    RT3_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, owner->device));
+    if (!can) { return fail(RT3_ERR_CUDA, "device %d cannot access the memory of device %d", ctx->device, owner->device); }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(owner->device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void) cudaGetLastError(); e = cudaSuccess; }
+    if (e != cudaSuccess) { (void) cudaGetLastError(); return fail(RT3_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", owner->device, cudaGetErrorString(e)); }
+    return RT3_OK;
+}
+
+int rt3_frame_read(rt3_ctx* ctx, const uint32_t* device_frame, uint32_t* host_frame, uint64_t n_pixels) {
+    if (!ctx || !device_frame || !host_frame) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    RT3_CUDA(cudaMemcpyAsync(host_frame, device_frame, (size_t) n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RT3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RT3_OK;
+}
+
 uint32_t rt3_uv_sphere_faces(uint32_t n_meridians, uint32_t n_parallels) { return n_parallels >= 3 ? uv_sphere_faces(n_meridians, n_parallels) : 0u; }
 uint32_t rt3_uv_sphere_vertices(uint32_t n_meridians, uint32_t n_parallels) { return n_parallels >= 3 ? uv_sphere_vertices(n_meridians, n_parallels) : 0u; }
 

@@ -114,6 +114,21 @@ int rt3host_renderer_create(void* s, int device, uint32_t mode, uint32_t spp, ui
         hs->renderer->set_settings(st);
     });
 }
+/* The same over several devices (one context each, CudaRenderer(const std::vector<int>&)); a device may be listed twice. */
+int rt3host_renderer_create_multi(void* s, const int* devices, uint32_t n_devices, uint32_t mode, uint32_t spp, uint32_t max_depth, uint32_t seed,
+                                  uint32_t flags, int analytic_spheres, uint32_t tile_rows) {
+    HostScene* hs = (HostScene*) s;
+    return guarded([&] {
+        delete hs->renderer;
+        hs->renderer = nullptr;
+        hs->renderer = new CudaRenderer(std::vector<int>(devices, devices + n_devices));
+        CudaRenderSettings st;
+        st.mode = mode; st.spp = spp; st.max_depth = max_depth; st.seed = seed; st.flags = flags;
+        st.analytic_spheres = (analytic_spheres & 1) != 0; st.device_tessellation = (analytic_spheres & 2) != 0;
+        if (tile_rows) { st.tile_rows = tile_rows; }
+        hs->renderer->set_settings(st);
+    });
+}
 int rt3host_set_material(void* s, uint32_t entity_index, uint32_t kind, const float* albedo, float fuzz, float ior) {
     HostScene* hs = (HostScene*) s;
     if (!hs->renderer) { g_error = "create the renderer first"; return -1; }

@@ -44,12 +44,65 @@ CudaRenderSettings CudaRenderSettings::from_environment(int* device) {
     return s;
 }
 
-CudaRenderer::CudaRenderer(int device) : Renderer(), ctx(nullptr) {
+std::vector<int> CudaRenderSettings::devices_from_environment() {
+    std::vector<int> out;
+    const char* v = std::getenv("RT3_DEVICES");
+    if (v && std::string(v) == "all") {
+        /* as many as rt3_create accepts */
+        for (int d = 0; d < 64; d++) {
+            rt3_ctx* probe = nullptr;
+            if (rt3_create(&probe, d) != RT3_OK) { break; }
+            rt3_destroy(probe);
+            out.push_back(d);
+        }
+    } else if (v && *v) {
+        const char* p = v;
+        while (*p) {
+            char* end = nullptr;
+            long d = std::strtol(p, &end, 10);
+            if (end == p) { break; }
+            out.push_back((int) d);
+            p = (*end == ',') ? end + 1 : end;
+            if (*end != ',' && *end != '\0') { break; }
+        }
+    }
+    if (out.empty()) { out.push_back((int) env_u32("RT3_DEVICE", 0)); }
+    return out;
+}
+
+CudaRenderer::CudaRenderer(int device) : Renderer(), ctx(nullptr), shared_frame(nullptr), shared_pixels(0) {
     std::memset(&this->last_stats, 0, sizeof this->last_stats);
     check(rt3_create(&this->ctx, device), "Could not create the CUDA render context");
 }
 
-CudaRenderer::~CudaRenderer() { rt3_destroy(this->ctx); }
+CudaRenderer::CudaRenderer(const std::vector<int>& devices) : Renderer(), ctx(nullptr), shared_frame(nullptr), shared_pixels(0) {
+    std::memset(&this->last_stats, 0, sizeof this->last_stats);
+    if (devices.empty()) { DLOG(fatal, "CudaRenderer needs at least one device."); }
+    check(rt3_create(&this->ctx, devices[0]), "Could not create the CUDA render context");
+    for (size_t i = 1; i < devices.size(); i++) {
+        rt3_ctx* helper = nullptr;
+        int rc = rt3_create(&helper, devices[i]);
+        if (rc == RT3_OK) {
+            this->helpers.push_back(helper);
+            rc = rt3_frame_attach(helper, this->ctx);
+        }
+        if (rc != RT3_OK) {
+            const std::string why = rt3_last_error();
+            this->release();
+            DLOG(fatal, "Could not set up device " + std::to_string(devices[i]) + ": " + why);
+        }
+    }
+}
+
+void CudaRenderer::release() noexcept {
+    if (this->shared_frame) { rt3_frame_free(this->ctx, this->shared_frame); this->shared_frame = nullptr; this->shared_pixels = 0; }
+    for (size_t i = 0; i < this->helpers.size(); i++) { rt3_destroy(this->helpers[i]); }
+    this->helpers.clear();
+    rt3_destroy(this->ctx);
+    this->ctx = nullptr;
+}
+
+CudaRenderer::~CudaRenderer() { this->release(); }
 
 void CudaRenderer::prerender(const Tools::Array<ECS::RenderEntity*>& entities) {
     this->flat_faces.clear(); this->flat_vertices.clear(); this->flat_face_entity.clear(); this->flat_spheres.clear();
@@ -155,6 +208,7 @@ void CudaRenderer::prerender(const Tools::Array<ECS::RenderEntity*>& entities) {
     scene.n_materials = (uint32_t) table.size();
     scene.materials = table.data();
     check(rt3_scene_upload(this->ctx, &scene), "Could not upload the scene");
+    for (size_t i = 0; i < this->helpers.size(); i++) { check(rt3_scene_upload(this->helpers[i], &scene), "Could not upload the scene to a further device"); }
 }
 
 void CudaRenderer::render(Camera& camera) const { this->render_samples(camera, 0, false); }
@@ -193,15 +247,50 @@ void CudaRenderer::render_samples(Camera& camera, uint32_t first_sample, bool ac
     params.tile_rows = this->settings.tile_rows;
     params.part_index = this->settings.part_index;
     params.part_count = this->settings.part_count;
-    check(rt3_render(this->ctx, &cam, &params, camera.get_frame().d()), "Render failed");
-    check(rt3_get_stats(this->ctx, &this->last_stats), "Could not read render statistics");
+    if (this->helpers.empty()) {
+        check(rt3_render(this->ctx, &cam, &params, camera.get_frame().d()), "Render failed");
+        check(rt3_get_stats(this->ctx, &this->last_stats), "Could not read render statistics");
+        return;
+    }
+
+    /* several devices: every context renders its tiles into the first device's frame (stores over NVLink), asynchronously;
+     * the statistics calls below wait for each of them, then the frame is read once */
+    const uint64_t n_pixels = (uint64_t) params.width * params.height;
+    if (this->shared_pixels != n_pixels) {
+        if (this->shared_frame) { check(rt3_frame_free(this->ctx, this->shared_frame), "Could not free the shared frame"); this->shared_frame = nullptr; this->shared_pixels = 0; }
+        check(rt3_frame_alloc(this->ctx, n_pixels, &this->shared_frame), "Could not allocate the shared frame");
+        this->shared_pixels = n_pixels;
+    }
+    const uint32_t n = (uint32_t) this->n_devices();
+    const uint32_t outer = params.part_count ? params.part_count : 1; /* this process may itself be one part of a larger split */
+    for (uint32_t i = 0; i < n; i++) {
+        rt3_params mine = params;
+        mine.part_count = outer * n;
+        mine.part_index = i * outer + params.part_index; /* tile % (outer n) == i outer + p  implies  tile % outer == p */
+        check(rt3_render_device(i == 0 ? this->ctx : this->helpers[i - 1], &cam, &mine, this->shared_frame, nullptr), "Render failed");
+    }
+    rt3_stats total;
+    std::memset(&total, 0, sizeof total);
+    for (uint32_t i = 0; i < n; i++) {
+        rt3_stats st;
+        check(rt3_get_stats(i == 0 ? this->ctx : this->helpers[i - 1], &st), "Could not read render statistics");
+        if (i == 0) { total = st; continue; }
+        total.rays += st.rays; total.sphere_tests += st.sphere_tests; total.face_tests += st.face_tests;
+        total.accel_node_visits += st.accel_node_visits; total.accel_prim_tests += st.accel_prim_tests;
+        total.rows_rendered += st.rows_rendered; total.kernel_launches += st.kernel_launches;
+        if (st.device_ms > total.device_ms) { total.device_ms = st.device_ms; }
+        if (st.trace_kernel_ms > total.trace_kernel_ms) { total.trace_kernel_ms = st.trace_kernel_ms; }
+    }
+    check(rt3_frame_read(this->ctx, this->shared_frame, camera.get_frame().d(), n_pixels), "Could not read the frame");
+    this->last_stats = total;
 }
 
 /* Factory of this backend (reference Renderer.hpp:63; counterpart of SequentialRenderer.cpp:315-323). */
 Renderer* RayTracer::initialize_renderer() {
     int device = 0;
     CudaRenderSettings settings = CudaRenderSettings::from_environment(&device);
-    CudaRenderer* renderer = new CudaRenderer(device);
+    const std::vector<int> devices = CudaRenderSettings::devices_from_environment();
+    CudaRenderer* renderer = devices.size() > 1 ? new CudaRenderer(devices) : new CudaRenderer(devices[0]);
     renderer->set_settings(settings);
     return (Renderer*) renderer;
 }

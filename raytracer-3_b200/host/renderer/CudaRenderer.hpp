@@ -49,17 +49,27 @@ namespace RayTracer {
         uint32_t tile_rows = 8, part_index = 0, part_count = 1;
         /* Reads RT3_MODE (reference|pathtrace), RT3_SPP, RT3_DEPTH, RT3_SEED, RT3_ANALYTIC_SPHERES, RT3_DEVICE_TESSELLATION, RT3_BVH, RT3_BVH_ABOVE, RT3_DEVICE. */
         static CudaRenderSettings from_environment(int* device);
+        /* RT3_DEVICES = comma-separated device ids ("0,1,2,3") or "all"; falls back to the single RT3_DEVICE. */
+        static std::vector<int> devices_from_environment();
     };
 
     class CudaRenderer : public Renderer {
-        rt3_ctx* ctx;
+        rt3_ctx* ctx;                 /* first device: owns the frame when there are several */
+        std::vector<rt3_ctx*> helpers; /* further devices: each renders its row tiles straight into ctx's frame */
+        mutable uint32_t* shared_frame;
+        mutable uint64_t shared_pixels;
         CudaRenderSettings settings;
         std::map<size_t, Material> materials;
         mutable rt3_stats last_stats;
         void render_samples(Camera& camera, uint32_t first_sample, bool accumulate) const;
+        void release() noexcept;
 
     public:
         explicit CudaRenderer(int device = 0);
+        /* One context per listed device; a frame is split in row tiles of settings.tile_rows rows dealt round-robin over
+         * them, the scene is replicated. The result is the one-device frame bit for bit (global pixel indices seed the RNG). */
+        explicit CudaRenderer(const std::vector<int>& devices);
+        size_t n_devices() const { return 1 + this->helpers.size(); }
         CudaRenderer(const CudaRenderer&) = delete;
         virtual ~CudaRenderer();
 

@@ -24,6 +24,7 @@ def lib():
         L.rt3host_add_object.argtypes = [vp, C.c_char_p, fp, C.c_float, fp]
         L.rt3host_flatten.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), vp, vp, vp]
         L.rt3host_renderer_create.argtypes = [vp, C.c_int, u32, u32, u32, u32, u32, C.c_int]
+        L.rt3host_renderer_create_multi.argtypes = [vp, C.POINTER(C.c_int), u32, u32, u32, u32, u32, u32, C.c_int, u32]
         L.rt3host_set_material.argtypes = [vp, u32, u32, fp, C.c_float, C.c_float]
         L.rt3host_prerender.argtypes = [vp]
         L.rt3host_render.argtypes = [vp, u32, u32, C.c_float, C.c_float, C.c_float, fp, vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
@@ -89,6 +90,12 @@ class HostScene:
                         device_tessellation=False):
         self._ok(self.L.rt3host_renderer_create(self.h, device, mode, spp, max_depth, seed, flags,
                                                 int(analytic_spheres) | (2 if device_tessellation else 0)))
+
+    def create_renderer_multi(self, devices, mode=abi.MODE_REFERENCE, spp=1, max_depth=1, seed=1, flags=0, analytic_spheres=False,
+                              device_tessellation=False, tile_rows=0):
+        arr = (C.c_int * len(devices))(*devices)
+        self._ok(self.L.rt3host_renderer_create_multi(self.h, arr, len(devices), mode, spp, max_depth, seed, flags,
+                                                      int(analytic_spheres) | (2 if device_tessellation else 0), tile_rows))
 
     def set_material(self, entity_index, kind, albedo=(1, 1, 1), fuzz=0.0, ior=1.5):
         self._ok(self.L.rt3host_set_material(self.h, entity_index, kind, _f(albedo), fuzz, ior))

@@ -96,3 +96,50 @@ def test_progressive_mode_through_the_host_backend(built):
         one_shot, _, _ = scene(3 * (k + 1)).render(w, h, focal=1.0)
         assert np.array_equal(frames[k], one_shot), f"pass {k}"
     assert not np.array_equal(frames[0], frames[3])
+
+
+def gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("mode", [abi.MODE_REFERENCE, abi.MODE_PATHTRACE])
+def test_several_devices_render_the_one_device_frame(built, mode):
+    """CudaRenderer over several contexts (SURVEY 8e behind the reference's Renderer interface): every context renders its
+    row tiles into the first one's frame. Uses distinct GPUs when the box has them; otherwise the same GPU three times,
+    which runs the same split, frame sharing and statistics merge."""
+    w, h = 120, 67
+    devices = [0, 1, 0] if gpu_count() >= 2 else [0, 0, 0]
+
+    def scene(multi):
+        hs = hostlib.HostScene()
+        hs.add_sphere((0, -100.5, -1), 100.0, 8, 8, (0.8, 0.8, 0.0))
+        hs.add_sphere((0, 0, -1), 0.5, 12, 12, (0.1, 0.2, 0.5))
+        hs.add_triangle((1, 0, -2), (-1, 0, -2), (0, 1, -2), (1, 0, 0))
+        kw = dict(mode=mode, spp=5, max_depth=12, seed=9)
+        if multi:
+            hs.create_renderer_multi(devices, tile_rows=4, **kw)
+        else:
+            hs.create_renderer(**kw)
+        hs.prerender()
+        return hs
+
+    one, _, rays_one = scene(False).render(w, h, focal=1.0)
+    hs = scene(True)
+    many, ms, rays_many = hs.render(w, h, focal=1.0)
+    assert np.array_equal(many, one)
+    assert rays_many == rays_one and ms > 0
+    again, _, _ = hs.render(w // 2, h // 2, focal=1.0)        # the shared frame is re-allocated for another size
+    small, _, _ = scene(False).render(w // 2, h // 2, focal=1.0)
+    assert np.array_equal(again, small)
+    if mode == abi.MODE_PATHTRACE:
+        frames = hs.render_progressive(w, h, 2, focal=1.0)     # accumulators stay with the context that owns the rows
+        assert np.array_equal(frames[0], one)
+        hs2 = hostlib.HostScene()
+        hs2.add_sphere((0, -100.5, -1), 100.0, 8, 8, (0.8, 0.8, 0.0))
+        hs2.add_sphere((0, 0, -1), 0.5, 12, 12, (0.1, 0.2, 0.5))
+        hs2.add_triangle((1, 0, -2), (-1, 0, -2), (0, 1, -2), (1, 0, 0))
+        hs2.create_renderer(mode=mode, spp=10, max_depth=12, seed=9)
+        hs2.prerender()
+        ten, _, _ = hs2.render(w, h, focal=1.0)
+        assert np.array_equal(frames[1], ten)

@@ -80,3 +80,22 @@ def test_argument_errors(gpu_ctx):
         gpu_ctx.frame_import(b"short")
     with pytest.raises(abi.Rt3Error):
         gpu_ctx.frame_import(bytes(abi.IPC_HANDLE_BYTES))  # not a handle anybody exported
+
+
+def test_shared_frame_single_rank(gpu_ctx):
+    """distributed.SharedFrame with one rank: the owner's torch view is the memory the kernels wrote."""
+    import torch
+    from rt3_b200 import distributed
+    scene, cam = scenes.rtiow_four_spheres(W, H)
+    gpu_ctx.upload(scene)
+    params = abi.make_params(W, H, mode=abi.MODE_PATHTRACE, spp=2, max_depth=5, seed=3)
+    whole = gpu_ctx.render(cam, params)
+    shared = distributed.SharedFrame(gpu_ctx, None, W * H, 0, 1, torch.device("cuda", 0))
+    try:
+        gpu_ctx.render_device(cam, params, shared.ptr, None)
+        shared.finish()
+        gpu_ctx.stats()
+        assert np.array_equal(shared.tensor.cpu().numpy().view(np.uint32).reshape(H, W), whole)
+    finally:
+        shared.close()
+    assert shared.ptr is None
