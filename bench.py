@@ -33,7 +33,7 @@ W, H, SPP, DEPTH, SEED, TILE_ROWS = 1200, 800, 500, 50, 1, 2
 FLOP_PER_SPHERE_TEST, FLOP_PER_FACE_TEST = 17, 45
 CPU_SAMPLE = dict(width=480, height=320, spp=48)    # bounded sample of the same workload for the CPU legs (~20 M ray segments)
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
-NCU_DRAM_BYTES_PER_LAUNCH = 23143680 + 0            # profiles/r01_v3_ncu_summary.txt (N = 1, the BASELINE config)
+NCU_DRAM_BYTES_PER_LAUNCH = 23199488 + 0            # profiles/r01_v3_ncu_summary.txt (N = 1, the BASELINE config)
 
 
 def hbm_line(kernel_ms):
