@@ -225,6 +225,10 @@ def main():
     torch.cuda.set_stream(stream)
     peer = world > 1 and args.gather == "peer"
     shared = distributed.SharedFrame(ctx, dist, H * W, rank, world, dev) if peer else None
+    if shared and not shared.ok:   # agreed on by all ranks: no mapping somewhere -> plain NCCL gather everywhere
+        print(f"[bench] rank {rank}: shared frame unavailable ({shared.error}); gathering with NCCL", file=sys.stderr)
+        shared.close()
+        shared, peer = None, False
     frame = shared.tensor if (peer and rank == 0) else torch.zeros(H * W, dtype=torch.int32, device=dev)
     frame_ptr = shared.ptr if peer else frame.data_ptr()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

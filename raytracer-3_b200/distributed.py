@@ -65,22 +65,39 @@ class SharedFrame:
     allocation there, the IPC mapping elsewhere); ``tensor`` is the owner's torch view of it
     (None on the other ranks). ``finish()`` is the frame-end barrier: an all-reduce of one
     element on the current stream, after which the owner's stream has every rank's pixels.
+    Construction and ``close()`` are collective. If any rank cannot map the frame (no peer access
+    between two GPUs, IPC unavailable), ``ok`` is False on every rank and ``error`` says why: the
+    caller then closes it and gathers with NCCL instead.
     """
 
     def __init__(self, ctx, dist, n_pixels, rank, world, device, owner=0):
         self.ctx, self.dist, self.rank, self.world, self.owner = ctx, dist, rank, world, owner
-        self.ptr, self.tensor, self._mapped = None, None, False
+        self.ptr, self.tensor, self._mapped, self.error = None, None, False, None
         handle = [None]
         if rank == owner:
-            self.ptr = ctx.frame_alloc(n_pixels)
-            self.tensor = torch.as_tensor(_DevicePointer(self.ptr, n_pixels), device=device)
-            handle[0] = ctx.frame_export(self.ptr) if world > 1 else None
+            try:
+                self.ptr = ctx.frame_alloc(n_pixels)
+                self.tensor = torch.as_tensor(_DevicePointer(self.ptr, n_pixels), device=device)
+                handle[0] = ctx.frame_export(self.ptr) if world > 1 else None
+            except Exception as e:  # reported below, after the collectives every rank takes part in
+                self.error = e
         if world > 1:
             dist.broadcast_object_list(handle, src=owner)
             if rank != owner:
-                self.ptr = ctx.frame_import(handle[0])
-                self._mapped = True
+                try:
+                    if handle[0] is None:
+                        raise RuntimeError(f"rank {owner} could not export its frame")
+                    self.ptr = ctx.frame_import(handle[0])
+                    self._mapped = True
+                except Exception as e:
+                    self.error = e
             self._token = torch.zeros(1, dtype=torch.int32, device=device)
+            # all ranks agree on whether the mapping exists everywhere
+            bad = torch.tensor([1 if self.error is not None else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(bad)
+            if int(bad.item()) and self.error is None:
+                self.error = RuntimeError("another rank could not map the shared frame")
+        self.ok = self.error is None
 
     def finish(self):
         if self.world > 1:
@@ -88,13 +105,13 @@ class SharedFrame:
 
     def close(self):
         """Unmaps on the importing ranks, then frees on the owner (collective: every rank calls it)."""
-        if self.ptr is None:
-            return
         if self._mapped:
             self.ctx.frame_release(self.ptr)
+            self._mapped = False
+            self.ptr = None
         if self.world > 1:
             self.dist.barrier()
-        if self.rank == self.owner:
+        if self.rank == self.owner and self.ptr is not None:
             self.tensor = None
             self.ctx.frame_free(self.ptr)
         self.ptr = None

@@ -47,6 +47,19 @@ def test_partition_rows_cover_the_image(built, h, tile, cnt):
     assert sum(rows) == h
 
 
+@pytest.mark.parametrize("h,tile,outer,inner", [(225, 8, 2, 3), (67, 4, 1, 3), (800, 2, 4, 2), (36, 1, 3, 5)])
+def test_partitions_nest(built, h, tile, outer, inner):
+    """A process that is part p of `outer` and splits its share over `inner` devices (CudaRenderer with several contexts) uses
+    parts i * outer + p of outer * inner: together exactly the rows of part p."""
+    from rt3_b200 import distributed
+    lib = abi.load_core()
+    for p in range(outer):
+        mine = set(distributed.owned_rows(h, tile, p, outer).tolist())
+        split = [distributed.owned_rows(h, tile, i * outer + p, outer * inner).tolist() for i in range(inner)]
+        assert sum(len(x) for x in split) == len(mine) and set().union(*map(set, split)) == mine
+        assert [len(x) for x in split] == [lib.rt3_partition_rows(h, tile, i * outer + p, outer * inner) for i in range(inner)]
+
+
 def test_fails_loudly_without_a_device(built):
     """No CPU fallback: on a box without CUDA, creating a context is an error, not a slow path."""
     try:
