@@ -269,6 +269,11 @@ int rt3_tessellate_spheres(rt3_ctx* ctx, const rt3_uv_sphere* spheres, uint32_t 
 int rt3_frame_bytes(rt3_ctx* ctx, const uint32_t* device_frame, unsigned char* device_out, uint32_t width, uint32_t height, uint32_t channels,
                     void* cuda_stream);
 
+/* Float AOV of the last path-traced render on this context: the mean linear radiance behind the frame (the value the
+ * resolve takes the square root of and packs, reference packing SequentialRenderer.cpp:297), 3 floats (r, g, b) per pixel,
+ * width * height pixels in frame order (the size of that render, checked); rows of other partitions are 0. Blocking. */
+int rt3_read_radiance(rt3_ctx* ctx, float* host_rgb, uint32_t width, uint32_t height);
+
 int rt3_get_stats(rt3_ctx* ctx, rt3_stats* out);
 
 /* Achieved FP32 FMA throughput of a dependent-chain-free FFMA micro-kernel on

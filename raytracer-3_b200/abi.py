@@ -207,6 +207,7 @@ def load_core():
     lib.rt3_uv_sphere_vertices.argtypes = [u32, u32]
     lib.rt3_uv_sphere_vertices.restype = u32
     lib.rt3_tessellate_spheres.argtypes = [vp, C.POINTER(UvSphere), u32, u32, vp, vp, vp]
+    lib.rt3_read_radiance.argtypes = [vp, vp, u32, u32]
     lib.rt3_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.rt3_measure_fma_peak.argtypes = [vp, C.POINTER(C.c_double)]
     _core = lib
@@ -219,7 +220,7 @@ EXPORTED_SYMBOLS = [
     "rt3_frame_alloc", "rt3_frame_free", "rt3_frame_export", "rt3_frame_import", "rt3_frame_release",
     "rt3_frame_attach", "rt3_frame_read",
     "rt3_uv_sphere_faces", "rt3_uv_sphere_vertices", "rt3_tessellate_spheres",
-    "rt3_get_stats", "rt3_measure_fma_peak",
+    "rt3_read_radiance", "rt3_get_stats", "rt3_measure_fma_peak",
 ]
 
 
@@ -331,6 +332,12 @@ class Context:
         """rt3_frame_read: blocking copy of a device frame into a new (height, width) uint32 array."""
         out = np.zeros((height, width), np.uint32)
         self._check(self.lib.rt3_frame_read(self.handle, C.c_void_p(ptr), _ptr(out), width * height))
+        return out
+
+    def read_radiance(self, width, height):
+        """rt3_read_radiance: mean linear radiance of the last path-traced render, (height, width, 3) float32."""
+        out = np.zeros((height, width, 3), np.float32)
+        self._check(self.lib.rt3_read_radiance(self.handle, _ptr(out), width, height))
         return out
 
     def stats(self):

@@ -112,6 +112,8 @@ struct rt3_ctx {
     DeviceBuffer<float> aov_t;
     DeviceBuffer<unsigned long long> accum, counters;
     uint32_t accum_width = 0, accum_height = 0; /* frame the accumulators were last cleared for */
+    rt3_kparams accum_kp{};                      /* the path-traced render the accumulators currently hold */
+    bool accum_valid = false;
 
     rt3_stats stats{};
 };
@@ -483,6 +485,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
             return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE needs a previous path-traced render of the same %ux%u frame on this context", kp.width, kp.height);
         }
     } else {
+        ctx->accum_valid = false;
         rc = ctx->accum.reserve(n_acc);
         if (rc != RT3_OK) { return rc; }
         ctx->accum_width = kp.width; ctx->accum_height = kp.height;
@@ -502,6 +505,8 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     RT3_CUDA(cudaGetLastError());
     RT3_CUDA(cudaEventRecord(ctx->ev_end, stream));
     ctx->stats.kernel_launches = accumulate ? 2 : 3;
+    ctx->accum_kp = kp;
+    ctx->accum_valid = true;
     return RT3_OK;
 }
 
@@ -997,6 +1002,29 @@ int rt3_frame_bytes(rt3_ctx* ctx, const uint32_t* device_frame, unsigned char* d
     if (channels == 4) { frame_bytes_kernel<4><<<grid, 256, 0, stream>>>(device_frame, device_out, n); }
     else { frame_bytes_kernel<3><<<grid, 256, 0, stream>>>(device_frame, device_out, n); }
     RT3_CUDA(cudaGetLastError());
+    return RT3_OK;
+}
+
+int rt3_read_radiance(rt3_ctx* ctx, float* host_rgb, uint32_t width, uint32_t height) {
+    if (!ctx || !host_rgb) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    if (!ctx->accum_valid) { return fail(RT3_ERR_INVALID, "no path-traced render on this context to read the radiance of"); }
+    const rt3_kparams& kp = ctx->accum_kp;
+    if (kp.width != width || kp.height != height) {
+        return fail(RT3_ERR_INVALID, "the last path-traced frame was %ux%u, not %ux%u", kp.width, kp.height, width, height);
+    }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t) kp.width * kp.height * 3;
+    DeviceBuffer<float> rgb;
+    int rc = rgb.reserve(n);
+    if (rc != RT3_OK) { return rc; }
+    cudaStream_t stream = ctx->last_stream ? ctx->last_stream : ctx->stream; /* behind the render that filled the accumulators */
+    RT3_CUDA(cudaMemsetAsync(rgb.ptr, 0, n * sizeof(float), stream));
+    if (kp.n_pixels) {
+        radiance_kernel<<<(unsigned) ((kp.n_pixels + 255ull) / 256ull), 256, 0, stream>>>(kp, ctx->accum.ptr, rgb.ptr);
+        RT3_CUDA(cudaGetLastError());
+    }
+    RT3_CUDA(cudaMemcpyAsync(host_rgb, rgb.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    RT3_CUDA(cudaStreamSynchronize(stream));
     return RT3_OK;
 }
 

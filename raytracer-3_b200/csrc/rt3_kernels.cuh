@@ -5,6 +5,7 @@
  *   pathtrace_kernel   : persistent multi-bounce path tracer with in-warp path
  *                        regeneration and fixed-point accumulation.
  *   resolve_kernel     : mean over samples, gamma, 8-bit pack.
+ *   radiance_kernel    : the same mean as linear float RGB (AOV dump).
  *   pack/unpack kernels: frame <-> partition slab for the frame-end gather.
  *   fma_peak_kernel    : FFMA throughput probe (roofline denominator).
  *
@@ -671,6 +672,16 @@ __global__ void resolve_kernel(rt3_kparams P, const unsigned long long* __restri
         ch[c] = unorm8(m);
     }
     frame[idx] = (ch[0] << 24) | (ch[1] << 16) | (ch[2] << 8) | 0xFFu;
+}
+
+/* The same mean as a float image (linear radiance: before gamma and the pack), for AOV dumps. */
+__global__ void radiance_kernel(rt3_kparams P, const unsigned long long* __restrict__ accum, float* __restrict__ rgb) {
+    unsigned long long p = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_pixels) { return; }
+    uint32_t local_row = (uint32_t) (p / P.width), x = (uint32_t) (p - (unsigned long long) local_row * P.width);
+    size_t idx = (size_t) owned_row_to_global(P, local_row) * P.width + x;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { rgb[3 * idx + c] = (float) ((double) accum[3 * idx + c] / ((double) P.resolve_spp * (double) RT3_ACC_SCALE)); }
 }
 
 /* Clears the accumulators of the owned rows. */

@@ -169,6 +169,19 @@ int rt3host_render_progressive(void* s, uint32_t width, uint32_t height, float f
         }, &sink);
     });
 }
+/* CudaRenderer::read_radiance of the last render (rgb_out: width * height * 3 floats) and, if path != NULL, write_radiance_pfm. */
+int rt3host_radiance(void* s, uint32_t width, uint32_t height, float* rgb_out, const char* path) {
+    HostScene* hs = (HostScene*) s;
+    if (!hs->renderer) { g_error = "create the renderer first"; return -1; }
+    return guarded([&] {
+        if (rgb_out) {
+            std::vector<float> rgb;
+            hs->renderer->read_radiance(width, height, rgb);
+            std::memcpy(rgb_out, rgb.data(), rgb.size() * sizeof(float));
+        }
+        if (path) { hs->renderer->write_radiance_pfm(width, height, path); }
+    });
+}
 int rt3host_camera_vectors(uint32_t width, uint32_t height, const float* look, float* out19) {
     return guarded([&] {
         Camera cam;

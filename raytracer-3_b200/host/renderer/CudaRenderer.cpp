@@ -1,4 +1,5 @@
 /* renderer/CudaRenderer.cpp — see CudaRenderer.hpp. */
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -283,6 +284,31 @@ void CudaRenderer::render_samples(Camera& camera, uint32_t first_sample, bool ac
     }
     check(rt3_frame_read(this->ctx, this->shared_frame, camera.get_frame().d(), n_pixels), "Could not read the frame");
     this->last_stats = total;
+}
+
+void CudaRenderer::read_radiance(uint32_t width, uint32_t height, std::vector<float>& rgb) const {
+    const size_t n = (size_t) width * height * 3;
+    rgb.assign(n, 0.0f);
+    check(rt3_read_radiance(this->ctx, rgb.data(), width, height), "Could not read the radiance");
+    if (this->helpers.empty()) { return; }
+    /* every context returns zeros outside the rows it rendered: the frame is their sum */
+    std::vector<float> part(n);
+    for (size_t i = 0; i < this->helpers.size(); i++) {
+        check(rt3_read_radiance(this->helpers[i], part.data(), width, height), "Could not read the radiance of a further device");
+        for (size_t k = 0; k < n; k++) { rgb[k] += part[k]; }
+    }
+}
+
+void CudaRenderer::write_radiance_pfm(uint32_t width, uint32_t height, const std::string& path) const {
+    std::vector<float> rgb;
+    this->read_radiance(width, height, rgb);
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) { DLOG(fatal, "Could not open '" + path + "' for writing."); }
+    std::fprintf(f, "PF\n%u %u\n-1.0\n", width, height); /* negative scale: little-endian */
+    bool ok = true;
+    for (uint32_t y = height; y-- > 0 && ok;) { ok = std::fwrite(rgb.data() + (size_t) y * width * 3, sizeof(float), (size_t) width * 3, f) == (size_t) width * 3; }
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) { DLOG(fatal, "Could not write '" + path + "'."); }
 }
 
 /* Factory of this backend (reference Renderer.hpp:63; counterpart of SequentialRenderer.cpp:315-323). */

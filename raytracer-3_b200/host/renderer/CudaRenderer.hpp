@@ -18,6 +18,7 @@
 
 #include <cstdint>
 #include <map>
+#include <string>
 #include <vector>
 
 #include "renderer/Renderer.hpp"
@@ -89,6 +90,12 @@ namespace RayTracer {
          * passes * spp samples bit for bit. Path tracing only. */
         typedef void (*FrameCallback)(uint32_t pass, const Frame& frame, void* user);
         void render_progressive(Camera& camera, uint32_t passes, FrameCallback on_frame = nullptr, void* user = nullptr) const;
+
+        /* Float AOV of the last path-traced render(): mean linear radiance (before gamma and the 8-bit pack), 3 floats per
+         * pixel in frame order (rt3_read_radiance; with several devices each context contributes the rows it rendered). */
+        void read_radiance(uint32_t width, uint32_t height, std::vector<float>& rgb) const;
+        /* The same as a Portable Float Map ("PF", little-endian, rows bottom to top), the float counterpart of Frame::to_ppm. */
+        void write_radiance_pfm(uint32_t width, uint32_t height, const std::string& path) const;
 
         /* Device timings / ray counters of the last render(). */
         const rt3_stats& stats() const { return this->last_stats; }

@@ -2,10 +2,10 @@
  * (create renderer, camera, entities; prerender; render; save), with the scene chosen by name.
  *
  *   rt3_render [-W width] [-H height] [-s scene] [-o out.ppm|out.png] [--teddy path/to/teddy.obj]
- *              [--pathtrace] [--spp n] [--depth n] [--seed n] [--analytic] [--passes k]
+ *              [--pathtrace] [--spp n] [--depth n] [--seed n] [--analytic] [--passes k] [--pfm out.pfm]
  *   --pathtrace / --spp / --depth / --seed: CudaRenderSettings (default: the reference's ray caster); --analytic keeps
  *   ECS spheres analytic; --passes k renders k progressive passes of spp samples each (render_progressive) and writes
- *   the frame after every pass to <out>.<pass>.<ext>.
+ *   the frame after every pass to <out>.<pass>.<ext>; --pfm also writes the linear float radiance (path tracing only).
  *   scenes: default (reference Main.cpp:280-283, needs --teddy), triangle, sphere, rtiow (path traced, C1),
  *           or the path of a SceneLang file (*.scene)
  */
@@ -26,7 +26,7 @@ using namespace RayTracer;
 
 int main(int argc, const char** argv) {
     uint32_t width = 800, height = 600; /* reference defaults, Main.cpp:78-79 */
-    std::string scene = "triangle", out = "result.ppm", teddy = "bin/objects/teddy.obj";
+    std::string scene = "triangle", out = "result.ppm", teddy = "bin/objects/teddy.obj", pfm;
     bool pathtrace = false, analytic = false;
     uint32_t spp = 0, depth = 0, seed = 0, passes = 1;
     for (int i = 1; i < argc; i++) {
@@ -42,9 +42,10 @@ int main(int argc, const char** argv) {
         else if (a == "--spp") { spp = (uint32_t) std::strtoul(next(), nullptr, 0); pathtrace = true; }
         else if (a == "--depth") { depth = (uint32_t) std::strtoul(next(), nullptr, 0); }
         else if (a == "--seed") { seed = (uint32_t) std::strtoul(next(), nullptr, 0); }
+        else if (a == "--pfm") { pfm = next(); pathtrace = true; }
         else if (a == "--passes") { passes = (uint32_t) std::strtoul(next(), nullptr, 0); pathtrace = true; }
         else { std::fprintf(stderr, "usage: %s [-W w] [-H h] [-s default|triangle|sphere|rtiow|file.scene] [-o out.ppm|out.png] [--teddy file] "
-                               "[--pathtrace] [--spp n] [--depth n] [--seed n] [--analytic] [--passes k]\n", argv[0]); return a == "-h" ? 0 : 1; }
+                               "[--pathtrace] [--spp n] [--depth n] [--seed n] [--analytic] [--passes k] [--pfm out.pfm]\n", argv[0]); return a == "-h" ? 0 : 1; }
     }
     try {
         Renderer* renderer = initialize_renderer();
@@ -108,6 +109,7 @@ int main(int argc, const char** argv) {
             else { delete (ECS::Triangle*) entities[i]; }
         }
         save(cam.get_frame(), out);
+        if (!pfm.empty()) { cuda->write_radiance_pfm(width, height, pfm); }
         std::printf("%s: %ux%u, %.3f ms on the device, %llu rays -> %s\n", scene.c_str(), width, height, cuda->stats().device_ms,
                     (unsigned long long) cuda->stats().rays, out.c_str());
         delete renderer;

@@ -31,6 +31,7 @@ def lib():
         L.rt3host_camera_vectors.argtypes = [u32, u32, fp, fp]
         L.rt3host_render_progressive.argtypes = [vp, u32, u32, C.c_float, C.c_float, C.c_float, u32, vp]
         L.rt3host_add_scene_text.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(u32)]
+        L.rt3host_radiance.argtypes = [vp, u32, u32, vp, C.c_char_p]
         L.rt3host_write_image.argtypes = [vp, u32, u32, C.c_char_p, C.c_int]
         _lib = L
     return _lib
@@ -116,6 +117,12 @@ class HostScene:
         vw = float(np.float32(np.float32(width) / np.float32(height)) * np.float32(2.0))
         self._ok(self.L.rt3host_render_progressive(self.h, width, height, focal, vw, vh, passes, frames.ctypes.data))
         return frames
+
+    def radiance(self, width, height, path=None):
+        """CudaRenderer::read_radiance (and write_radiance_pfm when a path is given): (height, width, 3) float32."""
+        rgb = np.zeros((height, width, 3), np.float32)
+        self._ok(self.L.rt3host_radiance(self.h, width, height, rgb.ctypes.data, path.encode() if path else None))
+        return rgb
 
     def close(self):
         if self.h:

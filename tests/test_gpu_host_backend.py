@@ -143,3 +143,48 @@ def test_several_devices_render_the_one_device_frame(built, mode):
         hs2.prerender()
         ten, _, _ = hs2.render(w, h, focal=1.0)
         assert np.array_equal(frames[1], ten)
+
+
+def read_pfm(path):
+    with open(path, "rb") as f:
+        assert f.readline() == b"PF\n"
+        w, h = map(int, f.readline().split())
+        assert float(f.readline()) < 0          # little-endian
+        data = np.frombuffer(f.read(), "<f4").reshape(h, w, 3)
+    return data[::-1]                            # rows are stored bottom to top
+
+
+def test_radiance_dump_through_the_host_backend(built, tmp_path):
+    """CudaRenderer::read_radiance / write_radiance_pfm (float AOV of the output side), one and several contexts."""
+    w, h = 64, 36
+
+    def scene(devices):
+        hs = hostlib.HostScene()
+        hs.add_sphere((0, -100.5, -1), 100.0, 8, 8, (0.8, 0.8, 0.0))
+        hs.add_sphere((0, 0, -1), 0.5, 8, 8, (0.1, 0.2, 0.5))
+        kw = dict(mode=abi.MODE_PATHTRACE, spp=4, max_depth=10, seed=2, analytic_spheres=True)
+        if devices:
+            hs.create_renderer_multi(devices, tile_rows=2, **kw)
+        else:
+            hs.create_renderer(**kw)
+        hs.prerender()
+        return hs
+
+    hs = scene(None)
+    frame, _, _ = hs.render(w, h, focal=1.0)
+    path = str(tmp_path / "radiance.pfm")
+    rgb = hs.radiance(w, h, path)
+    v = np.clip(np.sqrt(rgb), np.float32(0), np.float32(1)) * np.float32(255)
+    ch = np.floor(v.astype(np.float64) + 0.5).astype(np.uint32)
+    assert np.array_equal((ch[..., 0] << 24) | (ch[..., 1] << 16) | (ch[..., 2] << 8) | np.uint32(0xFF), frame)
+    assert np.array_equal(read_pfm(path), rgb)
+    many = scene([0, 0])
+    frame2, _, _ = many.render(w, h, focal=1.0)
+    assert np.array_equal(frame2, frame) and np.array_equal(many.radiance(w, h), rgb)
+    ref = hostlib.HostScene()
+    ref.add_triangle((1, 0, -3), (-1, 0, -3), (0, 1, -3), (1, 0, 0))
+    ref.create_renderer(mode=abi.MODE_REFERENCE)
+    ref.prerender()
+    ref.render(w, h)
+    with pytest.raises(hostlib.HostError, match="path-traced"):
+        ref.radiance(w, h)

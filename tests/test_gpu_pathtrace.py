@@ -161,3 +161,35 @@ def test_progressive_refinement_equals_one_shot(gpu_ctx):
     assert np.array_equal(gpu_ctx.render(cam, params), cpu)
     with pytest.raises(abi.Rt3Error, match="ACCUMULATE"):
         gpu_ctx.render(cam, abi.make_params(w + 2, h, spp=1, first_sample=12, flags=abi.FLAG_ACCUMULATE, **base))
+
+
+def resolve_like_the_kernel(rgb):
+    """resolve_kernel on a float image: gamma 2, then glm::packUnorm4x8 = round-half-away(clamp(v, 0, 1) * 255)."""
+    v = np.sqrt(rgb.astype(np.float32))
+    v = np.clip(v, np.float32(0), np.float32(1)) * np.float32(255)
+    ch = np.floor(v.astype(np.float64) + 0.5).astype(np.uint32)
+    return (ch[..., 0] << 24) | (ch[..., 1] << 16) | (ch[..., 2] << 8) | np.uint32(0xFF)
+
+
+def test_radiance_aov_is_the_frame_before_gamma_and_pack(gpu_ctx):
+    """rt3_read_radiance: the float image whose resolve is the packed frame, exactly; partitions return their rows only."""
+    w, h = 96, 54
+    scene, cam = scenes.rtiow_four_spheres(w, h)
+    gpu_ctx.upload(scene)
+    params = abi.make_params(w, h, mode=abi.MODE_PATHTRACE, spp=6, max_depth=12, seed=5)
+    frame = gpu_ctx.render(cam, params)
+    rgb = gpu_ctx.read_radiance(w, h)
+    assert rgb.shape == (h, w, 3) and np.isfinite(rgb).all() and rgb.min() >= 0 and rgb.max() > 0.5
+    assert np.array_equal(resolve_like_the_kernel(rgb), frame)
+    with pytest.raises(abi.Rt3Error, match="96x54"):
+        gpu_ctx.read_radiance(w, h + 1)
+    # the accumulators of a progressive render hold every pass so far
+    gpu_ctx.render(cam, abi.make_params(w, h, mode=abi.MODE_PATHTRACE, spp=3, max_depth=12, seed=5))
+    gpu_ctx.render(cam, abi.make_params(w, h, mode=abi.MODE_PATHTRACE, spp=3, max_depth=12, seed=5, flags=abi.FLAG_ACCUMULATE, first_sample=3))
+    assert np.array_equal(gpu_ctx.read_radiance(w, h), rgb)
+    # one partition of three: its rows, zeros elsewhere
+    part = gpu_ctx.render(cam, abi.make_params(w, h, mode=abi.MODE_PATHTRACE, spp=6, max_depth=12, seed=5, tile_rows=4, part_index=1, part_count=3))
+    mine = (np.arange(h) // 4) % 3 == 1
+    got = gpu_ctx.read_radiance(w, h)
+    assert np.array_equal(got[mine], rgb[mine]) and not got[~mine].any()
+    assert np.array_equal(part[mine], frame[mine])
