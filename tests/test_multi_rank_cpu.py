@@ -66,3 +66,49 @@ def test_owned_rows_partition_the_image():
     for h, tile, world in [(800, 8, 8), (225, 8, 2), (7, 3, 4), (2160, 16, 8)]:
         rows = np.concatenate([distributed.owned_rows(h, tile, r, world) for r in range(world)])
         assert sorted(rows.tolist()) == list(range(h))
+
+
+class _NoSharing:
+    """Stands in for a context whose GPU cannot share frames (no IPC / no peer access)."""
+
+    def __init__(self, fail_on_owner):
+        self.fail_on_owner = fail_on_owner
+
+    def frame_alloc(self, n_pixels):
+        if self.fail_on_owner:
+            raise RuntimeError("cudaIpcGetMemHandle failed: operation not supported")
+        raise AssertionError("this stand-in has no device memory")
+
+    def frame_import(self, handle):
+        raise RuntimeError("cudaIpcOpenMemHandle failed: peer access is not supported between these two devices")
+
+    def frame_release(self, ptr):
+        raise AssertionError("nothing was mapped")
+
+    def frame_free(self, ptr):
+        raise AssertionError("nothing was allocated")
+
+
+def _shared_frame_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import rt3_b200  # noqa: F401
+    from rt3_b200 import distributed
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shared = distributed.SharedFrame(_NoSharing(fail_on_owner=True), dist, 64 * 37, rank, world, torch.device("cpu"))
+    verdict = f"ok={shared.ok} error={type(shared.error).__name__} ptr={shared.ptr}"
+    shared.close()   # collective, must not touch the (absent) mapping
+    with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+        f.write(verdict)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shared_frame_setup_fails_on_every_rank_together(built, tmp_path):
+    """SharedFrame: when the owner cannot export its frame, every rank learns it in the same collective calls (no hang, no
+    half-mapped state) and the caller can fall back to the NCCL gather."""
+    mp.spawn(_shared_frame_worker, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
+    for rank in range(3):
+        assert (tmp_path / f"rank{rank}.txt").read_text() == "ok=False error=RuntimeError ptr=None"
