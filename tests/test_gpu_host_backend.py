@@ -188,3 +188,20 @@ def test_radiance_dump_through_the_host_backend(built, tmp_path):
     ref.render(w, h)
     with pytest.raises(hostlib.HostError, match="path-traced"):
         ref.radiance(w, h)
+
+
+def test_cli_over_several_contexts_and_pfm(built, tmp_path):
+    """rt3_render (initialize_renderer + RT3_DEVICES): the frame from two contexts equals the one-context frame; --pfm writes the float image."""
+    exe = os.path.join(ROOT, "raytracer-3_b200", "host", "rt3_render")
+    outs = {}
+    for tag, devices in (("one", None), ("two", "0,0")):
+        env = dict(os.environ)
+        env.pop("RT3_DEVICES", None)
+        if devices:
+            env["RT3_DEVICES"] = devices
+        ppm, pfm = tmp_path / f"{tag}.ppm", tmp_path / f"{tag}.pfm"
+        subprocess.run([exe, "-s", "rtiow", "-W", "160", "-H", "90", "--spp", "4", "--depth", "10", "-o", str(ppm), "--pfm", str(pfm)],
+                       check=True, env=env, stdout=subprocess.DEVNULL, timeout=120)
+        outs[tag] = (ppm.read_bytes(), read_pfm(str(pfm)))
+    assert outs["one"][0] == outs["two"][0]
+    assert outs["one"][1].shape == (90, 160, 3) and np.array_equal(outs["one"][1], outs["two"][1])
