@@ -324,6 +324,29 @@ namespace {
             if (name.text == "abs") { need(1); return Value::scalar(Type::real, std::fabs(real(0))); }
             if (name.text == "min") { need(2); return Value::scalar(Type::real, std::fmin(real(0), real(1))); }
             if (name.text == "max") { need(2); return Value::scalar(Type::real, std::fmax(real(0), real(1))); }
+            if (name.text == "tan") { need(1); return Value::scalar(Type::real, std::tan(real(0))); }
+            if (name.text == "pow") { need(2); return Value::scalar(Type::real, std::pow(real(0), real(1))); }
+            if (name.text == "floor") { need(1); return Value::scalar(Type::real, std::floor(real(0))); }
+            if (name.text == "ceil") { need(1); return Value::scalar(Type::real, std::ceil(real(0))); }
+            if (name.text == "radians") { need(1); return Value::scalar(Type::real, real(0) * (float) (M_PI / 180.0)); }
+            /* vector helpers (the specification names "vector operations and related build-in functions", its appendix C is empty) */
+            auto vec = [&](size_t i) -> const float* {
+                if (args[i].type != Type::vec3) { error(name.text + "() needs vec3 arguments", name.line); }
+                return args[i].v;
+            };
+            if (name.text == "dot") { need(2); const float *a = vec(0), *b = vec(1); return Value::scalar(Type::real, (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]); }
+            if (name.text == "length") { need(1); const float* a = vec(0); return Value::scalar(Type::real, std::sqrt((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2])); }
+            if (name.text == "cross") {
+                need(2);
+                const float *a = vec(0), *b = vec(1);
+                return Value::vector(a[1] * b[2] - b[1] * a[2], a[2] * b[0] - b[2] * a[0], a[0] * b[1] - b[0] * a[1]);
+            }
+            if (name.text == "normalize") {
+                need(1);
+                const float* a = vec(0);
+                const float inv = 1.0f / std::sqrt((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]);
+                return Value::vector(a[0] * inv, a[1] * inv, a[2] * inv);
+            }
             error("unknown function '" + name.text + "'", name.line);
         }
         Value unary() {

@@ -89,6 +89,28 @@ def test_include_and_expressions(built, tmp_path):
     same(parsed.flatten(), api.flatten())
 
 
+def test_builtin_functions(built):
+    """Scalar and vector built-ins (SceneLang.md section 3 names them, its appendix C lists none): evaluated in float like the API caller would."""
+    text = '''global { vec3 a: 1.0 2.0 2.0; vec3 b: 0.0 0.0 -1.0; float third: 1.0 / length(global.a); }
+    entities { sphere s { center: cross(global.a, global.b) + normalize(global.a) * 3.0;
+                          radius: pow(2.0, -1.0) + dot(global.a, global.b) * 0.0 + tan(0.0);
+                          n_meridians: (uint) ceil(5.5); n_parallels: (uint) floor(4.9) + (uint) (radians(180.0) > 3.14);
+                          color: global.third global.third max(0.25, min(global.third, 1.0)); } }'''
+    parsed = hostlib.HostScene()
+    assert parsed.add_scene_text(text)[0] == 1
+    f = np.float32
+    third = f(1) / f(3)
+    n = np.array([1, 2, 2], f) * (f(1) / np.sqrt(f(9)))
+    centre = np.array([-2, 1, 0], f) + n * f(3)          # a x b = (2*-1 - 0*2, 2*0 - (-1)*1, 0) = (-2, 1, 0)
+    api = hostlib.HostScene()
+    api.add_sphere(tuple(float(x) for x in centre), 0.5, 6, 5, (float(third), float(third), float(third)))
+    same(parsed.flatten(), api.flatten())
+    for bad, message in (("global { float x: dot(1.0, 2.0); }", "needs vec3"), ("global { float x: length(); }", "takes 1 argument"),
+                         ("global { float x: frobnicate(1.0); }", "unknown function")):
+        with pytest.raises(hostlib.HostError, match=message):
+            hostlib.HostScene().add_scene_text(bad)
+
+
 @pytest.mark.parametrize("text,message", [
     ("lights { }", "unknown section 'lights'"),
     ("entities { cube c { } }", "unknown entity type 'cube'"),
