@@ -25,6 +25,16 @@ def test_library_exports_every_declared_symbol(built):
     assert sorted(abi.EXPORTED_SYMBOLS) == names
 
 
+def test_headers_are_plain_c():
+    """The boundary is a C ABI: both public headers must compile as C99 on their own (what a cgo / JNI / ctypes-generator would see)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    for name in ("rt3cuda.h", "rt3_rng.h"):
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", name)], check=True)
+
+
 def test_struct_layouts_match_header():
     assert abi.FACE_DTYPE.itemsize == 48 and abi.VERTEX_DTYPE.itemsize == 16 and abi.MATERIAL_DTYPE.itemsize == 32
     assert C.sizeof(abi.Camera) == 4 * (12 + 1 + 6)
