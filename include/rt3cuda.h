@@ -142,9 +142,14 @@ typedef struct rt3_camera {
 #define RT3_FLAG_NO_JITTER 0x1u /* pathtrace: sample pixel centres (deterministic primary rays) */
 #define RT3_FLAG_NO_GAMMA 0x2u  /* pathtrace: resolve the linear mean instead of its square root */
 #define RT3_FLAG_ACCUMULATE 0x8u /* pathtrace, progressive refinement: keep the accumulators of the previous render of this context
-                                 * (same frame size and partition) and add this call's samples [first_sample, first_sample + spp)
-                                 * to them; the frame is resolved over first_sample + spp samples. k calls of n spp produce
-                                 * exactly the frame of one call of k*n spp (integer accumulation). */
+                                 * and add this call's samples [first_sample, first_sample + spp) to them; the frame is resolved
+                                 * over first_sample + spp samples. k calls of n spp produce exactly the frame of one call of
+                                 * k*n spp (integer accumulation). Checked (RT3_ERR_INVALID otherwise): same scene upload, frame
+                                 * size, partition, seed, max_depth and sampling flags as the accumulated render, and
+                                 * first_sample == the end of the range accumulated so far. */
+#define RT3_FLAG_UNIFORM_SKY 0x10u /* pathtrace: a miss returns radiance (1, 1, 1) instead of the reference's sky gradient
+                                 * (SequentialRenderer.cpp:105-107): the white-furnace configuration the energy-conservation
+                                 * tests use (an albedo-1 scene must resolve to exactly white) */
 #define RT3_FLAG_BVH 0x4u       /* closest hits through a bounding-volume hierarchy built on the device at the first such render
                                  * after rt3_scene_upload, instead of the reference's brute-force loop over every primitive
                                  * (SequentialRenderer.cpp:55-95). The frame and the AOVs are identical, bit for bit. */
@@ -216,7 +221,11 @@ int rt3_render_aov(rt3_ctx* ctx, const rt3_camera* camera, const rt3_params* par
 /* Device-resident variant for multi-GPU plumbing: renders this partition's
  * rows into `device_frame` (a device pointer to width*height uint32, full-frame
  * indexing) asynchronously on `cuda_stream` (a cudaStream_t; NULL = the
- * context's own stream). No host copies, no synchronisation. */
+ * context's own stream). No host copies, and the call does not wait for the render. It is not entirely free
+ * of synchronisation: the first RT3_FLAG_BVH render after an upload builds the hierarchy and waits for it, and
+ * when several contexts on one device take turns with scenes small enough for the constant bank
+ * (<= 768 primitives), a change of turn waits for the device to drain before the records are swapped.
+ * Contexts may be driven from different host threads (one thread per context at a time). */
 int rt3_render_device(rt3_ctx* ctx, const rt3_camera* camera, const rt3_params* params, uint32_t* device_frame,
                       void* cuda_stream);
 

@@ -277,6 +277,7 @@ static v3 trace_path(const rt3_scene* s, const rt3_camera* cam, const rt3_params
         (*rays)++;
         if (best.prim == NO_HIT) {
             /* sky, SequentialRenderer.cpp:105-107, for an already-unit direction */
+            if (p->flags & RT3_FLAG_UNIFORM_SKY) { return thr; } /* white furnace */
             float t = 0.5f * (d.y + 1.0f);
             float a = 1.0f - t;
             return vmul(thr, V(a * 1.0f + t * 0.5f, a * 1.0f + t * 0.7f, a * 1.0f + t * 1.0f));

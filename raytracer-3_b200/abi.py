@@ -16,7 +16,7 @@ CORE_LIB_PATH = os.path.join(_HERE, "csrc", "librt3cuda.so")
 
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 MODE_REFERENCE, MODE_PATHTRACE = 0, 1
-FLAG_NO_JITTER, FLAG_NO_GAMMA, FLAG_BVH, FLAG_ACCUMULATE = 0x1, 0x2, 0x4, 0x8
+FLAG_NO_JITTER, FLAG_NO_GAMMA, FLAG_BVH, FLAG_ACCUMULATE, FLAG_UNIFORM_SKY = 0x1, 0x2, 0x4, 0x8, 0x10
 NO_HIT = 0xFFFFFFFF
 IPC_HANDLE_BYTES = 64  # RT3_IPC_HANDLE_BYTES
 

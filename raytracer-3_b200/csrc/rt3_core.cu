@@ -245,9 +245,12 @@ void scene_basis(const std::vector<Bound>& b, float e[3][3]) {
     for (int k = 0; k < 3; k++) { e[0][k] = (float) a1[k]; e[1][k] = (float) a2[k]; e[2][k] = (float) a3[k]; }
 }
 
-/* Which scene owns the constant-bank records of each device (rt3_device.cuh c_pair_xy / c_pair_w). */
-std::mutex g_const_mutex;
+/* Which scene owns the constant-bank records of each device (rt3_device.cuh c_pair_xy / c_pair_w).
+ * One mutex per device, held from the claim until the kernel that reads the bank has been enqueued: a
+ * later claim by another context then waits for that kernel (cudaDeviceSynchronize under the same
+ * mutex) before it overwrites the records. */
 constexpr int RT3_MAX_DEVICES = 64;
+std::mutex g_const_mutex[RT3_MAX_DEVICES];
 uint64_t g_const_owner[RT3_MAX_DEVICES] = { 0 };
 std::atomic<uint64_t> g_next_scene_id{ 1 };
 
@@ -418,10 +421,11 @@ int build_bvh(rt3_ctx* ctx, cudaStream_t stream) {
 
 /* Makes this context's scene the owner of the device's constant-bank records. The bank is one per
  * device and module, so a change of owner waits for everything in flight on the device, copies the
- * records (device to device) and waits for the copy; renders of one scene never pay this. */
-int claim_constant_bank(rt3_ctx* ctx, cudaStream_t stream) {
-    std::lock_guard<std::mutex> lock(g_const_mutex);
-    if (ctx->device < 0 || ctx->device >= 64) { return fail(RT3_ERR_INVALID, "device %d out of range", ctx->device); }
+ * records (device to device) and waits for the copy; renders of one scene never pay this.
+ * `lock` is taken here and stays with the caller until its kernel launch has been enqueued. */
+int claim_constant_bank(rt3_ctx* ctx, cudaStream_t stream, std::unique_lock<std::mutex>& lock) {
+    if (ctx->device < 0 || ctx->device >= RT3_MAX_DEVICES) { return fail(RT3_ERR_INVALID, "device %d out of range", ctx->device); }
+    lock = std::unique_lock<std::mutex>(g_const_mutex[ctx->device]);
     if (g_const_owner[ctx->device] == ctx->scene_id) { return RT3_OK; }
     RT3_CUDA(cudaDeviceSynchronize());
     const size_t pairs = ctx->view.n_prims_padded / 2;
@@ -455,7 +459,8 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     ctx->stats_pending = true;
     ctx->copy_timed = false;
     int rc = RT3_OK;
-    if (resident && kp.n_pixels != 0 && (rc = claim_constant_bank(ctx, stream)) != RT3_OK) { return rc; }
+    std::unique_lock<std::mutex> bank_lock; /* released when this function returns, i.e. after the launch below */
+    if (resident && kp.n_pixels != 0 && (rc = claim_constant_bank(ctx, stream, bank_lock)) != RT3_OK) { return rc; }
     RT3_CUDA(cudaEventRecord(ctx->ev_begin, stream));
     RT3_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 4 * sizeof(unsigned long long), stream));
     if (kp.n_pixels == 0) {
@@ -481,8 +486,19 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     size_t n_acc = (size_t) kp.width * kp.height * 3;
     const bool accumulate = (params->flags & RT3_FLAG_ACCUMULATE) != 0;
     if (accumulate) {
-        if (ctx->accum_width != kp.width || ctx->accum_height != kp.height || !ctx->accum.ptr) {
-            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE needs a previous path-traced render of the same %ux%u frame on this context", kp.width, kp.height);
+        const rt3_kparams& prev = ctx->accum_kp;
+        if (!ctx->accum_valid || ctx->accum_width != kp.width || ctx->accum_height != kp.height || !ctx->accum.ptr) {
+            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE needs a previous path-traced render of the same %ux%u frame and scene on this context", kp.width, kp.height);
+        }
+        if (prev.tile_rows != kp.tile_rows || prev.part_index != kp.part_index || prev.part_count != kp.part_count) {
+            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE: partition (tile_rows %u, part %u of %u) differs from the accumulated render's (%u, %u of %u)",
+                        kp.tile_rows, kp.part_index, kp.part_count, prev.tile_rows, prev.part_index, prev.part_count);
+        }
+        if (prev.seed != kp.seed || prev.max_depth != kp.max_depth || ((prev.flags ^ kp.flags) & ~(RT3_FLAG_ACCUMULATE | RT3_FLAG_BVH | RT3_FLAG_NO_GAMMA))) {
+            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE: seed, max_depth and sampling flags must be those of the accumulated render");
+        }
+        if (kp.first_sample != prev.first_sample + prev.spp) {
+            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE: first_sample must continue the accumulated range (expected %u, got %u)", prev.first_sample + prev.spp, kp.first_sample);
         }
     } else {
         ctx->accum_valid = false;
@@ -658,6 +674,8 @@ int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     if ((unsigned long long) s->n_faces + s->n_spheres > 0x7FFFFFFFull) { return fail(RT3_ERR_INVALID, "too many primitives"); }
     RT3_CUDA(cudaSetDevice(ctx->device));
     ctx->has_scene = false;
+    ctx->accum_valid = false; /* the accumulators belong to the previous scene */
+    ctx->accum_width = ctx->accum_height = 0;
 
     const uint32_t nf = s->n_faces, ns = s->n_spheres, np = nf + ns;
     const uint32_t np_pad = (np + RT3_PAD_PRIMS - 1) / RT3_PAD_PRIMS * RT3_PAD_PRIMS;

@@ -441,6 +441,7 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
         float t = 0.5f * (dr.y + 1.0f);
         float a = 1.0f - t;
         L = s.thr * v3(a * 1.0f + t * 0.5f, a * 1.0f + t * 0.7f, a * 1.0f + t * 1.0f);
+        if (P.flags & RT3_FLAG_UNIFORM_SKY) { L = s.thr; } /* white furnace */
         done = true;
     } else {
         const uint32_t prim = best.prim;

@@ -14,10 +14,12 @@ from rt3_b200 import abi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 PORT_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+BOOK_LIB = os.path.join(ORACLE_DIR, "liboracle_book.so")
 REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_seq.so")
 REF_TEDDY = os.path.join(ORACLE_DIR, "_ref", "teddy.obj")
 
 _port = None
+_book = None
 _ref = None
 
 
@@ -72,6 +74,43 @@ def oracle_pathtrace(scene: abi.SceneArrays, camera, params, n_threads=0, want_a
                                      accum.ctypes.data if want_accum else None, C.byref(rays), n_threads)
     assert rc == 0
     return frame, accum, rays.value
+
+
+def book_render(scene: abi.SceneArrays, camera, width, height, spp, max_depth=50, seed=1, flags=0, rows=None, n_threads=0):
+    """The independent checker (oracle/rtiow_book.cpp): mean linear radiance [H, W, 3] float32 of rows `rows` = (first, count)."""
+    global _book
+    if _book is None:
+        if not os.path.exists(BOOK_LIB):
+            build("book")
+        _book = C.CDLL(BOOK_LIB)
+        _book.book_render.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Camera)] + [C.c_uint32] * 8 + [C.c_void_p, C.c_int]
+    first, count = rows if rows is not None else (0, height)
+    rgb = np.zeros((height, width, 3), np.float32)
+    st = scene.as_struct()
+    rc = _book.book_render(C.byref(st), C.byref(camera), width, height, spp, max_depth, seed, flags, first, count, rgb.ctypes.data, n_threads)
+    assert rc == 0
+    return rgb
+
+
+def resolve_8bit(rgb, gamma=True):
+    """The product's resolve on a float image: gamma 2, then glm::packUnorm4x8 rounding; returns [H, W, 3] uint8 levels as float64."""
+    v = np.sqrt(np.maximum(rgb.astype(np.float64), 0)) if gamma else rgb.astype(np.float64)
+    return np.floor(np.clip(v, 0, 1) * 255 + 0.5)
+
+
+def unpack_rgb(frame):
+    """Packed frame (r<<24 | g<<16 | b<<8 | a) -> [H, W, 3] float64 levels."""
+    return np.stack([(frame >> s) & 0xFF for s in (24, 16, 8)], -1).astype(np.float64)
+
+
+def psnr_levels(a, b):
+    mse = ((a - b) ** 2).mean()
+    return 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+def block_mean(img, k):
+    h, w = img.shape[0] // k * k, img.shape[1] // k * k
+    return img[:h, :w].reshape(h // k, k, w // k, k, -1).mean(axis=(1, 3))
 
 
 def have_ref():
