@@ -2,7 +2,7 @@
 bench.py --gpus N). Each config is rendered through the brute-force sweep and through the hierarchy
 (RT3_FLAG_BVH) -- the frames must be identical -- at the configured resolution and depth; spp is reduced
 where the brute-force side would take minutes, and says so. Device time is rt3_stats.device_ms
-(CUDA events around clear + trace + resolve). Usage: python profiles/configs.py [c1 c2 c3 c4 c5]"""
+(CUDA events around clear + trace + resolve). Usage: python profiles/configs.py [c1 c2 c3 c4 c5] [--oracle]"""
 import json
 import os
 import sys
@@ -16,21 +16,9 @@ import rt3_b200  # noqa: F401,E402
 from rt3_b200 import abi, scenes  # noqa: E402
 
 
-def c3_scene(w, h):
-    """~100k triangles (create_sphere(.., 225, 225, ..), reference Sphere.cpp tessellation) + 3 analytic spheres."""
-    import hostlib
-    hs = hostlib.HostScene()
-    hs.add_sphere((0, 0, -3), 1.0, 225, 225, (0.8, 0.3, 0.3))
-    mesh = hs.flatten()
-    mats = np.zeros(3, abi.MATERIAL_DTYPE)
-    mats["kind"] = [abi.MAT_LAMBERTIAN, abi.MAT_METAL, abi.MAT_DIELECTRIC]
-    mats["albedo"] = [(0.8, 0.8, 0.0), (0.8, 0.6, 0.2), (1, 1, 1)]
-    mats["fuzz"] = [0, 0.1, 0]
-    mats["ior"] = [1, 1, 1.5]
-    spheres = np.array([(0, -101, -3, 100), (2.2, 0, -3, 1), (-2.2, 0, -3, 1)], np.float32)
-    scene = abi.SceneArrays(faces=mesh.faces, vertices=mesh.vertices, face_entity=mesh.face_entity, spheres=spheres,
-                            sphere_material=np.arange(3, dtype=np.uint32), sphere_entity=np.arange(1, 4, dtype=np.uint32), materials=mats)
-    return scene, abi.reference_camera(w, h)
+import fullsize  # noqa: E402  (tests/fullsize.py: the configurations' real shapes and the oracle band check)
+
+c3_scene = fullsize.c3_scene
 
 
 CONFIGS = {
@@ -46,7 +34,7 @@ CONFIGS = {
 }
 
 ctx = abi.Context(0)
-for name in (sys.argv[1:] or list(CONFIGS)):
+for name in ([a for a in sys.argv[1:] if not a.startswith("--")] or list(CONFIGS)):
     c = CONFIGS[name]
     scene, cam = c["scene"](c["w"], c["h"])
     ctx.upload(scene)
@@ -63,6 +51,16 @@ for name in (sys.argv[1:] or list(CONFIGS)):
         if flag:
             out["bvh_build_ms"] = round(st.accel_build_ms, 3)
     out["frames_identical"] = bool(np.array_equal(frames["sweep"], frames["bvh"]))
+    if "--oracle" in sys.argv:
+        # row bands of the full-size frame (and sample windows where a row is minutes of brute force) against the CPU oracle
+        fc = fullsize.CONFIGS[name]
+        cpu = fullsize.oracle_bands(fc, scene, cam)
+        for path, flag in (("sweep", 0), ("bvh", abi.FLAG_BVH)):
+            if name == "c5" and path == "sweep":
+                continue
+            diff, rays_equal = fullsize.bands_match(fullsize.gpu_bands(ctx, fc, cam, flag), cpu)
+            out["matches_oracle_bands_" + path] = bool(diff == 0 and rays_equal)
+        out["oracle_bands"] = [list(b) for b in fullsize.bands(fc)]
     if c["spp"] != c["full_spp"]:
         # the configured sample count through the hierarchy (and through the sweep where that takes seconds, not minutes)
         for path, flag in (("bvh", abi.FLAG_BVH),) + ((("sweep", 0),) if name == "c4" else ()):

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-CORE_LIB_PATH = os.path.join(_HERE, "csrc", "librt3cuda.so")
+# RT3_CORE_LIB selects another build of the same library (profiling variants under profiles/); there is still no CPU path
+CORE_LIB_PATH = os.environ.get("RT3_CORE_LIB") or os.path.join(_HERE, "csrc", "librt3cuda.so")
 
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 MODE_REFERENCE, MODE_PATHTRACE = 0, 1

@@ -1054,6 +1054,19 @@ int rt3_get_stats(rt3_ctx* ctx, rt3_stats* out) {
     return RT3_OK;
 }
 
+#ifdef RT3_SURVIVOR_STATS
+/* Debug build only: reads and clears the level-1 survivor statistics (rt3_kernels.cuh g_survivor_stats). */
+int rt3_debug_survivor_stats(rt3_ctx* ctx, unsigned long long* out4) {
+    if (!ctx || !out4) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    RT3_CUDA(cudaDeviceSynchronize());
+    RT3_CUDA(cudaMemcpyFromSymbol(out4, g_survivor_stats, 4 * sizeof(unsigned long long)));
+    const unsigned long long zero[4] = { 0, 0, 0, 0 };
+    RT3_CUDA(cudaMemcpyToSymbol(g_survivor_stats, zero, sizeof zero));
+    return RT3_OK;
+}
+#endif
+
 int rt3_measure_fma_peak(rt3_ctx* ctx, double* tflops_out) {
     if (!ctx || !tflops_out) { return fail(RT3_ERR_INVALID, "NULL argument"); }
     int rc0 = collect_stats(ctx);

@@ -43,7 +43,8 @@
 #ifndef RT3_CTAS_PER_SM
 #define RT3_CTAS_PER_SM 5       /* register budget: 65536 / (128 * 5) = 102 per thread */
 #endif
-#define RT3_ITEM_CHUNK 256u     /* path items a warp claims per global atomic (short tail when the frame is split 8 ways) */
+#define RT3_ITEM_CHUNK 256u     /* path items a warp claims per global atomic while plenty are left ... */
+#define RT3_ITEM_CHUNK_MIN 32u  /* ... shrinking to this towards the end of the frame (rt3_kernels.cuh chunk_size) */
 
 /* Relative slack of the prefilter (64 units of 2^-24), applied to |c|^2 + r^2
  * per primitive (host, folded into R^2) and to |o|^2 per ray (folded into the

@@ -166,6 +166,23 @@ __device__ __forceinline__ void slot_filters(const rt3_scene_view& S, const rt3_
     }
 }
 
+#ifdef RT3_SURVIVOR_STATS
+/* Debug build only (profiles/survivors.py): how many primitives level 1 lets through. [0] survivors (ray, primitive) pairs,
+ * [1] sum over warp-drains of the largest per-lane survivor count (= iterations the warp spends in the drain loop),
+ * [2] warp-drains, [3] lanes with a live ray in them. */
+__device__ unsigned long long g_survivor_stats[4];
+__device__ __forceinline__ void count_survivors(const uint32_t* __restrict__ masks, uint32_t n_words, uint32_t nz, bool live) {
+    uint32_t mine = 0;
+    for (uint32_t wd = 0; wd < n_words; wd++) { if ((nz >> (n_words - 1u - wd)) & 1u) { mine += (uint32_t) __popc(masks[wd * RT3_CTA_THREADS]); } }
+    const uint32_t total = __reduce_add_sync(0xffffffffu, mine), most = __reduce_max_sync(0xffffffffu, mine);
+    const uint32_t lanes = (uint32_t) __popc(__ballot_sync(0xffffffffu, live));
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&g_survivor_stats[0], (unsigned long long) total); atomicAdd(&g_survivor_stats[1], (unsigned long long) most);
+        atomicAdd(&g_survivor_stats[2], 1ull); atomicAdd(&g_survivor_stats[3], (unsigned long long) lanes);
+    }
+}
+#endif
+
 /* Drains one chunk for every slot, one slot at a time from a single copy of the code. */
 template <bool SPHERES_ONLY>
 __device__ __forceinline__ void drain_slots(const rt3_scene_view& S, const rt3_smem_view& sm, uint32_t first_prim, uint32_t n_pairs,
@@ -183,6 +200,9 @@ __device__ __forceinline__ void drain_slots(const rt3_scene_view& S, const rt3_s
         rt3_ray_filter fr = f[0]; /* level 2 is only needed for faces; rebuilt below for the slot at hand */
         const rt3_vec3 o = slot_vec(sm, r, RT3_F_OX), d = slot_vec(sm, r, RT3_F_DX);
         if (!SPHERES_ONLY) { fr = make_ray_filter(S, o, d); }
+#ifdef RT3_SURVIVOR_STATS
+        count_survivors(sm.masks + r * RT3_CHUNK_WORDS * RT3_CTA_THREADS + threadIdx.x, n_words, mine, slot_word(sm, r, RT3_F_BOUNCE) != RT3_NO_HIT);
+#endif
         drain_chunk<true, SPHERES_ONLY>(S, first_prim, n_words, fr, o, d, sm.masks + r * RT3_CHUNK_WORDS * RT3_CTA_THREADS + threadIdx.x, mine, best);
         slot_word(sm, r, RT3_F_BEST_T) = __float_as_uint(best.t); slot_word(sm, r, RT3_F_BEST_PRIM) = best.prim;
     }
@@ -352,6 +372,16 @@ struct rt3_chunk {
     bool dry;                 /* the global counter is exhausted */
 };
 
+/* Items a warp takes from the global counter at a time: RT3_ITEM_CHUNK while there is plenty left, shrinking with
+ * what remains (guided self-scheduling) so that the warps run dry together -- with the frame split over 8 GPUs
+ * a kernel is only ~17 ms long and a fixed chunk of 256 items is a visible tail. `seen` is a (possibly stale)
+ * reading of the counter; any value is correct, it only steers the size. */
+__device__ __forceinline__ unsigned long long chunk_size(unsigned long long seen, const rt3_kparams& P) {
+    const unsigned long long left = seen < P.n_items ? P.n_items - seen : 0ull;
+    const unsigned long long share = left / ((unsigned long long) gridDim.x * (RT3_CTA_THREADS / 32) * 2ull);
+    return share >= RT3_ITEM_CHUNK ? RT3_ITEM_CHUNK : (share <= RT3_ITEM_CHUNK_MIN ? RT3_ITEM_CHUNK_MIN : share);
+}
+
 /* Warp-cooperative claim of one path item per requesting lane. Items are
  * item = pixel * spp + sample over this partition's compact pixel list. */
 __device__ __forceinline__ bool claim_item(bool want, rt3_chunk& c, const rt3_kparams& P, unsigned long long* next_item,
@@ -363,12 +393,16 @@ __device__ __forceinline__ bool claim_item(bool want, rt3_chunk& c, const rt3_kp
     bool got = false;
     while (n > 0 && !c.dry) {
         if (c.cur == c.end) {
-            unsigned long long v = 0;
-            if (lane == 0) { v = atomicAdd(next_item, (unsigned long long) RT3_ITEM_CHUNK); }
+            unsigned long long v = 0, size = 0;
+            if (lane == 0) {
+                size = chunk_size(*(volatile unsigned long long*) next_item, P);
+                v = atomicAdd(next_item, size);
+            }
             v = __shfl_sync(0xffffffffu, v, 0);
+            size = __shfl_sync(0xffffffffu, size, 0);
             if (v >= P.n_items) { c.dry = true; break; }
             c.cur = c.start = v;
-            c.end = v + RT3_ITEM_CHUNK < P.n_items ? v + RT3_ITEM_CHUNK : P.n_items;
+            c.end = v + size < P.n_items ? v + size : P.n_items;
             unsigned long long p0 = v / P.spp; /* one 64-bit divide per chunk */
             c.pixel0 = (uint32_t) p0;
             c.sample0 = (uint32_t) (v - p0 * P.spp);
