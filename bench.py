@@ -421,15 +421,16 @@ def main():
         executed_tflops = executed_frac = traffic = hbm = None
         executed_note = prof_src
         if prof:
-            # thread-level instruction counts: an FFMA is 2 FLOP, FMUL / FADD 1; the packed FFMA2 is counted by ncu as ONE ffma
-            # instruction per thread but performs two, so its count (from the opcode histogram of the same capture) is added once more
-            fl = 2.0 * (prof["ffma_thread_inst"] + prof.get("ffma2_thread_inst", 0)) + prof["fmul_thread_inst"] + prof["fadd_thread_inst"]
+            # thread-level instruction counts: an FFMA is 2 FLOP, FMUL / FADD 1. ncu's op_ffma counter does not include the packed
+            # FFMA2 (fma.rn.f32x2: two FMAs = 4 FLOP per thread instruction); its count comes from the per-opcode sums of the
+            # source page of the same capture (profiles/ncu_counters.py) and is consistent with op_fp32
+            fl = 2.0 * prof["ffma_thread_inst"] + 4.0 * prof.get("ffma2_thread_inst", 0) + prof["fmul_thread_inst"] + prof["fadd_thread_inst"]
             executed_tflops = fl / (st.trace_kernel_ms * 1e-3) / 1e12 if st.trace_kernel_ms > 0 else None
             executed_frac = executed_tflops / peak if (peak and executed_tflops is not None) else None
             traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
             hbm = hbm_line(st.trace_kernel_ms, traffic)
             executed_note = (f"{prof_src}: smsp__sass_thread_inst_executed_op_ffma/fmul/fadd_pred_on.sum of one launch of this workload "
-                             f"(ffma {prof['ffma_thread_inst']:.4g}, of which packed FFMA2 {prof.get('ffma2_thread_inst', 0):.4g} counted twice; "
+                             f"(FFMA {prof['ffma_thread_inst']:.4g} x 2 FLOP, packed FFMA2 {prof.get('ffma2_thread_inst', 0):.4g} x 4 FLOP from the source page; "
                              f"fmul {prof['fmul_thread_inst']:.4g}; fadd {prof['fadd_thread_inst']:.4g}) / this run's kernel time; "
                              f"pipe_fma_cycles_active {prof.get('pipe_fma_cycles_active_pct')} %, issue slots busy {prof.get('issue_active_pct')} %")
         line = {

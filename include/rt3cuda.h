@@ -176,7 +176,8 @@ typedef struct rt3_params {
 typedef struct rt3_stats {
     double device_ms;       /* CUDA-event time of all render kernels (clear + trace + resolve), on the render stream */
     double trace_kernel_ms; /* CUDA-event time of the dominant kernel alone (reference_kernel / pathtrace_kernel) */
-    double h2d_ms;          /* host->device copies inside rt3_render (camera/params) */
+    double h2d_ms;          /* host->device copies of the most recent rt3_scene_upload on this context (a render copies nothing to the
+                             * device: camera and parameters travel as kernel arguments); 0 after rt3_scene_upload_device */
     double d2h_ms;          /* device->host copy of the frame / AOVs */
     uint64_t rays;          /* ray segments traced (primary + bounce), counted by the kernel */
     uint64_t sphere_tests;  /* ray-sphere tests = rays * n_spheres (brute force) */
@@ -189,6 +190,9 @@ typedef struct rt3_stats {
     double accel_build_ms;      /* device time of the hierarchy build for the current scene */
     uint32_t accel;             /* 1 if the most recent render used the hierarchy */
     uint32_t _pad;
+    /* the most recent scene upload on this context (the reference's prerender, Main.cpp:284) */
+    double upload_ms;           /* wall clock of rt3_scene_upload / rt3_scene_upload_device, call to return */
+    double upload_device_ms;    /* CUDA-event time of the kernels that derive bounds, boxes, prefilter records and the scene basis */
 } rt3_stats;
 
 typedef struct rt3_ctx rt3_ctx;
@@ -201,8 +205,23 @@ const char* rt3_last_error(void);
 int rt3_create(rt3_ctx** out, int device);
 int rt3_destroy(rt3_ctx* ctx);
 
-/* Flattens the scene into device SoA arrays (replacing any previous scene). */
+/* Flattens the scene into device SoA arrays (replacing any previous scene): the input arrays are copied to the device as
+ * they are and everything derived from them (exact-test arrays, bounding spheres and boxes, prefilter records, the scene
+ * basis) is built there by kernels; the host does no per-primitive work. Validation errors (a face index or a material
+ * index out of range, an unknown material kind) are found on the device and reported here: the first one in input order. */
 int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* scene);
+
+/* The same for a scene that already lies in this context's device memory: every pointer of `scene` is a DEVICE pointer
+ * (faces, vertices, spheres and materials 16-byte aligned), e.g. buffers from rt3_buffer_alloc filled by
+ * rt3_tessellate_spheres_device and rt3_buffer_write. Nothing is copied from the host. The buffers are only read during
+ * the call. (The reference keeps its flattened scene on the GPU the same way, VulkanRenderer.cpp:266-399.) */
+int rt3_scene_upload_device(rt3_ctx* ctx, const rt3_scene* scene);
+
+/* Plain device memory on the context's GPU for such scenes; write / read are blocking copies. */
+int rt3_buffer_alloc(rt3_ctx* ctx, uint64_t bytes, void** device_ptr);
+int rt3_buffer_free(rt3_ctx* ctx, void* device_ptr);
+int rt3_buffer_write(rt3_ctx* ctx, void* device_dst, const void* host_src, uint64_t bytes);
+int rt3_buffer_read(rt3_ctx* ctx, void* host_dst, const void* device_src, uint64_t bytes);
 
 /* Renders into a HOST frame of width*height packed pixels, reference packing
  * r<<24 | g<<16 | b<<8 | 0xFF, index y*width + x, row 0 = top
@@ -270,6 +289,12 @@ uint32_t rt3_uv_sphere_faces(uint32_t n_meridians, uint32_t n_parallels);
 uint32_t rt3_uv_sphere_vertices(uint32_t n_meridians, uint32_t n_parallels);
 int rt3_tessellate_spheres(rt3_ctx* ctx, const rt3_uv_sphere* spheres, uint32_t n, uint32_t first_vertex, rt3_face* host_faces,
                            rt3_vertex* host_vertices, uint32_t* host_face_entity);
+/* The same without the trip to the host: the batch is written into DEVICE arrays the caller owns, sphere k's vertices
+ * from device_vertices[first_vertex] on and its faces from device_faces[first_face] on, face indices absolute (they index
+ * device_vertices). device_face_entity may be NULL. Asynchronous on the context's stream, which rt3_scene_upload_device
+ * and rt3_buffer_* also use, so the calls order themselves. */
+int rt3_tessellate_spheres_device(rt3_ctx* ctx, const rt3_uv_sphere* spheres, uint32_t n, uint32_t first_vertex, uint32_t first_face,
+                                  rt3_face* device_faces, rt3_vertex* device_vertices, uint32_t* device_face_entity);
 
 /* Output side (the step after the path, reference camera/Frame.cpp:88-96,131-142): unpacks a device frame of
  * width*height packed pixels into interleaved 8-bit RGB (channels = 3) or RGBA (channels = 4, alpha 255) bytes,

@@ -38,7 +38,8 @@ for name in ([a for a in sys.argv[1:] if not a.startswith("--")] or list(CONFIGS
     c = CONFIGS[name]
     scene, cam = c["scene"](c["w"], c["h"])
     ctx.upload(scene)
-    out = {"config": name, "what": c["what"], "spp": c["spp"], "spp_in_BASELINE": c["full_spp"], "faces": scene.n_faces, "spheres": scene.n_spheres}
+    up = ctx.stats()
+    out = {"config": name, "upload_ms": round(up.upload_ms, 3), "upload_h2d_ms": round(up.h2d_ms, 3), "upload_build_kernels_ms": round(up.upload_device_ms, 3), "what": c["what"], "spp": c["spp"], "spp_in_BASELINE": c["full_spp"], "faces": scene.n_faces, "spheres": scene.n_spheres}
     frames = {}
     for path, flag in (("sweep", 0), ("bvh", abi.FLAG_BVH)):
         params = abi.make_params(c["w"], c["h"], mode=abi.MODE_PATHTRACE, spp=c["spp"], max_depth=c["depth"], seed=1, flags=c.get("flags", 0) | flag)
@@ -50,6 +51,8 @@ for name in ([a for a in sys.argv[1:] if not a.startswith("--")] or list(CONFIGS
         out["rays"] = st.rays
         if flag:
             out["bvh_build_ms"] = round(st.accel_build_ms, 3)
+            out["bvh_node_visits_per_ray"] = round(st.accel_node_visits / max(st.rays, 1), 2)
+            out["bvh_prim_tests_per_ray"] = round(st.accel_prim_tests / max(st.rays, 1), 2)
     out["frames_identical"] = bool(np.array_equal(frames["sweep"], frames["bvh"]))
     if "--oracle" in sys.argv:
         # row bands of the full-size frame (and sample windows where a row is minutes of brute force) against the CPU oracle

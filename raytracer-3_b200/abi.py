@@ -83,6 +83,7 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_uint32), ("rows_rendered", C.c_uint32),
         ("accel_node_visits", C.c_uint64), ("accel_prim_tests", C.c_uint64), ("accel_build_ms", C.c_double),
         ("accel", C.c_uint32), ("_pad", C.c_uint32),
+        ("upload_ms", C.c_double), ("upload_device_ms", C.c_double),
     ]
 
 
@@ -188,6 +189,12 @@ def load_core():
     lib.rt3_create.argtypes = [C.POINTER(vp), C.c_int]
     lib.rt3_destroy.argtypes = [vp]
     lib.rt3_scene_upload.argtypes = [vp, C.POINTER(Scene)]
+    lib.rt3_scene_upload_device.argtypes = [vp, C.POINTER(Scene)]
+    lib.rt3_buffer_alloc.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
+    lib.rt3_buffer_free.argtypes = [vp, vp]
+    lib.rt3_buffer_write.argtypes = [vp, vp, vp, C.c_uint64]
+    lib.rt3_buffer_read.argtypes = [vp, vp, vp, C.c_uint64]
+    lib.rt3_tessellate_spheres_device.argtypes = [vp, C.POINTER(UvSphere), u32, u32, u32, vp, vp, vp]
     lib.rt3_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(Params), u32p]
     lib.rt3_render_aov.argtypes = [vp, C.POINTER(Camera), C.POINTER(Params), u32p, u32p, u32p, vp]
     lib.rt3_render_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(Params), vp, vp]
@@ -216,7 +223,8 @@ def load_core():
 
 
 EXPORTED_SYMBOLS = [
-    "rt3_last_error", "rt3_create", "rt3_destroy", "rt3_scene_upload", "rt3_render", "rt3_render_aov",
+    "rt3_last_error", "rt3_create", "rt3_destroy", "rt3_scene_upload", "rt3_scene_upload_device", "rt3_buffer_alloc", "rt3_buffer_free",
+    "rt3_buffer_write", "rt3_buffer_read", "rt3_tessellate_spheres_device", "rt3_render", "rt3_render_aov",
     "rt3_render_device", "rt3_partition_rows", "rt3_pack_partition", "rt3_unpack_partition", "rt3_frame_bytes",
     "rt3_frame_alloc", "rt3_frame_free", "rt3_frame_export", "rt3_frame_import", "rt3_frame_release",
     "rt3_frame_attach", "rt3_frame_read",
@@ -252,6 +260,48 @@ class Context:
     def upload(self, scene: SceneArrays):
         st = scene.as_struct()
         self._check(self.lib.rt3_scene_upload(self.handle, C.byref(st)))
+
+    def buffer_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.lib.rt3_buffer_alloc(self.handle, nbytes, C.byref(p)))
+        return p.value
+
+    def buffer_free(self, ptr):
+        self._check(self.lib.rt3_buffer_free(self.handle, C.c_void_p(ptr)))
+
+    def buffer_write(self, ptr, array):
+        a = np.ascontiguousarray(array)
+        self._check(self.lib.rt3_buffer_write(self.handle, C.c_void_p(ptr), _ptr(a), a.nbytes))
+
+    def buffer_read(self, ptr, array):
+        self._check(self.lib.rt3_buffer_read(self.handle, _ptr(array), C.c_void_p(ptr), array.nbytes))
+        return array
+
+    def to_device(self, array):
+        """A device copy of a host array (rt3_buffer_alloc + rt3_buffer_write); None stays None. The caller frees it."""
+        if array is None or array.nbytes == 0:
+            return None
+        p = self.buffer_alloc(array.nbytes)
+        self.buffer_write(p, array)
+        return p
+
+    def upload_device(self, n_faces=0, n_vertices=0, faces=None, vertices=None, face_material=None, face_entity=None,
+                      n_spheres=0, spheres=None, sphere_color=None, sphere_material=None, sphere_entity=None, n_materials=0, materials=None):
+        """rt3_scene_upload_device: every array argument is a DEVICE pointer (int) or None."""
+        st = Scene()
+        st.n_faces, st.n_vertices, st.n_spheres, st.n_materials = n_faces, n_vertices, n_spheres, n_materials
+        st.faces, st.vertices, st.face_material, st.face_entity = faces, vertices, face_material, face_entity
+        st.spheres, st.sphere_color, st.sphere_material, st.sphere_entity, st.materials = spheres, sphere_color, sphere_material, sphere_entity, materials
+        self._check(self.lib.rt3_scene_upload_device(self.handle, C.byref(st)))
+
+    def tessellate_spheres_device(self, spheres, first_vertex, first_face, faces_ptr, vertices_ptr, entity_ptr=None):
+        """rt3_tessellate_spheres_device: the batch is written straight into the caller's device arrays."""
+        arr = (UvSphere * len(spheres))()
+        for dst, (center, radius, m, p, color, entity) in zip(arr, spheres):
+            dst.center = (C.c_float * 3)(*center); dst.radius = radius; dst.n_meridians = m; dst.n_parallels = p
+            dst.color = (C.c_float * 3)(*color); dst.entity = entity
+        self._check(self.lib.rt3_tessellate_spheres_device(self.handle, arr, len(spheres), first_vertex, first_face, C.c_void_p(faces_ptr),
+                                                           C.c_void_p(vertices_ptr), C.c_void_p(entity_ptr or 0)))
 
     def render(self, camera, params, out=None):
         """rt3_render into a host frame (numpy uint32 [H, W])."""

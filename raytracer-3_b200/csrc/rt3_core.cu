@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <limits>
 #include <mutex>
 #include <string>
@@ -26,6 +27,7 @@
 
 #include "rt3_kernels.cuh"
 #include "rt3_scene.cuh"
+#include "rt3_upload.cuh"
 
 namespace {
 
@@ -116,6 +118,7 @@ struct rt3_ctx {
     bool accum_valid = false;
 
     rt3_stats stats{};
+    double upload_ms = 0.0, upload_h2d_ms = 0.0, upload_device_ms = 0.0; /* most recent scene upload */
 };
 
 namespace {
@@ -156,95 +159,6 @@ int make_kparams(const rt3_params* p, rt3_kparams* k) {
     return RT3_OK;
 }
 
-float round_down(double v) {
-    float f = (float) v;
-    if ((double) f > v) { f = std::nextafterf(f, -std::numeric_limits<float>::infinity()); }
-    return f;
-}
-float round_up(double v) {
-    float f = (float) v;
-    if ((double) f < v) { f = std::nextafterf(f, std::numeric_limits<float>::infinity()); }
-    return f;
-}
-
-/* Bounding sphere of a primitive as the prefilter sees it: centre (double) and R^2 with the
- * per-primitive slack folded in, R^2 = r^2 + RT3_FILTER_SLACK (|c|^2 + r^2); negative R^2 marks
- * a primitive that can never be hit (non-finite data). */
-struct Bound { double c[3]; double R2; };
-
-Bound make_bound(const double c[3], double r) {
-    Bound b = { { 0.0, 0.0, 0.0 }, -1.0 };
-    if (!(std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]) && std::isfinite(r))) { return b; }
-    const double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
-    const double R2 = (r * r + (double) RT3_FILTER_SLACK * (cc + r * r)) * (1.0 + 1e-6) + 1e-30;
-    if (!std::isfinite(R2) || R2 > 1e37) { return b; }
-    b.c[0] = c[0]; b.c[1] = c[1]; b.c[2] = c[2]; b.R2 = R2;
-    return b;
-}
-
-/* Jacobi eigen-decomposition of a symmetric 3x3 matrix; eigenvectors in the columns of v. */
-void jacobi3(double a[3][3], double v[3][3], double w[3]) {
-    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) { v[i][j] = i == j ? 1.0 : 0.0; } }
-    for (int sweep = 0; sweep < 32; sweep++) {
-        double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
-        if (off < 1e-300) { break; }
-        for (int p = 0; p < 2; p++) {
-            for (int q = p + 1; q < 3; q++) {
-                if (std::fabs(a[p][q]) < 1e-300) { continue; }
-                double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
-                double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-                double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < 3; k++) { double akp = a[k][p], akq = a[k][q]; a[k][p] = c * akp - s * akq; a[k][q] = s * akp + c * akq; }
-                for (int k = 0; k < 3; k++) { double apk = a[p][k], aqk = a[q][k]; a[p][k] = c * apk - s * aqk; a[q][k] = s * apk + c * aqk; }
-                for (int k = 0; k < 3; k++) { double vkp = v[k][p], vkq = v[k][q]; v[k][p] = c * vkp - s * vkq; v[k][q] = s * vkp + c * vkq; }
-            }
-        }
-    }
-    for (int i = 0; i < 3; i++) { w[i] = a[i][i]; }
-}
-
-/* Scene basis for the slab prefilter: e3 = the direction along which the primitive centres spread
- * least (PCA), e1 = the direction of largest spread, e2 = e3 x e1; rounded to float. Primitives far
- * larger than the typical one (a ground sphere of radius 1000) survive every slab anyway and would
- * only skew the statistics, so they are left out. */
-void scene_basis(const std::vector<Bound>& b, float e[3][3]) {
-    const float dflt[3][3] = { { 1.f, 0.f, 0.f }, { 0.f, 0.f, -1.f }, { 0.f, 1.f, 0.f } }; /* e3 = y */
-    memcpy(e, dflt, sizeof dflt);
-    std::vector<double> r2;
-    for (const Bound& x : b) { if (x.R2 >= 0) { r2.push_back(x.R2); } }
-    if (r2.size() < 2) { return; }
-    std::nth_element(r2.begin(), r2.begin() + r2.size() / 2, r2.end());
-    const double cap = 100.0 * r2[r2.size() / 2];
-    double mean[3] = { 0, 0, 0 };
-    size_t cnt = 0;
-    for (const Bound& x : b) { if (x.R2 >= 0 && x.R2 <= cap) { for (int k = 0; k < 3; k++) { mean[k] += x.c[k]; } cnt++; } }
-    if (cnt < 2) { return; }
-    for (int k = 0; k < 3; k++) { mean[k] /= (double) cnt; }
-    double cov[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
-    for (const Bound& x : b) {
-        if (!(x.R2 >= 0 && x.R2 <= cap)) { continue; }
-        double d[3] = { x.c[0] - mean[0], x.c[1] - mean[1], x.c[2] - mean[2] };
-        for (int p = 0; p < 3; p++) { for (int q = 0; q < 3; q++) { cov[p][q] += d[p] * d[q]; } }
-    }
-    double vec[3][3], val[3];
-    jacobi3(cov, vec, val);
-    if (!(std::isfinite(val[0]) && std::isfinite(val[1]) && std::isfinite(val[2]))) { return; }
-    int lo = 0, hi = 0;
-    for (int k = 1; k < 3; k++) { if (val[k] < val[lo]) { lo = k; } if (val[k] > val[hi]) { hi = k; } }
-    if (lo == hi) { return; }
-    double a3[3], a1[3], la = 0, lb = 0;
-    for (int k = 0; k < 3; k++) { a3[k] = vec[k][lo]; a1[k] = vec[k][hi]; la += a3[k] * a3[k]; lb += a1[k] * a1[k]; }
-    if (!(la > 0.5 && lb > 0.5)) { return; }
-    for (int k = 0; k < 3; k++) { a3[k] /= std::sqrt(la); a1[k] /= std::sqrt(lb); }
-    /* re-orthogonalise e1 against e3 (eigenvectors of a symmetric matrix already are, up to rounding) */
-    double dp = a1[0] * a3[0] + a1[1] * a3[1] + a1[2] * a3[2], l1 = 0;
-    for (int k = 0; k < 3; k++) { a1[k] -= dp * a3[k]; l1 += a1[k] * a1[k]; }
-    if (!(l1 > 0.25)) { return; }
-    for (int k = 0; k < 3; k++) { a1[k] /= std::sqrt(l1); }
-    const double a2[3] = { a3[1] * a1[2] - a3[2] * a1[1], a3[2] * a1[0] - a3[0] * a1[2], a3[0] * a1[1] - a3[1] * a1[0] };
-    for (int k = 0; k < 3; k++) { e[0][k] = (float) a1[k]; e[1][k] = (float) a2[k]; e[2][k] = (float) a3[k]; }
-}
-
 /* Which scene owns the constant-bank records of each device (rt3_device.cuh c_pair_xy / c_pair_w).
  * One mutex per device, held from the claim until the kernel that reads the bank has been enqueued: a
  * later claim by another context then waits for that kernel (cudaDeviceSynchronize under the same
@@ -253,44 +167,6 @@ constexpr int RT3_MAX_DEVICES = 64;
 std::mutex g_const_mutex[RT3_MAX_DEVICES];
 uint64_t g_const_owner[RT3_MAX_DEVICES] = { 0 };
 std::atomic<uint64_t> g_next_scene_id{ 1 };
-
-/* Smallest sphere through/around a triangle (double precision). */
-void triangle_bound(const double a[3], const double b[3], const double c[3], double centre[3], double* radius) {
-    const double* v[3] = { a, b, c };
-    auto dist = [](const double* p, const double* q) {
-        return std::sqrt((p[0] - q[0]) * (p[0] - q[0]) + (p[1] - q[1]) * (p[1] - q[1]) + (p[2] - q[2]) * (p[2] - q[2]));
-    };
-    /* longest edge first: if the opposite vertex lies inside its diameter sphere, that sphere is minimal */
-    int e0 = 0;
-    double best = -1.0;
-    for (int e = 0; e < 3; e++) { double l = dist(v[e], v[(e + 1) % 3]); if (l > best) { best = l; e0 = e; } }
-    const double *p = v[e0], *q = v[(e0 + 1) % 3], *o = v[(e0 + 2) % 3];
-    double mid[3] = { 0.5 * (p[0] + q[0]), 0.5 * (p[1] + q[1]), 0.5 * (p[2] + q[2]) };
-    if (dist(mid, o) <= 0.5 * best) { memcpy(centre, mid, sizeof mid); *radius = 0.5 * best; return; }
-    /* acute: circumsphere */
-    double ab[3] = { b[0] - a[0], b[1] - a[1], b[2] - a[2] }, ac[3] = { c[0] - a[0], c[1] - a[1], c[2] - a[2] };
-    double n[3] = { ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0] };
-    double n2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
-    double ab2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2], ac2 = ac[0] * ac[0] + ac[1] * ac[1] + ac[2] * ac[2];
-    if (n2 > 0.0 && std::isfinite(n2)) {
-        /* centre = a + (|ac|^2 (n x ab) + |ab|^2 (ac x n)) / (2 |n|^2) */
-        double nxab[3] = { n[1] * ab[2] - n[2] * ab[1], n[2] * ab[0] - n[0] * ab[2], n[0] * ab[1] - n[1] * ab[0] };
-        double acxn[3] = { ac[1] * n[2] - ac[2] * n[1], ac[2] * n[0] - ac[0] * n[2], ac[0] * n[1] - ac[1] * n[0] };
-        for (int i = 0; i < 3; i++) { centre[i] = a[i] + (ac2 * nxab[i] + ab2 * acxn[i]) / (2.0 * n2); }
-    } else {
-        for (int i = 0; i < 3; i++) { centre[i] = (a[i] + b[i] + c[i]) / 3.0; }
-    }
-    double r = 0.0;
-    for (int i = 0; i < 3; i++) { double l = dist(centre, v[i]); if (l > r) { r = l; } }
-    *radius = r;
-}
-
-template <class T> int upload(DeviceBuffer<T>& buf, const std::vector<T>& host, cudaStream_t stream) {
-    int rc = buf.reserve(host.size() ? host.size() : 1);
-    if (rc != RT3_OK) { return rc; }
-    if (!host.empty()) { RT3_CUDA(cudaMemcpyAsync(buf.ptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, stream)); }
-    return RT3_OK;
-}
 
 size_t render_smem_bytes(const rt3_scene_view& v, bool path_slots, bool* resident) {
     *resident = v.n_prims_padded <= RT3_CONST_PRIMS;
@@ -308,7 +184,7 @@ int launch_reference(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
                      uint32_t* ent, float* t, cudaStream_t stream) {
     int rc = configure(reference_kernel<RESIDENT, SPHERES_ONLY, ACCEL>, smem, nullptr);
     if (rc != RT3_OK) { return rc; }
-    unsigned long long per_cta = (unsigned long long) RT3_CTA_THREADS * RT3_RAYS;
+    unsigned long long per_cta = (unsigned long long) RT3_CTA_THREADS * RT3_REF_RAYS;
     unsigned grid = (unsigned) ((kp.n_pixels + per_cta - 1) / per_cta);
     reference_kernel<RESIDENT, SPHERES_ONLY, ACCEL><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, ctx->bvh, cam, kp, frame, prim, ent, t, ctx->counters.ptr);
     RT3_CUDA(cudaGetLastError());
@@ -610,6 +486,136 @@ int collect_stats(rt3_ctx* ctx) {
     return RT3_OK;
 }
 
+int check_scene_args(const rt3_scene* s) {
+    if (s->n_faces && (!s->faces || !s->vertices)) { return fail(RT3_ERR_INVALID, "faces/vertices missing"); }
+    if (s->n_spheres && !s->spheres) { return fail(RT3_ERR_INVALID, "spheres missing"); }
+    if ((s->face_material || s->sphere_material) && s->n_materials && !s->materials) { return fail(RT3_ERR_INVALID, "materials missing"); }
+    if ((unsigned long long) s->n_faces + s->n_spheres > 0x7FFFFFFFull) { return fail(RT3_ERR_INVALID, "too many primitives"); }
+    return RT3_OK;
+}
+
+/* Copies one host input array into a scratch device buffer as it is and points *device_view at it (NULL stays NULL). */
+template <class T> int stage(DeviceBuffer<unsigned char>& buf, const T* host, size_t bytes, const T** device_view, cudaStream_t stream) {
+    if (!host || bytes == 0) { *device_view = nullptr; return RT3_OK; }
+    int rc = buf.reserve(bytes);
+    if (rc != RT3_OK) { return rc; }
+    RT3_CUDA(cudaMemcpyAsync(buf.ptr, host, bytes, cudaMemcpyHostToDevice, stream));
+    *device_view = reinterpret_cast<const T*>(buf.ptr);
+    return RT3_OK;
+}
+
+__global__ void build_init_kernel(rt3_build_info* info) {
+    info->error_key = ~0ull; info->n_valid = 0ull; info->ray_slack = 0.f; info->r2_median = 1.0; info->r2_min = 1.0;
+    for (int k = 0; k < 4; k++) { info->error_detail[k] = 0u; }
+    for (int k = 0; k < 3; k++) { info->cmin_bits[k] = 0x7fffffff; info->cmax_bits[k] = (int) 0x80000000; }
+}
+
+/* Every derived scene array from flattened inputs that lie in device memory (`d` holds device pointers): the
+ * kernels of rt3_upload.cuh on the context's stream, one small read-back (validation result, basis, slack,
+ * centroid box) at the end. Replaces any previous scene of the context. */
+int build_scene_on_device(rt3_ctx* ctx, const rt3_scene& d) {
+    cudaStream_t stream = ctx->stream;
+    ctx->has_scene = false;
+    ctx->accum_valid = false; /* the accumulators belong to the previous scene */
+    ctx->accum_width = ctx->accum_height = 0;
+    ctx->bvh_ready = false;
+    const uint32_t nf = d.n_faces, ns = d.n_spheres, np = nf + ns;
+    const uint32_t np_pad = (np + RT3_PAD_PRIMS - 1) / RT3_PAD_PRIMS * RT3_PAD_PRIMS;
+    int rc;
+    auto at_least_one = [](size_t n) { return n ? n : (size_t) 1; };
+    if ((rc = ctx->face_n.reserve(at_least_one(nf))) != RT3_OK || (rc = ctx->face_p1.reserve(at_least_one(nf))) != RT3_OK ||
+        (rc = ctx->face_p2.reserve(at_least_one(nf))) != RT3_OK || (rc = ctx->face_p3.reserve(at_least_one(nf))) != RT3_OK ||
+        (rc = ctx->spheres.reserve(at_least_one(ns))) != RT3_OK || (rc = ctx->prim_color.reserve(at_least_one(np))) != RT3_OK ||
+        (rc = ctx->prim_material.reserve(at_least_one(np))) != RT3_OK || (rc = ctx->prim_entity.reserve(at_least_one(np))) != RT3_OK ||
+        (rc = ctx->prim_lo.reserve(at_least_one(np))) != RT3_OK || (rc = ctx->prim_hi.reserve(at_least_one(np))) != RT3_OK ||
+        (rc = ctx->filt3.reserve(at_least_one(np_pad))) != RT3_OK || (rc = ctx->pair_xy.reserve(at_least_one(np_pad / 2))) != RT3_OK ||
+        (rc = ctx->pair_w.reserve(at_least_one(np_pad / 2))) != RT3_OK || (rc = ctx->materials.reserve(at_least_one((size_t) d.n_materials * 2))) != RT3_OK) {
+        return rc;
+    }
+    DeviceBuffer<rt3_bound> bounds;
+    DeviceBuffer<float> keys_in, keys_out;
+    DeviceBuffer<double> partials;
+    DeviceBuffer<rt3_build_info> info;
+    DeviceBuffer<unsigned char> temp;
+    if ((rc = bounds.reserve(at_least_one(np))) != RT3_OK || (rc = keys_in.reserve(at_least_one(np))) != RT3_OK || (rc = keys_out.reserve(at_least_one(np))) != RT3_OK ||
+        (rc = partials.reserve(RT3_MOMENT_BLOCKS * RT3_MOMENTS)) != RT3_OK || (rc = info.reserve(1)) != RT3_OK) {
+        return rc;
+    }
+    size_t temp_bytes = 0;
+    if (np) { RT3_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, keys_in.ptr, keys_out.ptr, (int) np, 0, 32, stream)); }
+    if ((rc = temp.reserve(at_least_one(temp_bytes))) != RT3_OK) { return rc; }
+    EventPair ev;
+    if ((rc = ev.create()) != RT3_OK) { return rc; }
+    RT3_CUDA(cudaEventRecord(ev.begin, stream));
+    build_init_kernel<<<1, 1, 0, stream>>>(info.ptr);
+    RT3_CUDA(cudaGetLastError());
+    rt3_build_out out;
+    out.face_n = ctx->face_n.ptr; out.face_p1 = ctx->face_p1.ptr; out.face_p2 = ctx->face_p2.ptr; out.face_p3 = ctx->face_p3.ptr;
+    out.spheres = ctx->spheres.ptr; out.prim_color = ctx->prim_color.ptr; out.prim_lo = ctx->prim_lo.ptr; out.prim_hi = ctx->prim_hi.ptr;
+    out.prim_material = ctx->prim_material.ptr; out.prim_entity = ctx->prim_entity.ptr; out.bounds = bounds.ptr; out.r2_keys = keys_in.ptr;
+    if (nf) {
+        build_faces_kernel<<<(nf + 255u) / 256u, 256, 0, stream>>>(nf, d.n_vertices, reinterpret_cast<const uint4*>(d.faces), reinterpret_cast<const float4*>(d.vertices),
+                                                                     d.face_material, d.face_entity, d.n_materials, out, info.ptr);
+        RT3_CUDA(cudaGetLastError());
+    }
+    if (ns) {
+        build_spheres_kernel<<<(ns + 255u) / 256u, 256, 0, stream>>>(nf, ns, reinterpret_cast<const float4*>(d.spheres), d.sphere_color, d.sphere_material,
+                                                                       d.sphere_entity, d.n_materials, out, info.ptr);
+        RT3_CUDA(cudaGetLastError());
+    }
+    if (d.n_materials && d.materials) {
+        build_materials_kernel<<<(d.n_materials + 255u) / 256u, 256, 0, stream>>>(d.n_materials, reinterpret_cast<const uint4*>(d.materials), ctx->materials.ptr, info.ptr);
+        RT3_CUDA(cudaGetLastError());
+    }
+    if (np) {
+        size_t tb = temp_bytes;
+        RT3_CUDA(cub::DeviceRadixSort::SortKeys(temp.ptr, tb, keys_in.ptr, keys_out.ptr, (int) np, 0, 32, stream));
+    }
+    build_radius_stats_kernel<<<1, 1, 0, stream>>>(keys_out.ptr, info.ptr);
+    RT3_CUDA(cudaGetLastError());
+    build_moments_kernel<<<RT3_MOMENT_BLOCKS, RT3_MOMENT_THREADS, 0, stream>>>(np, bounds.ptr, info.ptr, partials.ptr);
+    RT3_CUDA(cudaGetLastError());
+    build_basis_kernel<<<1, 1, 0, stream>>>(partials.ptr, info.ptr);
+    RT3_CUDA(cudaGetLastError());
+    if (np_pad) {
+        build_records_kernel<<<(np_pad / 2 + 255u) / 256u, 256, 0, stream>>>(np, np_pad / 2, bounds.ptr, ctx->prim_lo.ptr, ctx->prim_hi.ptr, ctx->filt3.ptr,
+                                                                              ctx->pair_xy.ptr, ctx->pair_w.ptr, info.ptr);
+        RT3_CUDA(cudaGetLastError());
+    }
+    RT3_CUDA(cudaEventRecord(ev.end, stream));
+    rt3_build_info h;
+    RT3_CUDA(cudaMemcpyAsync(&h, info.ptr, sizeof h, cudaMemcpyDeviceToHost, stream));
+    RT3_CUDA(cudaStreamSynchronize(stream)); /* also: the scratch arrays (and the caller's staging buffers) go out of scope */
+    float ms = 0.f;
+    RT3_CUDA(cudaEventElapsedTime(&ms, ev.begin, ev.end));
+    ctx->upload_device_ms = ms;
+    if (h.error_key != ~0ull) {
+        const unsigned stage_id = (unsigned) (h.error_key >> 62), kind = (unsigned) (h.error_key & 3ull);
+        const uint32_t index = (uint32_t) ((h.error_key >> 2) & 0xFFFFFFFFull);
+        if (kind == RT3_BUILD_ERR_VERTEX) {
+            return fail(RT3_ERR_INVALID, "face %u references vertex out of range (%u,%u,%u of %u)", index, h.error_detail[0], h.error_detail[1], h.error_detail[2], h.error_detail[3]);
+        }
+        if (kind == RT3_BUILD_ERR_MATERIAL) { return fail(RT3_ERR_INVALID, "%s %u: material %u out of range", stage_id == 0 ? "face" : "sphere", index, h.error_detail[0]); }
+        return fail(RT3_ERR_INVALID, "material %u: unknown kind %u", index, h.error_detail[0]);
+    }
+    for (int k = 0; k < 3; k++) {
+        float lo = ordered_to_float(h.cmin_bits[k]), hi = ordered_to_float(h.cmax_bits[k]);
+        if (!(lo <= hi)) { lo = hi = 0.0f; }
+        ctx->centroid_min[k] = lo; ctx->centroid_max[k] = hi;
+    }
+    rt3_scene_view& v = ctx->view;
+    for (int k = 0; k < 3; k++) { v.e1[k] = h.basis[0][k]; v.e2[k] = h.basis[1][k]; v.e3[k] = h.basis[2][k]; }
+    v.ray_slack = h.ray_slack;
+    ctx->scene_id = g_next_scene_id.fetch_add(1);
+    v.n_faces = nf; v.n_spheres = ns; v.n_prims = np; v.n_prims_padded = np_pad;
+    v.pair_xy = ctx->pair_xy.ptr; v.pair_w = ctx->pair_w.ptr; v.filt3 = ctx->filt3.ptr;
+    v.face_n = ctx->face_n.ptr; v.face_p1 = ctx->face_p1.ptr; v.face_p2 = ctx->face_p2.ptr; v.face_p3 = ctx->face_p3.ptr;
+    v.spheres = ctx->spheres.ptr; v.prim_color = ctx->prim_color.ptr;
+    v.prim_material = ctx->prim_material.ptr; v.prim_entity = ctx->prim_entity.ptr; v.materials = ctx->materials.ptr;
+    ctx->has_scene = true;
+    return RT3_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -668,169 +674,84 @@ int rt3_destroy(rt3_ctx* ctx) {
 
 int rt3_scene_upload(rt3_ctx* ctx, const rt3_scene* s) {
     if (!ctx || !s) { return fail(RT3_ERR_INVALID, "ctx or scene is NULL"); }
-    if (s->n_faces && (!s->faces || !s->vertices)) { return fail(RT3_ERR_INVALID, "faces/vertices missing"); }
-    if (s->n_spheres && !s->spheres) { return fail(RT3_ERR_INVALID, "spheres missing"); }
-    if ((s->face_material || s->sphere_material) && s->n_materials && !s->materials) { return fail(RT3_ERR_INVALID, "materials missing"); }
-    if ((unsigned long long) s->n_faces + s->n_spheres > 0x7FFFFFFFull) { return fail(RT3_ERR_INVALID, "too many primitives"); }
+    int rc = check_scene_args(s);
+    if (rc != RT3_OK) { return rc; }
     RT3_CUDA(cudaSetDevice(ctx->device));
-    ctx->has_scene = false;
-    ctx->accum_valid = false; /* the accumulators belong to the previous scene */
-    ctx->accum_width = ctx->accum_height = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    /* stage the flattened arrays as they are (one copy per array, nothing per primitive on the host); every derived
+     * array is then built by kernels (rt3_upload.cuh) */
+    DeviceBuffer<unsigned char> faces, vertices, face_material, face_entity, spheres, sphere_color, sphere_material, sphere_entity, materials;
+    rt3_scene d = *s;
+    EventPair ev;
+    if ((rc = ev.create()) != RT3_OK) { return rc; }
+    RT3_CUDA(cudaEventRecord(ev.begin, ctx->stream));
+    if ((rc = stage(faces, s->faces, (size_t) s->n_faces * sizeof(rt3_face), &d.faces, ctx->stream)) != RT3_OK ||
+        (rc = stage(vertices, s->vertices, (size_t) s->n_vertices * sizeof(rt3_vertex), &d.vertices, ctx->stream)) != RT3_OK ||
+        (rc = stage(face_material, s->face_material, (size_t) s->n_faces * 4, &d.face_material, ctx->stream)) != RT3_OK ||
+        (rc = stage(face_entity, s->face_entity, (size_t) s->n_faces * 4, &d.face_entity, ctx->stream)) != RT3_OK ||
+        (rc = stage(spheres, s->spheres, (size_t) s->n_spheres * sizeof(rt3_sphere), &d.spheres, ctx->stream)) != RT3_OK ||
+        (rc = stage(sphere_color, s->sphere_color, (size_t) s->n_spheres * 12, &d.sphere_color, ctx->stream)) != RT3_OK ||
+        (rc = stage(sphere_material, s->sphere_material, (size_t) s->n_spheres * 4, &d.sphere_material, ctx->stream)) != RT3_OK ||
+        (rc = stage(sphere_entity, s->sphere_entity, (size_t) s->n_spheres * 4, &d.sphere_entity, ctx->stream)) != RT3_OK ||
+        (rc = stage(materials, s->materials, (size_t) s->n_materials * sizeof(rt3_material), &d.materials, ctx->stream)) != RT3_OK) {
+        return rc;
+    }
+    RT3_CUDA(cudaEventRecord(ev.end, ctx->stream));
+    rc = build_scene_on_device(ctx, d);
+    if (rc != RT3_OK) { return rc; }
+    float h2d = 0.f;
+    RT3_CUDA(cudaEventElapsedTime(&h2d, ev.begin, ev.end));
+    ctx->upload_h2d_ms = h2d;
+    ctx->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return RT3_OK;
+}
 
-    const uint32_t nf = s->n_faces, ns = s->n_spheres, np = nf + ns;
-    const uint32_t np_pad = (np + RT3_PAD_PRIMS - 1) / RT3_PAD_PRIMS * RT3_PAD_PRIMS;
-    std::vector<Bound> bounds(np);
-    std::vector<float4> box_lo(np ? np : 1), box_hi(np ? np : 1); /* hierarchy leaves: the primitive's box, widened like its bounding sphere */
-    const float finf = std::numeric_limits<float>::infinity(), fnan = std::numeric_limits<float>::quiet_NaN();
-    std::vector<float4> fn(nf), p1(nf), p2(nf), p3(nf), sph(ns), color(np), mats((size_t) s->n_materials * 2);
-    std::vector<uint32_t> pmat(np, RT3_NO_HIT), pent(np, 0u);
+int rt3_scene_upload_device(rt3_ctx* ctx, const rt3_scene* s) {
+    if (!ctx || !s) { return fail(RT3_ERR_INVALID, "ctx or scene is NULL"); }
+    int rc = check_scene_args(s);
+    if (rc != RT3_OK) { return rc; }
+    if ((((uintptr_t) s->faces) | ((uintptr_t) s->vertices) | ((uintptr_t) s->spheres) | ((uintptr_t) s->materials)) & 15u) {
+        return fail(RT3_ERR_INVALID, "device arrays of faces, vertices, spheres and materials must be 16-byte aligned");
+    }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    rc = build_scene_on_device(ctx, *s);
+    if (rc != RT3_OK) { return rc; }
+    ctx->upload_h2d_ms = 0.0;
+    ctx->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return RT3_OK;
+}
 
-    for (uint32_t i = 0; i < nf; i++) {
-        const rt3_face& f = s->faces[i];
-        if (f.v1 >= s->n_vertices || f.v2 >= s->n_vertices || f.v3 >= s->n_vertices) {
-            return fail(RT3_ERR_INVALID, "face %u references vertex out of range (%u,%u,%u of %u)", i, f.v1, f.v2, f.v3, s->n_vertices);
-        }
-        const rt3_vertex &a = s->vertices[f.v1], &b = s->vertices[f.v2], &c = s->vertices[f.v3];
-        /* plane offset dot3(n, p1) in the reference's order (SequentialRenderer.cpp:32-33,67); volatile keeps
-         * the host compiler from contracting it */
-        volatile float m0 = f.normal[0] * a.x, m1 = f.normal[1] * a.y, m2 = f.normal[2] * a.z;
-        volatile float s01 = m0 + m1;
-        float pd = s01 + m2;
-        fn[i] = make_float4(f.normal[0], f.normal[1], f.normal[2], pd);
-        p1[i] = make_float4(a.x, a.y, a.z, 0.f);
-        p2[i] = make_float4(b.x, b.y, b.z, 0.f);
-        p3[i] = make_float4(c.x, c.y, c.z, 0.f);
-        double da[3] = { a.x, a.y, a.z }, db[3] = { b.x, b.y, b.z }, dc[3] = { c.x, c.y, c.z }, centre[3], radius;
-        triangle_bound(da, db, dc, centre, &radius);
-        const double r_geom = radius;
-        /* faces: the exact test accepts hit points up to a few ulps of the coordinates outside the triangle;
-         * widen the bounding sphere by 2^-10 relative and 2^-16 (|c| + r) absolute on top of the common slack */
-        radius = radius * (1.0 + 1.0 / 1024.0) + (std::sqrt(centre[0] * centre[0] + centre[1] * centre[1] + centre[2] * centre[2]) + radius) / 65536.0;
-        bounds[i] = make_bound(centre, radius);
-        if (bounds[i].R2 >= 0) {
-            /* around the triangle's own box: the geometric widening of its bounding sphere, without the slack term of
-             * the sphere discriminant (rt3_bvh.cuh) */
-            const double m = radius - r_geom;
-            box_lo[i] = make_float4(round_down(std::min({ da[0], db[0], dc[0] }) - m), round_down(std::min({ da[1], db[1], dc[1] }) - m),
-                                    round_down(std::min({ da[2], db[2], dc[2] }) - m), 0.f);
-            box_hi[i] = make_float4(round_up(std::max({ da[0], db[0], dc[0] }) + m), round_up(std::max({ da[1], db[1], dc[1] }) + m),
-                                    round_up(std::max({ da[2], db[2], dc[2] }) + m), 0.f);
-        } else {
-            box_lo[i] = make_float4(fnan, fnan, fnan, 0.f); box_hi[i] = make_float4(fnan, fnan, fnan, 0.f); /* never entered (every comparison of the slab test fails), ignored by fminf / fmaxf unions */
-        }
-        color[i] = make_float4(f.color[0], f.color[1], f.color[2], 0.f);
-        if (s->face_material) {
-            if (s->face_material[i] >= s->n_materials) { return fail(RT3_ERR_INVALID, "face %u: material %u out of range", i, s->face_material[i]); }
-            pmat[i] = s->face_material[i];
-        }
-        if (s->face_entity) { pent[i] = s->face_entity[i]; }
-    }
-    for (uint32_t i = 0; i < ns; i++) {
-        const rt3_sphere& sp = s->spheres[i];
-        sph[i] = make_float4(sp.cx, sp.cy, sp.cz, sp.r);
-        double c[3] = { sp.cx, sp.cy, sp.cz };
-        bounds[nf + i] = make_bound(c, std::fabs((double) sp.r));
-        if (bounds[nf + i].R2 >= 0) {
-            const double R = std::sqrt(bounds[nf + i].R2);
-            box_lo[nf + i] = make_float4(round_down(c[0] - R), round_down(c[1] - R), round_down(c[2] - R), 0.f);
-            box_hi[nf + i] = make_float4(round_up(c[0] + R), round_up(c[1] + R), round_up(c[2] + R), 0.f);
-        } else {
-            box_lo[nf + i] = make_float4(fnan, fnan, fnan, 0.f); box_hi[nf + i] = make_float4(fnan, fnan, fnan, 0.f);
-        }
-        if (s->sphere_color) { color[nf + i] = make_float4(s->sphere_color[3 * i], s->sphere_color[3 * i + 1], s->sphere_color[3 * i + 2], 0.f); }
-        else { color[nf + i] = make_float4(1.f, 1.f, 1.f, 0.f); }
-        if (s->sphere_material) {
-            if (s->sphere_material[i] >= s->n_materials) { return fail(RT3_ERR_INVALID, "sphere %u: material %u out of range", i, s->sphere_material[i]); }
-            pmat[nf + i] = s->sphere_material[i];
-        }
-        if (s->sphere_entity) { pent[nf + i] = s->sphere_entity[i]; }
-    }
-    for (uint32_t i = 0; i < s->n_materials; i++) {
-        const rt3_material& m = s->materials[i];
-        if (m.kind > RT3_MAT_DIELECTRIC) { return fail(RT3_ERR_INVALID, "material %u: unknown kind %u", i, m.kind); }
-        float kind_bits;
-        memcpy(&kind_bits, &m.kind, sizeof kind_bits);
-        mats[2 * i] = make_float4(kind_bits, m.albedo[0], m.albedo[1], m.albedo[2]);
-        mats[2 * i + 1] = make_float4(m.fuzz, m.ior, 0.f, 0.f);
-    }
+int rt3_buffer_alloc(rt3_ctx* ctx, uint64_t bytes, void** device_ptr) {
+    if (!ctx || !device_ptr) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    *device_ptr = nullptr;
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    RT3_CUDA(cudaMalloc(device_ptr, bytes ? (size_t) bytes : 1));
+    return RT3_OK;
+}
 
-    /* prefilter records in the scene basis */
-    float basis[3][3];
-    scene_basis(bounds, basis);
-    double r2min = 1.0;
-    {
-        /* smallest R^2 in the scene, floored at 1/400 of the median so that one sliver cannot widen every slab;
-         * records below the floor are raised to it (admits more, never less) */
-        std::vector<double> r2;
-        for (const Bound& b : bounds) { if (b.R2 >= 0) { r2.push_back(b.R2); } }
-        if (!r2.empty()) {
-            std::nth_element(r2.begin(), r2.begin() + r2.size() / 2, r2.end());
-            const double median = r2[r2.size() / 2], lowest = *std::min_element(r2.begin(), r2.end());
-            r2min = std::max(lowest, median / 400.0);
-            if (!(r2min > 0.0)) { r2min = 1e-30; }
-        }
-    }
-    const float ray_slack = (float) ((double) RT3_FILTER_SLACK / r2min * (1.0 + 1e-6));
-    const float inf = std::numeric_limits<float>::infinity();
-    std::vector<float4> filt3(np_pad, make_float4(0.f, 0.f, 0.f, inf)); /* never survives: a^2 + inf > 0 */
-    for (uint32_t i = 0; i < np; i++) {
-        const Bound& b = bounds[i];
-        if (b.R2 < 0) { continue; }
-        float p[3];
-        for (int k = 0; k < 3; k++) { p[k] = (float) (b.c[0] * (double) basis[k][0] + b.c[1] * (double) basis[k][1] + b.c[2] * (double) basis[k][2]); }
-        const float w = round_down(-std::max(b.R2, r2min));
-        if (!std::isfinite(w) || !std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) { continue; }
-        filt3[i] = make_float4(p[0], p[1], p[2], w);
-    }
-    std::vector<float4> pair_xy(np_pad / 2);
-    std::vector<float2> pair_w(np_pad / 2);
-    for (uint32_t j = 0; j < np_pad / 2; j++) {
-        const float4 &a = filt3[2 * j], &b = filt3[2 * j + 1];
-        pair_xy[j] = make_float4(a.x, b.x, a.y, b.y);
-        pair_w[j] = make_float2(a.w, b.w);
-    }
+int rt3_buffer_free(rt3_ctx* ctx, void* device_ptr) {
+    if (!ctx) { return fail(RT3_ERR_INVALID, "ctx is NULL"); }
+    if (!device_ptr) { return RT3_OK; }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    RT3_CUDA(cudaStreamSynchronize(ctx->stream)); /* scene builds read these buffers on the context's stream */
+    RT3_CUDA(cudaFree(device_ptr));
+    return RT3_OK;
+}
 
-    int rc;
-    {
-        /* box of the finite box centres: the Morton grid of the hierarchy build */
-        float cmin[3] = { finf, finf, finf }, cmax[3] = { -finf, -finf, -finf };
-        for (uint32_t i = 0; i < np; i++) {
-            if (!(box_lo[i].x <= box_hi[i].x)) { continue; }
-            const float cx[3] = { 0.5f * box_lo[i].x + 0.5f * box_hi[i].x, 0.5f * box_lo[i].y + 0.5f * box_hi[i].y, 0.5f * box_lo[i].z + 0.5f * box_hi[i].z };
-            for (int k = 0; k < 3; k++) { if (std::isfinite(cx[k])) { cmin[k] = std::min(cmin[k], cx[k]); cmax[k] = std::max(cmax[k], cx[k]); } }
-        }
-        for (int k = 0; k < 3; k++) {
-            if (!(cmin[k] <= cmax[k])) { cmin[k] = cmax[k] = 0.0f; }
-            ctx->centroid_min[k] = cmin[k]; ctx->centroid_max[k] = cmax[k];
-        }
-    }
-    ctx->bvh_ready = false;
-    if ((rc = upload(ctx->prim_lo, box_lo, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->prim_hi, box_hi, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->pair_xy, pair_xy, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->pair_w, pair_w, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->filt3, filt3, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->face_n, fn, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->face_p1, p1, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->face_p2, p2, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->face_p3, p3, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->spheres, sph, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->prim_color, color, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->materials, mats, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->prim_material, pmat, ctx->stream)) != RT3_OK) { return rc; }
-    if ((rc = upload(ctx->prim_entity, pent, ctx->stream)) != RT3_OK) { return rc; }
-    RT3_CUDA(cudaStreamSynchronize(ctx->stream)); /* host vectors go out of scope */
+int rt3_buffer_write(rt3_ctx* ctx, void* device_dst, const void* host_src, uint64_t bytes) {
+    if (!ctx || (bytes && (!device_dst || !host_src))) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    if (bytes) { RT3_CUDA(cudaMemcpyAsync(device_dst, host_src, (size_t) bytes, cudaMemcpyHostToDevice, ctx->stream)); }
+    RT3_CUDA(cudaStreamSynchronize(ctx->stream)); /* the caller may reuse host_src */
+    return RT3_OK;
+}
 
-    rt3_scene_view& v = ctx->view;
-    for (int k = 0; k < 3; k++) { v.e1[k] = basis[0][k]; v.e2[k] = basis[1][k]; v.e3[k] = basis[2][k]; }
-    v.ray_slack = ray_slack;
-    ctx->scene_id = g_next_scene_id.fetch_add(1);
-    v.n_faces = nf; v.n_spheres = ns; v.n_prims = np; v.n_prims_padded = np_pad;
-    v.pair_xy = ctx->pair_xy.ptr; v.pair_w = ctx->pair_w.ptr; v.filt3 = ctx->filt3.ptr;
-    v.face_n = ctx->face_n.ptr; v.face_p1 = ctx->face_p1.ptr; v.face_p2 = ctx->face_p2.ptr; v.face_p3 = ctx->face_p3.ptr;
-    v.spheres = ctx->spheres.ptr; v.prim_color = ctx->prim_color.ptr;
-    v.prim_material = ctx->prim_material.ptr; v.prim_entity = ctx->prim_entity.ptr; v.materials = ctx->materials.ptr;
-    ctx->has_scene = true;
+int rt3_buffer_read(rt3_ctx* ctx, void* host_dst, const void* device_src, uint64_t bytes) {
+    if (!ctx || (bytes && (!host_dst || !device_src))) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    if (bytes) { RT3_CUDA(cudaMemcpyAsync(host_dst, device_src, (size_t) bytes, cudaMemcpyDeviceToHost, ctx->stream)); }
+    RT3_CUDA(cudaStreamSynchronize(ctx->stream));
     return RT3_OK;
 }
 
@@ -967,44 +888,71 @@ int rt3_frame_read(rt3_ctx* ctx, const uint32_t* device_frame, uint32_t* host_fr
 uint32_t rt3_uv_sphere_faces(uint32_t n_meridians, uint32_t n_parallels) { return n_parallels >= 3 ? uv_sphere_faces(n_meridians, n_parallels) : 0u; }
 uint32_t rt3_uv_sphere_vertices(uint32_t n_meridians, uint32_t n_parallels) { return n_parallels >= 3 ? uv_sphere_vertices(n_meridians, n_parallels) : 0u; }
 
+/* Counts and checks a batch of UV spheres. */
+static int uv_batch_size(const rt3_uv_sphere* spheres, uint32_t n, unsigned long long* n_faces, unsigned long long* n_vertices) {
+    *n_faces = 0; *n_vertices = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (spheres[i].n_parallels < 3 || spheres[i].n_meridians < 1) {
+            return fail(RT3_ERR_INVALID, "sphere %u: needs n_parallels >= 3 and n_meridians >= 1 (got %u, %u)", i, spheres[i].n_parallels, spheres[i].n_meridians);
+        }
+        *n_faces += uv_sphere_faces(spheres[i].n_meridians, spheres[i].n_parallels);
+        *n_vertices += uv_sphere_vertices(spheres[i].n_meridians, spheres[i].n_parallels);
+    }
+    return RT3_OK;
+}
+
+/* Sphere k's vertices go to d_vertices[vertex_slot + ...] and its faces to d_faces[face_slot + ...]; a face refers to
+ * vertex j of its sphere as index_shift + (the vertex's position in d_vertices). Asynchronous on the context's stream. */
+static int tessellate_on_device(rt3_ctx* ctx, const rt3_uv_sphere* spheres, uint32_t n, uint32_t vertex_slot, uint32_t face_slot, uint32_t index_shift,
+                                uint4* d_faces, float4* d_vertices, uint32_t* d_entity) {
+    uint32_t v0 = vertex_slot, f0 = face_slot;
+    for (uint32_t i = 0; i < n; i++) {
+        const rt3_uv_sphere& s = spheres[i];
+        rt3_uv_sphere_dev d = { s.center[0], s.center[1], s.center[2], s.radius, s.n_meridians, s.n_parallels, s.color[0], s.color[1], s.color[2],
+                                v0, f0, s.entity, index_shift };
+        const uint32_t nv = uv_sphere_vertices(d.m, d.p), nf = uv_sphere_faces(d.m, d.p);
+        uv_sphere_vertices_kernel<<<(nv + 255u) / 256u, 256, 0, ctx->stream>>>(d, d_vertices);
+        RT3_CUDA(cudaGetLastError());
+        uv_sphere_faces_kernel<<<(nf + 255u) / 256u, 256, 0, ctx->stream>>>(d, d_vertices, d_faces, d_entity);
+        RT3_CUDA(cudaGetLastError());
+        v0 += nv; f0 += nf;
+    }
+    return RT3_OK;
+}
+
 int rt3_tessellate_spheres(rt3_ctx* ctx, const rt3_uv_sphere* spheres, uint32_t n, uint32_t first_vertex, rt3_face* host_faces,
                            rt3_vertex* host_vertices, uint32_t* host_face_entity) {
     if (!ctx || (n && (!spheres || !host_faces || !host_vertices))) { return fail(RT3_ERR_INVALID, "NULL argument"); }
     static_assert(sizeof(rt3_face) == 48 && sizeof(rt3_vertex) == 16, "flattened records must match the reference's GFace / glm::vec4");
     RT3_CUDA(cudaSetDevice(ctx->device));
     unsigned long long n_faces = 0, n_vertices = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        if (spheres[i].n_parallels < 3 || spheres[i].n_meridians < 1) {
-            return fail(RT3_ERR_INVALID, "sphere %u: needs n_parallels >= 3 and n_meridians >= 1 (got %u, %u)", i, spheres[i].n_parallels, spheres[i].n_meridians);
-        }
-        n_faces += uv_sphere_faces(spheres[i].n_meridians, spheres[i].n_parallels);
-        n_vertices += uv_sphere_vertices(spheres[i].n_meridians, spheres[i].n_parallels);
-    }
+    int rc = uv_batch_size(spheres, n, &n_faces, &n_vertices);
+    if (rc != RT3_OK) { return rc; }
     if (n_faces > 0x7FFFFFFFull || n_vertices + first_vertex > 0xFFFFFFFFull) { return fail(RT3_ERR_INVALID, "too many faces or vertices"); }
     if (n_faces == 0) { return RT3_OK; }
     DeviceBuffer<float4> d_vertices;
     DeviceBuffer<uint4> d_faces;
     DeviceBuffer<uint32_t> d_entity;
-    int rc;
     if ((rc = d_vertices.reserve(n_vertices)) != RT3_OK || (rc = d_faces.reserve(3 * n_faces)) != RT3_OK || (rc = d_entity.reserve(n_faces)) != RT3_OK) { return rc; }
-    uint32_t v0 = 0, f0 = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        const rt3_uv_sphere& s = spheres[i];
-        rt3_uv_sphere_dev d = { s.center[0], s.center[1], s.center[2], s.radius, s.n_meridians, s.n_parallels, s.color[0], s.color[1], s.color[2],
-                                v0, f0, s.entity };
-        const uint32_t nv = uv_sphere_vertices(d.m, d.p), nf = uv_sphere_faces(d.m, d.p);
-        uv_sphere_vertices_kernel<<<(nv + 255u) / 256u, 256, 0, ctx->stream>>>(d, d_vertices.ptr);
-        RT3_CUDA(cudaGetLastError());
-        uv_sphere_faces_kernel<<<(nf + 255u) / 256u, 256, 0, ctx->stream>>>(d, d_vertices.ptr, d_faces.ptr, d_entity.ptr);
-        RT3_CUDA(cudaGetLastError());
-        v0 += nv; f0 += nf;
-    }
+    if ((rc = tessellate_on_device(ctx, spheres, n, 0u, 0u, first_vertex, d_faces.ptr, d_vertices.ptr, d_entity.ptr)) != RT3_OK) { return rc; }
     RT3_CUDA(cudaMemcpyAsync(host_vertices, d_vertices.ptr, n_vertices * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     RT3_CUDA(cudaMemcpyAsync(host_faces, d_faces.ptr, n_faces * 48, cudaMemcpyDeviceToHost, ctx->stream));
     if (host_face_entity) { RT3_CUDA(cudaMemcpyAsync(host_face_entity, d_entity.ptr, n_faces * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)); }
     RT3_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (first_vertex) { for (unsigned long long f = 0; f < n_faces; f++) { host_faces[f].v1 += first_vertex; host_faces[f].v2 += first_vertex; host_faces[f].v3 += first_vertex; } }
     return RT3_OK;
+}
+
+int rt3_tessellate_spheres_device(rt3_ctx* ctx, const rt3_uv_sphere* spheres, uint32_t n, uint32_t first_vertex, uint32_t first_face,
+                                  rt3_face* device_faces, rt3_vertex* device_vertices, uint32_t* device_face_entity) {
+    if (!ctx || (n && (!spheres || !device_faces || !device_vertices))) { return fail(RT3_ERR_INVALID, "NULL argument"); }
+    if ((((uintptr_t) device_faces) | ((uintptr_t) device_vertices)) & 15u) { return fail(RT3_ERR_INVALID, "device arrays must be 16-byte aligned"); }
+    RT3_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long n_faces = 0, n_vertices = 0;
+    int rc = uv_batch_size(spheres, n, &n_faces, &n_vertices);
+    if (rc != RT3_OK) { return rc; }
+    if (n_faces + first_face > 0x7FFFFFFFull || n_vertices + first_vertex > 0xFFFFFFFFull) { return fail(RT3_ERR_INVALID, "too many faces or vertices"); }
+    return tessellate_on_device(ctx, spheres, n, first_vertex, first_face, 0u, reinterpret_cast<uint4*>(device_faces), reinterpret_cast<float4*>(device_vertices),
+                                device_face_entity);
 }
 
 int rt3_frame_bytes(rt3_ctx* ctx, const uint32_t* device_frame, unsigned char* device_out, uint32_t width, uint32_t height, uint32_t channels,
@@ -1051,6 +999,10 @@ int rt3_get_stats(rt3_ctx* ctx, rt3_stats* out) {
     int rc = collect_stats(ctx);
     if (rc != RT3_OK) { return rc; }
     *out = ctx->stats;
+    /* the scene build is not part of a render: reported from the most recent upload on this context */
+    out->h2d_ms = ctx->upload_h2d_ms;
+    out->upload_ms = ctx->upload_ms;
+    out->upload_device_ms = ctx->upload_device_ms;
     return RT3_OK;
 }
 

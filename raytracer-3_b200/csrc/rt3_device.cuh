@@ -27,7 +27,11 @@
 #define RT3_PRAGMA_STR(x) _Pragma(#x)
 #define RT3_PRAGMA_UNROLL(n) RT3_PRAGMA_STR(unroll n)
 #ifndef RT3_RAYS
-#define RT3_RAYS 2              /* rays (path slots) per thread */
+#define RT3_RAYS 2              /* rays (path slots) per thread of the path tracer */
+#endif
+#ifndef RT3_REF_RAYS
+#define RT3_REF_RAYS 4          /* pixels per thread of the reference-mode ray caster: it carries no path state, so the registers
+                                 * go into more rays per record load (LDS / LDCU per test halves against 2 rays) */
 #endif
 #define RT3_WORD_PRIMS 32       /* primitives per survivor-mask word */
 #define RT3_PAD_PRIMS 8         /* the primitive array is padded to a multiple of this with never-surviving records */
@@ -240,16 +244,18 @@ __device__ __forceinline__ void exact_sphere_path(uint32_t prim, float4 sp, rt3_
 __constant__ float4 c_pair_xy[RT3_CONST_PRIMS / 2];
 __constant__ float2 c_pair_w[RT3_CONST_PRIMS / 2];
 
-/* Per-thread survivor masks of the chunk being swept: [RT3_RAYS][RT3_CHUNK_WORDS][RT3_CTA_THREADS] words. */
-#define RT3_MASK_BYTES (RT3_RAYS * RT3_CHUNK_WORDS * RT3_CTA_THREADS * 4)
+/* Per-thread survivor masks of the chunk being swept: [rays][RT3_CHUNK_WORDS][RT3_CTA_THREADS] words. */
+#define RT3_MASK_BYTES_FOR(rays) ((rays) * RT3_CHUNK_WORDS * RT3_CTA_THREADS * 4)
+#define RT3_MASK_BYTES RT3_MASK_BYTES_FOR(RT3_RAYS)
 
 /* Level 1 for one primitive pair and every ray of the thread: three packed FMAs
  * (fma.rn.f32x2, SASS FFMA2: both primitives of the pair at once) and two funnel
  * shifts that push the sign bits of a^2 - R^2 into the ray's mask word. */
-__device__ __forceinline__ void slab_pair(const float4 A, const float2 B, const float2 (&u1)[RT3_RAYS], const float2 (&u2)[RT3_RAYS],
-                                          const float2 (&nou2)[RT3_RAYS], uint32_t (&m)[RT3_RAYS]) {
+template <int R>
+__device__ __forceinline__ void slab_pair(const float4 A, const float2 B, const float2 (&u1)[R], const float2 (&u2)[R],
+                                          const float2 (&nou2)[R], uint32_t (&m)[R]) {
 #pragma unroll
-    for (int r = 0; r < RT3_RAYS; r++) {
+    for (int r = 0; r < R; r++) {
         const float2 a = __ffma2_rn(make_float2(A.x, A.y), u1[r], __ffma2_rn(make_float2(A.z, A.w), u2[r], nou2[r]));
         const float2 d = __ffma2_rn(a, a, B);
         m[r] = __funnelshift_l(__float_as_uint(d.x), m[r], 1);
@@ -263,26 +269,26 @@ __device__ __forceinline__ void slab_pair(const float4 A, const float2 B, const 
  * belongs to its k-th primitive. Words go to shared memory; `nz` gets one bit per
  * word, set when the word is not empty, the first word of the chunk in the highest
  * of the bits used (bit n_words - 1). */
-template <bool CONST_BANK>
+template <bool CONST_BANK, int R>
 __device__ __forceinline__ void sweep_chunk(const float4* __restrict__ xy, const float2* __restrict__ w, uint32_t first_pair, uint32_t n_pairs,
-                                            const rt3_ray_filter (&f)[RT3_RAYS], uint32_t* __restrict__ masks, uint32_t (&nz)[RT3_RAYS]) {
+                                            const rt3_ray_filter (&f)[R], uint32_t* __restrict__ masks, uint32_t (&nz)[R]) {
     constexpr uint32_t WORD_PAIRS = RT3_WORD_PRIMS / 2, PAD_PAIRS = RT3_PAD_PRIMS / 2;
-    float2 nou2[RT3_RAYS], u1[RT3_RAYS], u2[RT3_RAYS];
+    float2 nou2[R], u1[R], u2[R];
 #pragma unroll
-    for (int r = 0; r < RT3_RAYS; r++) {
+    for (int r = 0; r < R; r++) {
         nou2[r] = make_float2(f[r].nou, f[r].nou); u1[r] = make_float2(f[r].u1, f[r].u1); u2[r] = make_float2(f[r].u2, f[r].u2);
         nz[r] = 0u;
     }
     uint32_t waddr = smem_u32(masks) + threadIdx.x * 4u; /* this thread's word 0 of ray 0 */
     for (uint32_t done = 0; done < n_pairs; done += WORD_PAIRS, waddr += RT3_CTA_THREADS * 4u) {
-        uint32_t m[RT3_RAYS];
+        uint32_t m[R];
 #pragma unroll
-        for (int r = 0; r < RT3_RAYS; r++) { m[r] = 0u; }
+        for (int r = 0; r < R; r++) { m[r] = 0u; }
         const uint32_t base = first_pair + done;
         if (n_pairs - done >= WORD_PAIRS) {
 RT3_PRAGMA_UNROLL(RT3_UNROLL_PAIRS)
             for (int j = 0; j < (int) WORD_PAIRS; j++) {
-                slab_pair(CONST_BANK ? c_pair_xy[base + j] : xy[base + j], CONST_BANK ? c_pair_w[base + j] : w[base + j], u1, u2, nou2, m);
+                slab_pair<R>(CONST_BANK ? c_pair_xy[base + j] : xy[base + j], CONST_BANK ? c_pair_w[base + j] : w[base + j], u1, u2, nou2, m);
             }
         } else {
             /* last, partial word of the scene */
@@ -290,14 +296,14 @@ RT3_PRAGMA_UNROLL(RT3_UNROLL_PAIRS)
             for (uint32_t g = 0; g < left; g += PAD_PAIRS) {
 #pragma unroll
                 for (int j = 0; j < (int) PAD_PAIRS; j++) {
-                    slab_pair(CONST_BANK ? c_pair_xy[base + g + j] : xy[base + g + j], CONST_BANK ? c_pair_w[base + g + j] : w[base + g + j], u1, u2, nou2, m);
+                    slab_pair<R>(CONST_BANK ? c_pair_xy[base + g + j] : xy[base + g + j], CONST_BANK ? c_pair_w[base + g + j] : w[base + g + j], u1, u2, nou2, m);
                 }
             }
 #pragma unroll
-            for (int r = 0; r < RT3_RAYS; r++) { m[r] <<= 32u - 2u * left; }
+            for (int r = 0; r < R; r++) { m[r] <<= 32u - 2u * left; }
         }
 #pragma unroll
-        for (int r = 0; r < RT3_RAYS; r++) {
+        for (int r = 0; r < R; r++) {
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(waddr + (uint32_t) (r * RT3_CHUNK_WORDS * RT3_CTA_THREADS * 4)), "r"(m[r]) : "memory");
             nz[r] = (nz[r] << 1) + (m[r] < 1u ? m[r] : 1u);
         }
@@ -340,19 +346,19 @@ __device__ __forceinline__ void drain_chunk(const rt3_scene_view& S, uint32_t fi
 /* Closest hit of the thread's rays against `n_prims` primitives (a multiple of
  * RT3_PAD_PRIMS) whose records start at pair index `first_pair`; `first_prim` is
  * the global id of the first one. */
-template <bool PATH_MODE, bool CONST_BANK, bool SPHERES_ONLY>
+template <bool PATH_MODE, bool CONST_BANK, bool SPHERES_ONLY, int R>
 __device__ __forceinline__ void sweep_range(const rt3_scene_view& S, const float4* __restrict__ xy, const float2* __restrict__ w, uint32_t first_pair,
-                                            uint32_t first_prim, uint32_t n_prims, const rt3_ray_filter (&f)[RT3_RAYS],
-                                            const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&d)[RT3_RAYS], const bool (&live)[RT3_RAYS],
-                                            uint32_t* __restrict__ masks, rt3_hit (&best)[RT3_RAYS]) {
+                                            uint32_t first_prim, uint32_t n_prims, const rt3_ray_filter (&f)[R],
+                                            const rt3_vec3 (&o)[R], const rt3_vec3 (&d)[R], const bool (&live)[R],
+                                            uint32_t* __restrict__ masks, rt3_hit (&best)[R]) {
     constexpr uint32_t CHUNK_PAIRS = RT3_CHUNK_WORDS * RT3_WORD_PRIMS / 2;
     const uint32_t n_pairs = n_prims / 2;
     for (uint32_t p0 = 0, w0 = 0; p0 < n_pairs; p0 += CHUNK_PAIRS, w0 += RT3_CHUNK_WORDS) {
-        uint32_t nz[RT3_RAYS];
+        uint32_t nz[R];
         const uint32_t np = n_pairs - p0 < CHUNK_PAIRS ? n_pairs - p0 : CHUNK_PAIRS;
-        sweep_chunk<CONST_BANK>(xy, w, first_pair + p0, np, f, masks, nz);
+        sweep_chunk<CONST_BANK, R>(xy, w, first_pair + p0, np, f, masks, nz);
 #pragma unroll
-        for (int r = 0; r < RT3_RAYS; r++) {
+        for (int r = 0; r < R; r++) {
             if (!live[r]) { nz[r] = 0u; }
             drain_chunk<PATH_MODE, SPHERES_ONLY>(S, first_prim + w0 * RT3_WORD_PRIMS, (np + RT3_WORD_PRIMS / 2 - 1) / (RT3_WORD_PRIMS / 2), f[r], o[r], d[r],
                                                  masks + r * RT3_CHUNK_WORDS * RT3_CTA_THREADS + threadIdx.x, nz[r], best[r]);

@@ -60,16 +60,17 @@ enum { RT3_F_OX, RT3_F_OY, RT3_F_OZ, RT3_F_DX, RT3_F_DY, RT3_F_DZ, RT3_F_TX, RT3
 #define RT3_TILE_XY_BYTES (RT3_TILE_PAIRS * 16)
 #define RT3_TILE_W_BYTES (RT3_TILE_PAIRS * 8)
 
+/* path_slots: the path tracer (RT3_RAYS rays per thread + their slots); otherwise the reference-mode kernel (RT3_REF_RAYS rays per thread). */
 __host__ __device__ inline size_t rt3_smem_bytes(bool resident, bool path_slots) {
-    return (resident ? (size_t) RT3_MASK_BYTES : (size_t) 64 + 2 * (RT3_TILE_XY_BYTES + RT3_TILE_W_BYTES) + RT3_MASK_BYTES) +
-           (path_slots ? (size_t) RT3_SLOT_BYTES : 0);
+    const size_t masks = path_slots ? (size_t) RT3_MASK_BYTES : (size_t) RT3_MASK_BYTES_FOR(RT3_REF_RAYS);
+    return (resident ? masks : (size_t) 64 + 2 * (RT3_TILE_XY_BYTES + RT3_TILE_W_BYTES) + masks) + (path_slots ? (size_t) RT3_SLOT_BYTES : 0);
 }
 
 /* Hierarchy kernels keep no survivor masks: their shared memory is the path slots alone, which
  * leaves the rest of the SM's 256 KB to the L1 the node records are read through. */
 __host__ __device__ inline size_t rt3_accel_smem_bytes(bool path_slots) { return path_slots ? (size_t) RT3_SLOT_BYTES : 0; }
 
-template <bool RESIDENT, bool ACCEL = false>
+template <bool RESIDENT, bool ACCEL = false, int MASK_BYTES = RT3_MASK_BYTES>
 __device__ __forceinline__ rt3_smem_view smem_view(unsigned char* base) {
     rt3_smem_view v;
     if (ACCEL) {
@@ -78,13 +79,13 @@ __device__ __forceinline__ rt3_smem_view smem_view(unsigned char* base) {
     } else if (RESIDENT) {
         v.bars = nullptr; v.tile_xy = nullptr; v.tile_w = nullptr;
         v.masks = reinterpret_cast<uint32_t*>(base);
-        v.slots = reinterpret_cast<uint32_t*>(base + RT3_MASK_BYTES);
+        v.slots = reinterpret_cast<uint32_t*>(base + MASK_BYTES);
     } else {
         v.bars = reinterpret_cast<uint64_t*>(base);
         v.tile_xy = reinterpret_cast<float4*>(base + 64);
         v.tile_w = reinterpret_cast<float2*>(base + 64 + 2 * RT3_TILE_XY_BYTES);
         v.masks = reinterpret_cast<uint32_t*>(base + 64 + 2 * (RT3_TILE_XY_BYTES + RT3_TILE_W_BYTES));
-        v.slots = reinterpret_cast<uint32_t*>(base + 64 + 2 * (RT3_TILE_XY_BYTES + RT3_TILE_W_BYTES) + RT3_MASK_BYTES);
+        v.slots = reinterpret_cast<uint32_t*>(base + 64 + 2 * (RT3_TILE_XY_BYTES + RT3_TILE_W_BYTES) + MASK_BYTES);
     }
     return v;
 }
@@ -113,19 +114,19 @@ __device__ __forceinline__ void fetch_tile(const rt3_scene_view& S, const rt3_sm
 /* Closest hit of the thread's rays against the whole scene. For streamed
  * scenes every thread of the CTA must call this together (tile barriers);
  * `phase` carries the mbarrier parities across calls. */
-template <bool PATH_MODE, bool RESIDENT, bool SPHERES_ONLY>
+template <bool PATH_MODE, bool RESIDENT, bool SPHERES_ONLY, int R>
 __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_smem_view& sm, uint32_t& phase,
-                                            const rt3_vec3 (&o)[RT3_RAYS], const rt3_vec3 (&d)[RT3_RAYS], const rt3_vec3 (&dn)[RT3_RAYS],
-                                            const bool (&live)[RT3_RAYS], rt3_hit (&best)[RT3_RAYS]) {
-    rt3_ray_filter f[RT3_RAYS];
+                                            const rt3_vec3 (&o)[R], const rt3_vec3 (&d)[R], const rt3_vec3 (&dn)[R],
+                                            const bool (&live)[R], rt3_hit (&best)[R]) {
+    rt3_ray_filter f[R];
 #pragma unroll
-    for (int r = 0; r < RT3_RAYS; r++) {
+    for (int r = 0; r < R; r++) {
         f[r] = make_ray_filter(S, o[r], dn[r]);
         best[r].t = __int_as_float(0x7f800000);
         best[r].prim = RT3_NO_HIT;
     }
     if (RESIDENT) {
-        sweep_range<PATH_MODE, true, SPHERES_ONLY>(S, nullptr, nullptr, 0u, 0u, S.n_prims_padded, f, o, d, live, sm.masks, best);
+        sweep_range<PATH_MODE, true, SPHERES_ONLY, R>(S, nullptr, nullptr, 0u, 0u, S.n_prims_padded, f, o, d, live, sm.masks, best);
         return;
     }
     const uint32_t n_tiles = (S.n_prims_padded + RT3_TILE_PRIMS - 1) / RT3_TILE_PRIMS;
@@ -138,7 +139,7 @@ __device__ __forceinline__ void sweep_scene(const rt3_scene_view& S, const rt3_s
         phase ^= 1u << stage;
         const uint32_t first = t * RT3_TILE_PRIMS;
         const uint32_t n = S.n_prims_padded - first < RT3_TILE_PRIMS ? S.n_prims_padded - first : RT3_TILE_PRIMS;
-        sweep_range<PATH_MODE, false, SPHERES_ONLY>(S, sm.tile_xy + (size_t) stage * RT3_TILE_PAIRS, sm.tile_w + (size_t) stage * RT3_TILE_PAIRS, 0u, first, n,
+        sweep_range<PATH_MODE, false, SPHERES_ONLY, R>(S, sm.tile_xy + (size_t) stage * RT3_TILE_PAIRS, sm.tile_w + (size_t) stage * RT3_TILE_PAIRS, 0u, first, n,
                                       f, o, d, live, sm.masks, best);
         __syncthreads();
     }
@@ -221,7 +222,7 @@ __device__ __forceinline__ void sweep_slots(const rt3_scene_view& S, const rt3_s
         for (uint32_t p0 = 0; p0 < n_pairs; p0 += CHUNK_PAIRS) {
             uint32_t nz[RT3_RAYS];
             const uint32_t np = n_pairs - p0 < CHUNK_PAIRS ? n_pairs - p0 : CHUNK_PAIRS;
-            sweep_chunk<true>(nullptr, nullptr, p0, np, f, sm.masks, nz);
+            sweep_chunk<true, RT3_RAYS>(nullptr, nullptr, p0, np, f, sm.masks, nz);
             drain_slots<SPHERES_ONLY>(S, sm, 2u * p0, np, f, nz);
         }
         return;
@@ -240,7 +241,7 @@ __device__ __forceinline__ void sweep_slots(const rt3_scene_view& S, const rt3_s
         for (uint32_t p0 = 0; p0 < n_pairs; p0 += CHUNK_PAIRS) {
             uint32_t nz[RT3_RAYS];
             const uint32_t np = n_pairs - p0 < CHUNK_PAIRS ? n_pairs - p0 : CHUNK_PAIRS;
-            sweep_chunk<false>(xy, w, p0, np, f, sm.masks, nz);
+            sweep_chunk<false, RT3_RAYS>(xy, w, p0, np, f, sm.masks, nz);
             drain_slots<SPHERES_ONLY>(S, sm, first + 2u * p0, np, f, nz);
         }
         __syncthreads();
@@ -265,16 +266,19 @@ __device__ __forceinline__ void count_accel(uint32_t visits, uint32_t tests, uns
     if ((threadIdx.x & 31) == 0) { atomicAdd(&counters[2], v); atomicAdd(&counters[3], t); }
 }
 
+#ifndef RT3_REF_CTAS_PER_SM
+#define RT3_REF_CTAS_PER_SM 4   /* register budget 128 per thread: four rays' filters, masks and closest hits stay in registers */
+#endif
 /* ------------------------------------------------------------------------ *
  * Reference mode: SequentialRenderer.cpp:269-308 (+ AOVs)
  * ------------------------------------------------------------------------ */
 template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL>
-__global__ void __launch_bounds__(RT3_CTA_THREADS, RT3_CTAS_PER_SM)
+__global__ void __launch_bounds__(RT3_CTA_THREADS, RT3_REF_CTAS_PER_SM)
 reference_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P, uint32_t* __restrict__ frame, uint32_t* __restrict__ hit_prim,
                  uint32_t* __restrict__ hit_entity, float* __restrict__ hit_t, unsigned long long* __restrict__ counters) {
-    constexpr int R = RT3_RAYS;
+    constexpr int R = RT3_REF_RAYS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const rt3_smem_view sm = smem_view<RESIDENT, ACCEL>(smem_raw);
+    const rt3_smem_view sm = smem_view<RESIDENT, ACCEL, RT3_MASK_BYTES_FOR(RT3_REF_RAYS)>(smem_raw);
     scene_prologue<RESIDENT>(sm);
     uint32_t phase = 0u;
 
@@ -311,7 +315,7 @@ reference_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
             if (live[r]) { bvh_closest_hit<false>(S, B, o[r], d[r], best[r], visits, tests); }
         }
     } else {
-        sweep_scene<false, RESIDENT, SPHERES_ONLY>(S, sm, phase, o, d, dn, live, best);
+        sweep_scene<false, RESIDENT, SPHERES_ONLY, R>(S, sm, phase, o, d, dn, live, best);
     }
     unsigned long long rays = 0;
 #pragma unroll

@@ -25,6 +25,7 @@ struct rt3_uv_sphere_dev {
     uint32_t first_vertex;    /* offset of this sphere's vertices in the output array */
     uint32_t first_face;
     uint32_t entity;
+    uint32_t index_shift;     /* added to the vertex indices a face records (where the caller keeps the batch in its own vertex array) */
 };
 
 __host__ __device__ inline uint32_t uv_sphere_vertices(uint32_t m, uint32_t p) { return 2u + (p - 2u) * m; }
@@ -82,7 +83,7 @@ __global__ void uv_sphere_faces_kernel(rt3_uv_sphere_dev s, const float4* __rest
     /* Sphere.cpp:153-155: normal = normalize(cross(c - a, b - a)), colour = colour * |n . (0, 0, -1)| */
     const rt3_vec3 nrm = normalize3(cross3(c - a, b - a));
     const float shade = fabsf((nrm.x * 0.0f + nrm.y * 0.0f) + nrm.z * -1.0f);
-    store_face(faces, s.first_face + f, s.first_vertex + ia, s.first_vertex + ib, s.first_vertex + ic, nrm,
+    store_face(faces, s.first_face + f, s.index_shift + s.first_vertex + ia, s.index_shift + s.first_vertex + ib, s.index_shift + s.first_vertex + ic, nrm,
                v3(s.r * shade, s.g * shade, s.b * shade));
     if (face_entity) { face_entity[s.first_face + f] = s.entity; }
 }

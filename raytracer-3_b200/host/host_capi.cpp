@@ -101,6 +101,17 @@ int rt3host_flatten(void* s, uint32_t* n_faces, uint32_t* n_vertices, void* face
     });
 }
 
+/* The flattened scene the renderer holds after prerender() (CudaRenderer::flat_faces / flat_vertices): with
+ * device_tessellation these are read back from the device arrays the kernels filled. Sizes first (NULL outputs), then the data. */
+int rt3host_renderer_flat(void* s, uint32_t* n_faces, uint32_t* n_vertices, void* faces_out, void* vertices_out) {
+    HostScene* hs = (HostScene*) s;
+    if (!hs->renderer) { g_error = "create the renderer first"; return -1; }
+    *n_faces = (uint32_t) hs->renderer->flat_faces.size(); *n_vertices = (uint32_t) hs->renderer->flat_vertices.size();
+    if (faces_out) { std::memcpy(faces_out, hs->renderer->flat_faces.data(), sizeof(rt3_face) * hs->renderer->flat_faces.size()); }
+    if (vertices_out) { std::memcpy(vertices_out, hs->renderer->flat_vertices.data(), sizeof(rt3_vertex) * hs->renderer->flat_vertices.size()); }
+    return 0;
+}
+
 /* initialize_renderer() + settings; mode 0 = reference, 1 = pathtrace. */
 int rt3host_renderer_create(void* s, int device, uint32_t mode, uint32_t spp, uint32_t max_depth, uint32_t seed, uint32_t flags, int analytic_spheres) {
     HostScene* hs = (HostScene*) s;

@@ -96,9 +96,11 @@ CudaRenderer::CudaRenderer(const std::vector<int>& devices) : Renderer(), ctx(nu
 }
 
 void CudaRenderer::release() noexcept {
-    if (this->shared_frame) { rt3_frame_free(this->ctx, this->shared_frame); this->shared_frame = nullptr; this->shared_pixels = 0; }
+    /* helpers first: rt3_destroy waits for their streams, and their kernels store into the shared frame over NVLink --
+     * it may only be freed once nothing can write to it any more (a render that failed half-way leaves work enqueued) */
     for (size_t i = 0; i < this->helpers.size(); i++) { rt3_destroy(this->helpers[i]); }
     this->helpers.clear();
+    if (this->shared_frame) { rt3_frame_free(this->ctx, this->shared_frame); this->shared_frame = nullptr; this->shared_pixels = 0; }
     rt3_destroy(this->ctx);
     this->ctx = nullptr;
 }
@@ -111,6 +113,15 @@ void CudaRenderer::prerender(const Tools::Array<ECS::RenderEntity*>& entities) {
     std::vector<float> sphere_color;
     std::vector<rt3_material> table;
     bool any_material = !this->materials.empty();
+
+    /* device scene (settings.device_tessellation): spheres are tessellated on the device straight into the flattened arrays
+     * there; the host arrays keep zeroed placeholders for them (so that offsets are the reference's) and are filled from the
+     * device afterwards for inspection. `host_ranges` are the stretches the host did produce (triangles, object files). */
+    struct DeferredSphere { rt3_uv_sphere d; uint32_t first_vertex, first_face; };
+    struct Range { size_t first_face, n_faces, first_vertex, n_vertices; };
+    std::vector<DeferredSphere> deferred;
+    std::vector<Range> host_ranges;
+    const bool device_scene = this->settings.device_tessellation;
 
     Tools::Array<GFace> faces;
     Tools::Array<glm::vec4> vertices;
@@ -159,14 +170,16 @@ void CudaRenderer::prerender(const Tools::Array<ECS::RenderEntity*>& entities) {
         switch (e->pre_render_operation) {
             case EntityPreRenderOperation::epro_generate_triangle: cpu_pre_render_triangle(faces, vertices, (Triangle*) e); break;
             case EntityPreRenderOperation::epro_generate_sphere:
-                if (this->settings.device_tessellation) {
-                    /* the reference's GPU pre-render (VulkanRenderer.cpp:310-336) as a CUDA kernel, CPU-path arithmetic */
+                if (device_scene) {
+                    /* the reference's GPU pre-render (VulkanRenderer.cpp:310-336) as a CUDA kernel, CPU-path arithmetic; run after
+                     * this loop, when the device arrays exist */
                     const Sphere* sp = (const Sphere*) e;
-                    rt3_uv_sphere d = { { sp->center.x, sp->center.y, sp->center.z }, sp->radius, sp->n_meridians, sp->n_parallels,
-                                        { sp->color.x, sp->color.y, sp->color.z }, (uint32_t) i };
-                    static_assert(sizeof(GFace) == sizeof(rt3_face) && sizeof(glm::vec4) == sizeof(rt3_vertex), "flattened records differ");
-                    check(rt3_tessellate_spheres(this->ctx, &d, 1, 0, (rt3_face*) &faces[0], (rt3_vertex*) &vertices[0], nullptr),
-                          "Could not tessellate a sphere on the device");
+                    DeferredSphere job = { { { sp->center.x, sp->center.y, sp->center.z }, sp->radius, sp->n_meridians, sp->n_parallels,
+                                             { sp->color.x, sp->color.y, sp->color.z }, (uint32_t) i },
+                                           (uint32_t) this->flat_vertices.size(), (uint32_t) this->flat_faces.size() };
+                    deferred.push_back(job);
+                    std::memset((void*) &faces[0], 0, faces.size() * sizeof(GFace));
+                    std::memset((void*) &vertices[0], 0, vertices.size() * sizeof(glm::vec4));
                 } else {
                     cpu_pre_render_sphere(faces, vertices, (Sphere*) e);
                 }
@@ -175,6 +188,10 @@ void CudaRenderer::prerender(const Tools::Array<ECS::RenderEntity*>& entities) {
             default:
                 DLOG(fatal, "Entity " + std::to_string(i) + " wants to be pre-rendered using unsupported operation '" +
                                 entity_pre_render_operation_names[e->pre_render_operation] + "'.");
+        }
+        if (device_scene && e->pre_render_operation != EntityPreRenderOperation::epro_generate_sphere) {
+            Range r = { this->flat_faces.size(), faces.size(), this->flat_vertices.size(), vertices.size() };
+            host_ranges.push_back(r);
         }
         /* append with re-based indices (SequentialRenderer.cpp:174-195) */
         const uint32_t offset = (uint32_t) this->flat_vertices.size();
@@ -208,8 +225,57 @@ void CudaRenderer::prerender(const Tools::Array<ECS::RenderEntity*>& entities) {
     scene.sphere_material = any_material ? sphere_material.data() : nullptr;
     scene.n_materials = (uint32_t) table.size();
     scene.materials = table.data();
-    check(rt3_scene_upload(this->ctx, &scene), "Could not upload the scene");
-    for (size_t i = 0; i < this->helpers.size(); i++) { check(rt3_scene_upload(this->helpers[i], &scene), "Could not upload the scene to a further device"); }
+    if (!device_scene) {
+        check(rt3_scene_upload(this->ctx, &scene), "Could not upload the scene");
+        for (size_t i = 0; i < this->helpers.size(); i++) { check(rt3_scene_upload(this->helpers[i], &scene), "Could not upload the scene to a further device"); }
+        return;
+    }
+
+    /* Device scene: the flattened arrays are assembled in each device's memory -- the host's stretches by plain copies, the
+     * spheres by the tessellation kernels -- and everything derived from them is built there (rt3_scene_upload_device). */
+    struct DeviceArrays {
+        rt3_ctx* ctx;
+        void* p[9] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+        explicit DeviceArrays(rt3_ctx* c) : ctx(c) {}
+        ~DeviceArrays() { for (int k = 0; k < 9; k++) { rt3_buffer_free(ctx, p[k]); } }
+        void* put(int slot, const void* host, size_t bytes, const char* what) {
+            if (!host || bytes == 0) { return nullptr; }
+            check(rt3_buffer_alloc(ctx, bytes, &p[slot]), what);
+            return p[slot];
+        }
+    };
+    for (size_t dev = 0; dev < 1 + this->helpers.size(); dev++) {
+        rt3_ctx* c = dev == 0 ? this->ctx : this->helpers[dev - 1];
+        DeviceArrays a(c);
+        rt3_scene d = scene;
+        d.faces = (const rt3_face*) a.put(0, scene.faces, (size_t) scene.n_faces * sizeof(rt3_face), "Could not allocate the device faces");
+        d.vertices = (const rt3_vertex*) a.put(1, scene.vertices, (size_t) scene.n_vertices * sizeof(rt3_vertex), "Could not allocate the device vertices");
+        for (size_t k = 0; k < host_ranges.size(); k++) {
+            const Range& r = host_ranges[k];
+            check(rt3_buffer_write(c, (rt3_face*) d.faces + r.first_face, scene.faces + r.first_face, r.n_faces * sizeof(rt3_face)), "Could not copy faces to the device");
+            check(rt3_buffer_write(c, (rt3_vertex*) d.vertices + r.first_vertex, scene.vertices + r.first_vertex, r.n_vertices * sizeof(rt3_vertex)), "Could not copy vertices to the device");
+        }
+        for (size_t k = 0; k < deferred.size(); k++) {
+            check(rt3_tessellate_spheres_device(c, &deferred[k].d, 1, deferred[k].first_vertex, deferred[k].first_face, (rt3_face*) d.faces, (rt3_vertex*) d.vertices, nullptr),
+                  "Could not tessellate a sphere on the device");
+        }
+        const struct { int slot; const void** view; const void* host; size_t bytes; } small[] = {
+            { 2, (const void**) &d.face_entity, scene.face_entity, (size_t) scene.n_faces * 4 }, { 3, (const void**) &d.face_material, scene.face_material, (size_t) scene.n_faces * 4 },
+            { 4, (const void**) &d.spheres, scene.spheres, (size_t) scene.n_spheres * sizeof(rt3_sphere) }, { 5, (const void**) &d.sphere_color, scene.sphere_color, (size_t) scene.n_spheres * 12 },
+            { 6, (const void**) &d.sphere_entity, scene.sphere_entity, (size_t) scene.n_spheres * 4 }, { 7, (const void**) &d.sphere_material, scene.sphere_material, (size_t) scene.n_spheres * 4 },
+            { 8, (const void**) &d.materials, scene.materials, (size_t) scene.n_materials * sizeof(rt3_material) },
+        };
+        for (size_t k = 0; k < sizeof small / sizeof small[0]; k++) {
+            *small[k].view = a.put(small[k].slot, small[k].host, small[k].bytes, "Could not allocate a device scene array");
+            if (*small[k].view) { check(rt3_buffer_write(c, (void*) *small[k].view, small[k].host, small[k].bytes), "Could not copy a scene array to the device"); }
+        }
+        check(rt3_scene_upload_device(c, &d), dev == 0 ? "Could not build the scene on the device" : "Could not build the scene on a further device");
+        if (dev == 0 && !deferred.empty()) {
+            /* host copies for inspection (flat_faces / flat_vertices): what the kernels wrote */
+            check(rt3_buffer_read(c, this->flat_faces.data(), d.faces, (size_t) scene.n_faces * sizeof(rt3_face)), "Could not read the faces back");
+            check(rt3_buffer_read(c, this->flat_vertices.data(), d.vertices, (size_t) scene.n_vertices * sizeof(rt3_vertex)), "Could not read the vertices back");
+        }
+    }
 }
 
 void CudaRenderer::render(Camera& camera) const { this->render_samples(camera, 0, false); }

@@ -46,7 +46,8 @@ namespace RayTracer {
          * the sweep wins while its records stay in the constant cache. 0 = always the hierarchy, UINT32_MAX = never. */
         uint32_t bvh_above = 768;
         bool analytic_spheres = false;      /* keep ECS spheres analytic instead of tessellating them */
-        bool device_tessellation = false;   /* tessellate ECS spheres on the device (rt3_tessellate_spheres) instead of the CPU */
+        bool device_tessellation = false;   /* build the flattened scene in device memory: ECS spheres are tessellated there (rt3_tessellate_spheres_device),
+                                             * the host's triangles / object files are copied next to them, and nothing is derived on the host (rt3_scene_upload_device) */
         uint32_t tile_rows = 8, part_index = 0, part_count = 1;
         /* Reads RT3_MODE (reference|pathtrace), RT3_SPP, RT3_DEPTH, RT3_SEED, RT3_ANALYTIC_SPHERES, RT3_DEVICE_TESSELLATION, RT3_BVH, RT3_BVH_ABOVE, RT3_DEVICE. */
         static CudaRenderSettings from_environment(int* device);

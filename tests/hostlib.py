@@ -87,6 +87,15 @@ class HostScene:
         self._ok(self.L.rt3host_flatten(self.h, C.byref(nf), C.byref(nv), faces.ctypes.data, verts.ctypes.data, ent.ctypes.data))
         return abi.SceneArrays(faces=faces, vertices=verts, face_entity=ent)
 
+    def renderer_flat(self) -> abi.SceneArrays:
+        """The flattened scene the renderer holds after prerender() (read back from the device with device_tessellation)."""
+        nf, nv = C.c_uint32(), C.c_uint32()
+        self.L.rt3host_renderer_flat.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p]
+        self._ok(self.L.rt3host_renderer_flat(self.h, C.byref(nf), C.byref(nv), None, None))
+        faces, verts = np.zeros(nf.value, abi.FACE_DTYPE), np.zeros(nv.value, abi.VERTEX_DTYPE)
+        self._ok(self.L.rt3host_renderer_flat(self.h, C.byref(nf), C.byref(nv), faces.ctypes.data, verts.ctypes.data))
+        return abi.SceneArrays(faces=faces, vertices=verts)
+
     def create_renderer(self, device=0, mode=abi.MODE_REFERENCE, spp=1, max_depth=1, seed=1, flags=0, analytic_spheres=False,
                         device_tessellation=False):
         self._ok(self.L.rt3host_renderer_create(self.h, device, mode, spp, max_depth, seed, flags,
