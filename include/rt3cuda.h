@@ -189,7 +189,8 @@ typedef struct rt3_stats {
     uint64_t accel_prim_tests;  /* exact ray-primitive tests run in leaves */
     double accel_build_ms;      /* device time of the hierarchy build for the current scene */
     uint32_t accel;             /* 1 if the most recent render used the hierarchy */
-    uint32_t _pad;
+    uint32_t accel_stack_overflows; /* subtrees the traversal could not stack (never, for trees this library builds: depth <= 94 of 128); a render
+                                 * with a non-zero count fails (rt3_render) or makes rt3_get_stats fail (rt3_render_device) */
     /* the most recent scene upload on this context (the reference's prerender, Main.cpp:284) */
     double upload_ms;           /* wall clock of rt3_scene_upload / rt3_scene_upload_device, call to return */
     double upload_device_ms;    /* CUDA-event time of the kernels that derive bounds, boxes, prefilter records and the scene basis */

@@ -82,7 +82,7 @@ class Stats(C.Structure):
         ("rays", C.c_uint64), ("sphere_tests", C.c_uint64), ("face_tests", C.c_uint64),
         ("kernel_launches", C.c_uint32), ("rows_rendered", C.c_uint32),
         ("accel_node_visits", C.c_uint64), ("accel_prim_tests", C.c_uint64), ("accel_build_ms", C.c_double),
-        ("accel", C.c_uint32), ("_pad", C.c_uint32),
+        ("accel", C.c_uint32), ("accel_stack_overflows", C.c_uint32),
         ("upload_ms", C.c_double), ("upload_device_ms", C.c_double),
     ]
 

@@ -200,7 +200,7 @@ __device__ __forceinline__ bool bvh_slab(const rt3_bvh_ray& r, float lox, float 
  * read, `tests` exact tests run. */
 template <bool PATH_MODE>
 __device__ __forceinline__ void bvh_closest_hit(const rt3_scene_view& S, const rt3_bvh_view& B, rt3_vec3 o, rt3_vec3 d, rt3_hit& best,
-                                                uint32_t& visits, uint32_t& tests) {
+                                                uint32_t& visits, uint32_t& tests, unsigned long long* __restrict__ counters) {
     best.t = __int_as_float(0x7f800000);
     best.prim = RT3_NO_HIT;
     uint2 stack[RT3_BVH_STACK]; /* (subtree reference, its entry distance): one 8-byte local access per push / pop */
@@ -249,6 +249,7 @@ __device__ __forceinline__ void bvh_closest_hit(const rt3_scene_view& S, const r
             if (h0 && h1) {
                 const bool first0 = t0 <= t1;
                 if (sp < RT3_BVH_STACK) { stack[sp++] = make_uint2((uint32_t) (first0 ? c1 : c0), __float_as_uint(first0 ? t1 : t0)); }
+                else { atomicAdd(&counters[4], 1ull); } /* cannot happen for a radix tree over 63-bit keys + 31 index bits (depth <= 94); counted, and the render fails (rt3_core.cu) */
                 return first0 ? c0 : c1;
             }
             if (h0) { return c0; }

@@ -338,7 +338,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     std::unique_lock<std::mutex> bank_lock; /* released when this function returns, i.e. after the launch below */
     if (resident && kp.n_pixels != 0 && (rc = claim_constant_bank(ctx, stream, bank_lock)) != RT3_OK) { return rc; }
     RT3_CUDA(cudaEventRecord(ctx->ev_begin, stream));
-    RT3_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 4 * sizeof(unsigned long long), stream));
+    RT3_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 5 * sizeof(unsigned long long), stream));
     if (kp.n_pixels == 0) {
         RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
         RT3_CUDA(cudaEventRecord(ctx->ev_k1, stream));
@@ -429,6 +429,8 @@ int copy_owned_rows(const rt3_kparams& kp, const T* dev, T* host, cudaStream_t s
     return RT3_OK;
 }
 
+int collect_stats(rt3_ctx* ctx);
+
 int render_to_host(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params, uint32_t* host_frame, uint32_t* host_prim,
                    uint32_t* host_ent, float* host_t, bool want_aov) {
     rt3_kparams kp;
@@ -454,6 +456,7 @@ int render_to_host(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     RT3_CUDA(cudaEventRecord(ctx->ev_copy, ctx->stream));
     ctx->copy_timed = true;
     RT3_CUDA(cudaStreamSynchronize(ctx->stream)); /* blocking, like the reference's render() (VulkanRenderer.cpp:497) */
+    if (ctx->stats.accel) { return collect_stats(ctx); } /* a traversal that overflowed its stack fails the render instead of dropping a subtree silently */
     return RT3_OK;
 }
 
@@ -462,7 +465,7 @@ int collect_stats(rt3_ctx* ctx) {
     if (!ctx->stats_pending) { return RT3_OK; }
     RT3_CUDA(cudaSetDevice(ctx->device));
     RT3_CUDA(cudaStreamSynchronize(ctx->last_stream));
-    unsigned long long counters[4] = { 0, 0, 0, 0 };
+    unsigned long long counters[5] = { 0, 0, 0, 0, 0 };
     RT3_CUDA(cudaMemcpy(counters, ctx->counters.ptr, sizeof counters, cudaMemcpyDeviceToHost));
     float ms = 0.0f, ms_k = 0.0f, ms_copy = 0.0f;
     RT3_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
@@ -482,7 +485,9 @@ int collect_stats(rt3_ctx* ctx) {
     ctx->stats.accel_node_visits = counters[2];
     ctx->stats.accel_prim_tests = counters[3];
     ctx->stats.accel_build_ms = ctx->bvh_build_ms;
+    ctx->stats.accel_stack_overflows = (uint32_t) std::min<unsigned long long>(counters[4], 0xFFFFFFFFull);
     ctx->stats_pending = false;
+    if (counters[4]) { return fail(RT3_ERR_INVALID, "hierarchy traversal overflowed its stack %llu times: the frame may miss hits", counters[4]); }
     return RT3_OK;
 }
 
@@ -645,7 +650,7 @@ int rt3_create(rt3_ctx** out, int device) {
     if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_copy); }
     if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_k0); }
     if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_k1); }
-    if (err == cudaSuccess && ctx->counters.reserve(4) != RT3_OK) { err = cudaErrorMemoryAllocation; }
+    if (err == cudaSuccess && ctx->counters.reserve(5) != RT3_OK) { err = cudaErrorMemoryAllocation; }
     if (err != cudaSuccess) {
         rt3_destroy(ctx);
         return fail(RT3_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(err));

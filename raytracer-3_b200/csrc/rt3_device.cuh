@@ -30,8 +30,9 @@
 #define RT3_RAYS 2              /* rays (path slots) per thread of the path tracer */
 #endif
 #ifndef RT3_REF_RAYS
-#define RT3_REF_RAYS 4          /* pixels per thread of the reference-mode ray caster: it carries no path state, so the registers
-                                 * go into more rays per record load (LDS / LDCU per test halves against 2 rays) */
+#define RT3_REF_RAYS 2          /* pixels per thread of the reference-mode ray caster (the sweep is templated on it). Four rays per thread
+                                 * halve the record loads per test but need 122-128 registers (4 CTAs per SM): measured slower on the
+                                 * B200, 6.13 against 5.56 SMSP-cycles per warp-test at 65 536 spheres (profiles/r02b_sweep_rate_*.jsonl) */
 #endif
 #define RT3_WORD_PRIMS 32       /* primitives per survivor-mask word */
 #define RT3_PAD_PRIMS 8         /* the primitive array is padded to a multiple of this with never-surviving records */

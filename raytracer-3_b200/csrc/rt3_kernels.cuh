@@ -249,12 +249,13 @@ __device__ __forceinline__ void sweep_slots(const rt3_scene_view& S, const rt3_s
 }
 
 /* Hierarchy traversal for every live slot (results in the slots' BEST fields). */
-__device__ __forceinline__ void traverse_slots(const rt3_scene_view& S, const rt3_bvh_view& B, const rt3_smem_view& sm, uint32_t& visits, uint32_t& tests) {
+__device__ __forceinline__ void traverse_slots(const rt3_scene_view& S, const rt3_bvh_view& B, const rt3_smem_view& sm, uint32_t& visits, uint32_t& tests,
+                                               unsigned long long* __restrict__ counters) {
 #pragma unroll 1
     for (int r = 0; r < RT3_RAYS; r++) {
         if (slot_word(sm, r, RT3_F_BOUNCE) == RT3_NO_HIT) { continue; }
         rt3_hit best;
-        bvh_closest_hit<true>(S, B, slot_vec(sm, r, RT3_F_OX), slot_vec(sm, r, RT3_F_DX), best, visits, tests);
+        bvh_closest_hit<true>(S, B, slot_vec(sm, r, RT3_F_OX), slot_vec(sm, r, RT3_F_DX), best, visits, tests, counters);
         slot_word(sm, r, RT3_F_BEST_T) = __float_as_uint(best.t); slot_word(sm, r, RT3_F_BEST_PRIM) = best.prim;
     }
 }
@@ -267,7 +268,7 @@ __device__ __forceinline__ void count_accel(uint32_t visits, uint32_t tests, uns
 }
 
 #ifndef RT3_REF_CTAS_PER_SM
-#define RT3_REF_CTAS_PER_SM 4   /* register budget 128 per thread: four rays' filters, masks and closest hits stay in registers */
+#define RT3_REF_CTAS_PER_SM RT3_CTAS_PER_SM
 #endif
 /* ------------------------------------------------------------------------ *
  * Reference mode: SequentialRenderer.cpp:269-308 (+ AOVs)
@@ -312,7 +313,7 @@ reference_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
 #pragma unroll
         for (int r = 0; r < R; r++) {
             best[r].t = __int_as_float(0x7f800000); best[r].prim = RT3_NO_HIT;
-            if (live[r]) { bvh_closest_hit<false>(S, B, o[r], d[r], best[r], visits, tests); }
+            if (live[r]) { bvh_closest_hit<false>(S, B, o[r], d[r], best[r], visits, tests, counters); }
         }
     } else {
         sweep_scene<false, RESIDENT, SPHERES_ONLY, R>(S, sm, phase, o, d, dn, live, best);
@@ -688,7 +689,7 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
         for (int r = 0; r < R; r++) { any = any || slot_word(sm, r, RT3_F_BOUNCE) != RT3_NO_HIT; }
         if (RESIDENT) { if (!__any_sync(0xffffffffu, any)) { break; } }   /* warps run independently */
         else { if (!__syncthreads_or(any ? 1 : 0)) { break; } }           /* tiles are CTA-wide */
-        if (ACCEL) { traverse_slots(S, B, sm, visits, tests); }
+        if (ACCEL) { traverse_slots(S, B, sm, visits, tests, counters); }
         else { sweep_slots<RESIDENT, SPHERES_ONLY>(S, sm, phase); }
     }
     for (int off = 16; off > 0; off >>= 1) { rays += __shfl_down_sync(0xffffffffu, rays, off); }

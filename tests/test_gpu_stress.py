@@ -106,3 +106,41 @@ def test_path_tracing_far_from_the_origin(gpu_ctx):
     for flags in (0, abi.FLAG_BVH):
         gpu = gpu_ctx.render(cam, abi.make_params(w, h, flags=flags, **base))
         assert gpu_ctx.stats().rays == rays and np.array_equal(gpu, cpu), f"flags={flags}: {int((gpu != cpu).sum())} pixels differ"
+
+
+def test_two_host_threads_share_the_constant_bank(built):
+    """Two contexts on one device, each driven by its own host thread with its own small scene (both small enough for
+    the constant-bank sweep): the bank is claimed under a per-device lock that is held until the kernel reading it has been
+    enqueued, and a change of owner waits for the device, so neither thread can sweep the other's records."""
+    import threading
+    from rt3_b200 import scenes
+    w, h = 160, 90
+    jobs = []
+    for seed in (1, 2):
+        scene, cam = scenes.random_spheres(300, seed=seed, width=w, height=h)
+        scene.spheres[:, :3] *= np.float32(0.05)
+        scene.spheres[:, 2] -= np.float32(1.0)
+        ctx = abi.Context(0)
+        ctx.upload(scene)
+        params = abi.make_params(w, h, mode=abi.MODE_PATHTRACE, spp=4, max_depth=6, seed=seed)
+        jobs.append((ctx, cam, params, ctx.render(cam, params)))   # the frame each context renders on its own
+    assert not np.array_equal(jobs[0][3], jobs[1][3])
+    errors = []
+
+    def hammer(ctx, cam, params, expected):
+        try:
+            for _ in range(40):
+                if not np.array_equal(ctx.render(cam, params), expected):
+                    errors.append("a frame differs from the one rendered alone")
+                    return
+        except Exception as e:   # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=hammer, args=j) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for ctx, *_ in jobs:
+        ctx.close()
+    assert not errors, errors
