@@ -1,0 +1,41 @@
+"""Times one build of the library (RT3_CORE_LIB) on BASELINE C2 (sweep and hierarchy) and, with --c3, on C3 through the hierarchy.
+Prints one JSON line with kernel times and a frame checksum (all variants must produce the same frames).
+Usage: RT3_CORE_LIB=<lib.so> python profiles/variants.py <label> [--c3] [--spp N]"""
+import json
+import os
+import sys
+import zlib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import rt3_b200  # noqa: F401,E402
+from rt3_b200 import abi, scenes  # noqa: E402
+
+label = sys.argv[1]
+ctx = abi.Context(0)
+out = {"variant": label, "lib": os.path.basename(abi.CORE_LIB_PATH), "binning": os.environ.get("RT3_BINNING", "default")}
+
+
+def timed(cam, params, reps=3):
+    best, frame = None, None
+    for _ in range(reps):
+        frame = ctx.render(cam, params)
+        st = ctx.stats()
+        best = st.trace_kernel_ms if best is None else min(best, st.trace_kernel_ms)
+    return round(best, 3), zlib.crc32(frame.tobytes()), st
+
+
+if "--c3" in sys.argv:
+    import fullsize
+    spp = int(sys.argv[sys.argv.index("--spp") + 1]) if "--spp" in sys.argv else 256
+    scene, cam = fullsize.c3_scene(1920, 1080)
+    ctx.upload(scene)
+    ms, crc, st = timed(cam, abi.make_params(1920, 1080, mode=abi.MODE_PATHTRACE, spp=spp, max_depth=50, seed=1, flags=abi.FLAG_BVH), reps=2)
+    out.update(c3_spp=spp, c3_bvh_kernel_ms=ms, c3_crc=crc, c3_grays_s=round(st.rays / ms / 1e6, 3), c3_visits_per_ray=round(st.accel_node_visits / st.rays, 2))
+else:
+    scene, cam = scenes.rtiow_cover(1200, 800)
+    ctx.upload(scene)
+    ms, crc, st = timed(cam, abi.make_params(1200, 800, mode=abi.MODE_PATHTRACE, spp=500, max_depth=50, seed=1, tile_rows=2))
+    out.update(c2_sweep_kernel_ms=ms, c2_crc=crc, c2_grays_s=round(st.rays / ms / 1e6, 3))
+print(json.dumps(out), flush=True)

@@ -23,6 +23,9 @@
 #include "rt3_device.cuh"
 
 #define RT3_BVH_STACK 128 /* >= depth of a radix tree over 63-bit keys + index bits */
+#define RT3_BVH_OVERFLOW_BIT 0x80000000u /* in a thread's leaf-test counter: it had to drop a subtree */
+#define RT3_BIN_MAX_SPP 8u      /* ... when a call renders at most this many samples per pixel */
+#define RT3_BIN_MIN_FACES 1024u /* face trees at least this large get the binned traversal of the path tracer (rt3_kernels.cuh) */
 
 /* Two trees, one over the faces and one over the analytic spheres, walked one after the other with the closest hit
  * carried over. They differ in how far a box must be widened for a ray starting at o: the exact sphere test's
@@ -200,7 +203,7 @@ __device__ __forceinline__ bool bvh_slab(const rt3_bvh_ray& r, float lox, float 
  * read, `tests` exact tests run. */
 template <bool PATH_MODE>
 __device__ __forceinline__ void bvh_closest_hit(const rt3_scene_view& S, const rt3_bvh_view& B, rt3_vec3 o, rt3_vec3 d, rt3_hit& best,
-                                                uint32_t& visits, uint32_t& tests, unsigned long long* __restrict__ counters) {
+                                                uint32_t& visits, uint32_t& tests) {
     best.t = __int_as_float(0x7f800000);
     best.prim = RT3_NO_HIT;
     uint2 stack[RT3_BVH_STACK]; /* (subtree reference, its entry distance): one 8-byte local access per push / pop */
@@ -248,8 +251,11 @@ __device__ __forceinline__ void bvh_closest_hit(const rt3_scene_view& S, const r
             const int32_t c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
             if (h0 && h1) {
                 const bool first0 = t0 <= t1;
+                /* a full stack cannot happen for a radix tree over 63-bit keys + 31 index bits (depth <= 94 of 128); if it ever does, the top
+                 * bit of the thread's test counter remembers it (no branch, no atomic in this loop: an atomic here cost 40 % on C3),
+                 * count_accel reports it and the render fails (rt3_core.cu) instead of dropping the subtree silently */
                 if (sp < RT3_BVH_STACK) { stack[sp++] = make_uint2((uint32_t) (first0 ? c1 : c0), __float_as_uint(first0 ? t1 : t0)); }
-                else { atomicAdd(&counters[4], 1ull); } /* cannot happen for a radix tree over 63-bit keys + 31 index bits (depth <= 94); counted, and the render fails (rt3_core.cu) */
+                else { tests |= RT3_BVH_OVERFLOW_BIT; }
                 return first0 ? c0 : c1;
             }
             if (h0) { return c0; }

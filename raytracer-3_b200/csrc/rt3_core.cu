@@ -191,10 +191,10 @@ int launch_reference(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
     return RT3_OK;
 }
 
-template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL>
+template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL, int BIN = 0>
 int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp, size_t smem, cudaStream_t stream) {
     int per_sm = 0;
-    int rc = configure(pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL>, smem, &per_sm);
+    int rc = configure(pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL, BIN>, smem, &per_sm);
     if (rc != RT3_OK) { return rc; }
     if (ACCEL) {
         /* The traversal reads its node records through L1: ask for the smallest shared-memory carve-out that still
@@ -204,7 +204,7 @@ int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
         const size_t need = (size_t) per_sm * (smem + 1024);
         int percent = sm_bytes > 0 ? (int) ((need * 100 + (size_t) sm_bytes - 1) / (size_t) sm_bytes) : 100;
         if (percent > 100) { percent = 100; }
-        RT3_CUDA(cudaFuncSetAttribute(pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL>, cudaFuncAttributePreferredSharedMemoryCarveout, percent));
+        RT3_CUDA(cudaFuncSetAttribute(pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL, BIN>, cudaFuncAttributePreferredSharedMemoryCarveout, percent));
     }
     if (per_sm < 1) { return fail(RT3_ERR_CUDA, "pathtrace kernel does not fit on an SM (smem %zu)", smem); }
     if (const char* cap = getenv("RT3_MAX_CTAS_PER_SM")) { /* tuning knob: fewer persistent CTAs per SM than fit */
@@ -216,7 +216,7 @@ int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
     unsigned long long want = (kp.n_items + per_cta - 1) / per_cta;
     unsigned grid = (unsigned) ctx->sm_count * (unsigned) per_sm;
     if (want < grid) { grid = want ? (unsigned) want : 1u; }
-    pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, ctx->bvh, cam, kp, ctx->accum.ptr, ctx->counters.ptr);
+    pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL, BIN><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, ctx->bvh, cam, kp, ctx->accum.ptr, ctx->counters.ptr);
     RT3_CUDA(cudaGetLastError());
     return RT3_OK;
 }
@@ -387,7 +387,19 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     }
     RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
     const bool spheres_only = ctx->view.n_faces == 0;
-    rc = accel ? launch_pathtrace<true, false, true>(ctx, *cam, kp, smem, stream)
+    /* scenes with a real face tree sort their rays by whether they enter it (rt3_kernels.cuh traverse_slots_binned) */
+    int bin = 0;
+    if (accel && ctx->bvh.tree[0].n_prims >= RT3_BIN_MIN_FACES && ctx->bvh.tree[0].root >= 0) {
+        /* Measured on C3 (profiles/r02e_variants.jsonl; none / CTA-wide / per warp): 256 spp 365 / 399 / 343 ms, 16 spp 28.7 / 27.8 / 27.3,
+         * 4 spp 10.4 / 8.9 / 9.6. The CTA-wide sort pays when a warp's rays come from many pixels (few samples per pixel and call:
+         * interactive / progressive passes) and costs 9 % at 256 spp, where a warp's rays share a pixel and the barriers only cost;
+         * the per-warp sort needs no barrier and gains 5-8 % everywhere. */
+        bin = kp.spp <= RT3_BIN_MAX_SPP ? 1 : 2;
+        if (const char* e = getenv("RT3_BINNING")) { bin = atoi(e); } /* 0 none, 1 CTA-wide, 2 per warp: for A/B measurements */
+    }
+    rc = bin == 1 ? launch_pathtrace<true, false, true, 1>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES, stream)
+       : bin == 2 ? launch_pathtrace<true, false, true, 2>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES, stream)
+       : accel ? launch_pathtrace<true, false, true>(ctx, *cam, kp, smem, stream)
        : resident ? (spheres_only ? launch_pathtrace<true, true, false>(ctx, *cam, kp, smem, stream) : launch_pathtrace<true, false, false>(ctx, *cam, kp, smem, stream))
                   : (spheres_only ? launch_pathtrace<false, true, false>(ctx, *cam, kp, smem, stream) : launch_pathtrace<false, false, false>(ctx, *cam, kp, smem, stream));
     if (rc != RT3_OK) { return rc; }

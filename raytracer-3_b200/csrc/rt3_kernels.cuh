@@ -69,6 +69,8 @@ __host__ __device__ inline size_t rt3_smem_bytes(bool resident, bool path_slots)
 /* Hierarchy kernels keep no survivor masks: their shared memory is the path slots alone, which
  * leaves the rest of the SM's 256 KB to the L1 the node records are read through. */
 __host__ __device__ inline size_t rt3_accel_smem_bytes(bool path_slots) { return path_slots ? (size_t) RT3_SLOT_BYTES : 0; }
+/* ... plus, for the binned traversal, the sort scratch (rt3_bin_scratch, defined with the traversal below): one KB */
+#define RT3_BIN_SCRATCH_BYTES 1024
 
 template <bool RESIDENT, bool ACCEL = false, int MASK_BYTES = RT3_MASK_BYTES>
 __device__ __forceinline__ rt3_smem_view smem_view(unsigned char* base) {
@@ -249,22 +251,163 @@ __device__ __forceinline__ void sweep_slots(const rt3_scene_view& S, const rt3_s
 }
 
 /* Hierarchy traversal for every live slot (results in the slots' BEST fields). */
-__device__ __forceinline__ void traverse_slots(const rt3_scene_view& S, const rt3_bvh_view& B, const rt3_smem_view& sm, uint32_t& visits, uint32_t& tests,
-                                               unsigned long long* __restrict__ counters) {
+__device__ __forceinline__ void traverse_slots(const rt3_scene_view& S, const rt3_bvh_view& B, const rt3_smem_view& sm, uint32_t& visits, uint32_t& tests) {
 #pragma unroll 1
     for (int r = 0; r < RT3_RAYS; r++) {
         if (slot_word(sm, r, RT3_F_BOUNCE) == RT3_NO_HIT) { continue; }
         rt3_hit best;
-        bvh_closest_hit<true>(S, B, slot_vec(sm, r, RT3_F_OX), slot_vec(sm, r, RT3_F_DX), best, visits, tests, counters);
+        bvh_closest_hit<true>(S, B, slot_vec(sm, r, RT3_F_OX), slot_vec(sm, r, RT3_F_DX), best, visits, tests);
         slot_word(sm, r, RT3_F_BEST_T) = __float_as_uint(best.t); slot_word(sm, r, RT3_F_BEST_PRIM) = best.prim;
     }
 }
 
+/* ---- binned traversal (hierarchy kernels of scenes with a face tree) --------------------------------------------
+ * The average ray of a mesh-in-a-landscape scene (BASELINE C3) is cheap -- it misses the mesh's box and is done after
+ * two or three node visits -- while a ray that enters the mesh walks forty nodes; with every lane walking its own
+ * slot's ray, the few expensive rays of a warp keep it busy with a handful of lanes active (9 of 32 measured in
+ * round 1). Here the CTA sorts its 256 in-flight rays by that one bit before each traversal: the rays that enter the
+ * face tree's root box first, then the others; warps then take 32 consecutive rays of that order at a time
+ * ("passes", handed out by a shared counter), so the expensive rays travel together in few, full warps and the
+ * cheap ones in warps that finish at once. The bit is a scheduling hint only: results do not depend on it.
+ *
+ * Scratch shared memory behind the path slots: */
+struct rt3_bin_scratch {
+    float root_lo[3], root_hi[3];     /* box of the face tree's root (union of its two child boxes) */
+    uint32_t counts[RT3_CTA_THREADS / 32][4]; /* per warp: expensive rays in slot 0, slot 1; cheap rays in slot 0, slot 1 */
+    uint32_t next_pass;
+    uint32_t pad;
+    uint16_t order[RT3_RAYS * RT3_CTA_THREADS]; /* ray ids (slot * RT3_CTA_THREADS + thread), expensive first */
+};
+static_assert(sizeof(rt3_bin_scratch) <= RT3_BIN_SCRATCH_BYTES, "the sort scratch must fit its reservation");
+
+__device__ __forceinline__ uint32_t& slot_word_at(const rt3_smem_view& sm, uint32_t r, int field, uint32_t t) {
+    return sm.slots[(r * RT3_SLOT_FIELDS + field) * RT3_CTA_THREADS + t];
+}
+__device__ __forceinline__ rt3_vec3 slot_vec_at(const rt3_smem_view& sm, uint32_t r, int field, uint32_t t) {
+    return v3(__uint_as_float(slot_word_at(sm, r, field, t)), __uint_as_float(slot_word_at(sm, r, field + 1, t)), __uint_as_float(slot_word_at(sm, r, field + 2, t)));
+}
+
+/* Does the ray meet the box at all (t >= 0)? Plain slab test; NaNs (a direction component of 0 on a slab plane) count as a hit. */
+__device__ __forceinline__ bool ray_meets_box(rt3_vec3 o, rt3_vec3 d, const float* lo, const float* hi) {
+    const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+    const float x0 = (lo[0] - o.x) * ix, x1 = (hi[0] - o.x) * ix, y0 = (lo[1] - o.y) * iy, y1 = (hi[1] - o.y) * iy, z0 = (lo[2] - o.z) * iz, z1 = (hi[2] - o.z) * iz;
+    const float tin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+    const float tout = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+    return !(tin > tout * 1.0001f) && !(tout < 0.0f);
+}
+
+/* Thread 0 of the CTA, once per kernel. */
+__device__ __forceinline__ void bin_prologue(const rt3_bvh_view& B, rt3_bin_scratch* bin) {
+    if (threadIdx.x == 0) {
+        const int32_t root = B.tree[0].root;
+        const float4 n0 = __ldg(&B.nodes[4 * root + 0]), n1 = __ldg(&B.nodes[4 * root + 1]), n2 = __ldg(&B.nodes[4 * root + 2]);
+        /* fminf / fmaxf ignore the NaN boxes of primitives that can never be hit */
+        bin->root_lo[0] = fminf(n0.x, n1.z); bin->root_lo[1] = fminf(n0.y, n1.w); bin->root_lo[2] = fminf(n0.z, n2.x);
+        bin->root_hi[0] = fmaxf(n0.w, n2.y); bin->root_hi[1] = fmaxf(n1.x, n2.z); bin->root_hi[2] = fmaxf(n1.y, n2.w);
+        bin->next_pass = 0u;
+    }
+    __syncthreads();
+}
+
+/* One traversal step of the whole CTA: sort the in-flight rays, traverse them pass by pass, leave every closest hit in its
+ * slot. Returns false (for every thread of the CTA alike) when no slot of the CTA holds a ray any more. */
+__device__ __forceinline__ bool traverse_slots_binned(const rt3_scene_view& S, const rt3_bvh_view& B, const rt3_smem_view& sm, rt3_bin_scratch* bin,
+                                                      uint32_t& visits, uint32_t& tests) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lane_lt = (1u << lane) - 1u;
+    constexpr uint32_t WARPS = RT3_CTA_THREADS / 32;
+    static_assert(RT3_RAYS == 2, "the binned traversal is written for two slots per thread");
+    uint32_t heavy[RT3_RAYS], light[RT3_RAYS];
+#pragma unroll
+    for (int r = 0; r < RT3_RAYS; r++) {
+        const bool live = slot_word(sm, r, RT3_F_BOUNCE) != RT3_NO_HIT;
+        const bool meets = live && ray_meets_box(slot_vec(sm, r, RT3_F_OX), slot_vec(sm, r, RT3_F_DX), bin->root_lo, bin->root_hi);
+        heavy[r] = __ballot_sync(0xffffffffu, meets);
+        light[r] = __ballot_sync(0xffffffffu, live && !meets);
+    }
+    if (lane == 0) {
+        bin->counts[warp][0] = (uint32_t) __popc(heavy[0]); bin->counts[warp][1] = (uint32_t) __popc(heavy[1]);
+        bin->counts[warp][2] = (uint32_t) __popc(light[0]); bin->counts[warp][3] = (uint32_t) __popc(light[1]);
+    }
+    __syncthreads();
+    uint32_t n_heavy = 0, n_light = 0, heavy_before = 0, light_before = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < WARPS; w++) {
+        const uint32_t h = bin->counts[w][0] + bin->counts[w][1], l = bin->counts[w][2] + bin->counts[w][3];
+        if (w < warp) { heavy_before += h; light_before += l; }
+        n_heavy += h; n_light += l;
+    }
+    const uint32_t n_live = n_heavy + n_light;
+    if (n_live == 0u) { return false; }
+#pragma unroll
+    for (int r = 0; r < RT3_RAYS; r++) {
+        const uint32_t id = (uint32_t) r * RT3_CTA_THREADS + threadIdx.x;
+        if ((heavy[r] >> lane) & 1u) { bin->order[heavy_before + (r ? (uint32_t) __popc(heavy[0]) : 0u) + (uint32_t) __popc(heavy[r] & lane_lt)] = (uint16_t) id; }
+        if ((light[r] >> lane) & 1u) { bin->order[n_heavy + light_before + (r ? (uint32_t) __popc(light[0]) : 0u) + (uint32_t) __popc(light[r] & lane_lt)] = (uint16_t) id; }
+    }
+    __syncthreads();
+    for (;;) {
+        uint32_t pass = 0;
+        if (lane == 0) { pass = atomicAdd(&bin->next_pass, 1u); }
+        pass = __shfl_sync(0xffffffffu, pass, 0);
+        if (pass * 32u >= n_live) { break; }
+        const uint32_t idx = pass * 32u + lane;
+        if (idx < n_live) {
+            const uint32_t id = bin->order[idx], r = id / RT3_CTA_THREADS, t = id - r * RT3_CTA_THREADS;
+            rt3_hit best;
+            bvh_closest_hit<true>(S, B, slot_vec_at(sm, r, RT3_F_OX, t), slot_vec_at(sm, r, RT3_F_DX, t), best, visits, tests);
+            slot_word_at(sm, r, RT3_F_BEST_T, t) = __float_as_uint(best.t); slot_word_at(sm, r, RT3_F_BEST_PRIM, t) = best.prim;
+        }
+    }
+    __syncthreads(); /* every closest hit is in its slot before the owners shade; nobody is in the pass loop any more */
+    if (threadIdx.x == 0) { bin->next_pass = 0u; } /* ordered before the next pass loop by the two barriers in front of it */
+    return true;
+}
+
+/* The same idea without leaving the warp (no barriers): a warp sorts its own 64 in-flight rays, heavy first, and walks them in two
+ * passes of 32. Gains less than the CTA-wide sort (a warp's heavy rays only meet each other) but costs no synchronisation. */
+__device__ __forceinline__ void traverse_slots_warp_sorted(const rt3_scene_view& S, const rt3_bvh_view& B, const rt3_smem_view& sm, rt3_bin_scratch* bin,
+                                                           uint32_t& visits, uint32_t& tests) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lane_lt = (1u << lane) - 1u;
+    static_assert(RT3_RAYS == 2, "the sorted traversal is written for two slots per thread");
+    uint16_t* const order = bin->order + warp * (RT3_RAYS * 32u);
+    uint32_t heavy[RT3_RAYS], light[RT3_RAYS];
+#pragma unroll
+    for (int r = 0; r < RT3_RAYS; r++) {
+        const bool live = slot_word(sm, r, RT3_F_BOUNCE) != RT3_NO_HIT;
+        const bool meets = live && ray_meets_box(slot_vec(sm, r, RT3_F_OX), slot_vec(sm, r, RT3_F_DX), bin->root_lo, bin->root_hi);
+        heavy[r] = __ballot_sync(0xffffffffu, meets);
+        light[r] = __ballot_sync(0xffffffffu, live && !meets);
+    }
+    const uint32_t n_heavy = (uint32_t) (__popc(heavy[0]) + __popc(heavy[1])), n_live = n_heavy + (uint32_t) (__popc(light[0]) + __popc(light[1]));
+#pragma unroll
+    for (int r = 0; r < RT3_RAYS; r++) {
+        const uint32_t id = (uint32_t) r * RT3_CTA_THREADS + threadIdx.x;
+        if ((heavy[r] >> lane) & 1u) { order[(r ? (uint32_t) __popc(heavy[0]) : 0u) + (uint32_t) __popc(heavy[r] & lane_lt)] = (uint16_t) id; }
+        if ((light[r] >> lane) & 1u) { order[n_heavy + (r ? (uint32_t) __popc(light[0]) : 0u) + (uint32_t) __popc(light[r] & lane_lt)] = (uint16_t) id; }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t first = 0; first < n_live; first += 32u) {
+        const uint32_t idx = first + lane;
+        if (idx < n_live) {
+            const uint32_t id = order[idx], r = id / RT3_CTA_THREADS, t = id - r * RT3_CTA_THREADS;
+            rt3_hit best;
+            bvh_closest_hit<true>(S, B, slot_vec_at(sm, r, RT3_F_OX, t), slot_vec_at(sm, r, RT3_F_DX, t), best, visits, tests);
+            slot_word_at(sm, r, RT3_F_BEST_T, t) = __float_as_uint(best.t); slot_word_at(sm, r, RT3_F_BEST_PRIM, t) = best.prim;
+        }
+    }
+    __syncwarp(); /* closest hits are in their slots before the owners shade */
+}
+
 /* Adds a thread's traversal counters to the context's (one atomic pair per warp). */
 __device__ __forceinline__ void count_accel(uint32_t visits, uint32_t tests, unsigned long long* __restrict__ counters) {
-    unsigned long long v = visits, t = tests;
+    unsigned long long v = visits, t = tests & ~RT3_BVH_OVERFLOW_BIT;
+    const unsigned overflowed = __ballot_sync(0xffffffffu, (tests & RT3_BVH_OVERFLOW_BIT) != 0u);
     for (int off = 16; off > 0; off >>= 1) { v += __shfl_down_sync(0xffffffffu, v, off); t += __shfl_down_sync(0xffffffffu, t, off); }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&counters[2], v); atomicAdd(&counters[3], t); }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&counters[2], v); atomicAdd(&counters[3], t);
+        if (overflowed) { atomicAdd(&counters[4], (unsigned long long) __popc(overflowed)); }
+    }
 }
 
 #ifndef RT3_REF_CTAS_PER_SM
@@ -313,7 +456,7 @@ reference_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
 #pragma unroll
         for (int r = 0; r < R; r++) {
             best[r].t = __int_as_float(0x7f800000); best[r].prim = RT3_NO_HIT;
-            if (live[r]) { bvh_closest_hit<false>(S, B, o[r], d[r], best[r], visits, tests, counters); }
+            if (live[r]) { bvh_closest_hit<false>(S, B, o[r], d[r], best[r], visits, tests); }
         }
     } else {
         sweep_scene<false, RESIDENT, SPHERES_ONLY, R>(S, sm, phase, o, d, dn, live, best);
@@ -578,15 +721,18 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
 #ifndef RT3_ACCEL_CTAS_PER_SM
 #define RT3_ACCEL_CTAS_PER_SM RT3_CTAS_PER_SM
 #endif
-template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL>
+template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL, int BIN = 0>
 __global__ void __launch_bounds__(RT3_CTA_THREADS, ACCEL ? RT3_ACCEL_CTAS_PER_SM : RT3_CTAS_PER_SM)
 pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P, unsigned long long* __restrict__ accum,
                  unsigned long long* __restrict__ counters) {
     constexpr int R = RT3_RAYS;
+    static_assert(!BIN || ACCEL, "ray binning belongs to the hierarchy kernels");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const rt3_smem_view sm = smem_view<RESIDENT, ACCEL>(smem_raw);
     scene_prologue<RESIDENT>(sm);
     uint32_t phase = 0u;
+    rt3_bin_scratch* const bin = reinterpret_cast<rt3_bin_scratch*>(smem_raw + RT3_SLOT_BYTES); /* BIN only */
+    if (BIN) { bin_prologue(B, bin); }
 
     rt3_cam_view C;
     C.origin = v3(cam.origin[0], cam.origin[1], cam.origin[2]);
@@ -684,12 +830,18 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
             }
             __syncwarp();
         }
+        if (BIN == 1) {
+            /* the whole CTA traverses together (and leaves together) */
+            if (!traverse_slots_binned(S, B, sm, bin, visits, tests)) { break; }
+            continue;
+        }
         bool any = false;
 #pragma unroll
         for (int r = 0; r < R; r++) { any = any || slot_word(sm, r, RT3_F_BOUNCE) != RT3_NO_HIT; }
         if (RESIDENT) { if (!__any_sync(0xffffffffu, any)) { break; } }   /* warps run independently */
         else { if (!__syncthreads_or(any ? 1 : 0)) { break; } }           /* tiles are CTA-wide */
-        if (ACCEL) { traverse_slots(S, B, sm, visits, tests, counters); }
+        if (BIN == 2) { traverse_slots_warp_sorted(S, B, sm, bin, visits, tests); }
+        else if (ACCEL) { traverse_slots(S, B, sm, visits, tests); }
         else { sweep_slots<RESIDENT, SPHERES_ONLY>(S, sm, phase); }
     }
     for (int off = 16; off > 0; off >>= 1) { rays += __shfl_down_sync(0xffffffffu, rays, off); }
