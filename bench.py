@@ -29,7 +29,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, SPP, DEPTH, SEED, TILE_ROWS = 1200, 800, 500, 50, 1, 2
+W, H, SPP, DEPTH, SEED, TILE_ROWS = 1200, 800, 500, 50, 1, 1   # rows dealt one by one: halves the systematic cost offset between ranks
 FLOP_PER_SPHERE_TEST, FLOP_PER_FACE_TEST = 17, 45
 CPU_SAMPLE = dict(width=480, height=320, spp=48)    # bounded sample of the same workload for the CPU legs (~20 M ray segments)
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
@@ -418,6 +418,18 @@ def main():
         # executed (not credited) FP32 work and DRAM traffic: per-launch ncu counters of this exact workload, from the committed capture
         kernel_name = "pathtrace_kernel<1,0,1>" if args.bvh else "pathtrace_kernel<1,1,0>"
         prof, prof_src = profiled_counters(kernel_name, W, H, spp, DEPTH, scene.n_spheres, world)
+        share = 1.0
+        if not prof and world > 1:
+            # ncu is never run on a multi-rank command: take the one-GPU capture of the same frame and scale it by this rank's share of
+            # the ray segments (the work per ray segment does not depend on which GPU traces it; the accumulators scale with the rows)
+            prof, prof_src = profiled_counters(kernel_name, W, H, spp, DEPTH, scene.n_spheres, 1)
+            if prof and prof.get("rays_per_launch"):
+                share = st.rays / prof["rays_per_launch"]
+                prof = dict(prof, **{k: prof[k] * share for k in ("ffma_thread_inst", "ffma2_thread_inst", "fmul_thread_inst", "fadd_thread_inst",
+                                                                 "dram_bytes_read", "dram_bytes_write")})
+                prof_src += f" (one-GPU capture scaled by rank 0's share of the ray segments, {share:.4f}: ncu does not run on multi-rank commands)"
+            else:
+                prof = None
         executed_tflops = executed_frac = traffic = hbm = None
         executed_note = prof_src
         if prof:

@@ -519,15 +519,18 @@ struct rt3_chunk {
     uint32_t pixel0, sample0; /* item `start` = (pixel0, sample0) */
     bool dry;                 /* the global counter is exhausted */
 };
+/* (`start` doubles as the warp's last reading of the global counter: the value its previous claim returned.) */
 
 /* Items a warp takes from the global counter at a time: RT3_ITEM_CHUNK while there is plenty left, shrinking with
  * what remains (guided self-scheduling) so that the warps run dry together -- with the frame split over 8 GPUs
- * a kernel is only ~17 ms long and a fixed chunk of 256 items is a visible tail. `seen` is a (possibly stale)
- * reading of the counter; any value is correct, it only steers the size. */
+ * a kernel is only ~17 ms long and a fixed chunk of 256 items is a visible tail. `seen` is a stale reading of the
+ * counter (what the warp's previous claim returned: no extra load); any value is correct, it only steers the size. */
 __device__ __forceinline__ unsigned long long chunk_size(unsigned long long seen, const rt3_kparams& P) {
     const unsigned long long left = seen < P.n_items ? P.n_items - seen : 0ull;
-    const unsigned long long share = left / ((unsigned long long) gridDim.x * (RT3_CTA_THREADS / 32) * 2ull);
-    return share >= RT3_ITEM_CHUNK ? RT3_ITEM_CHUNK : (share <= RT3_ITEM_CHUNK_MIN ? RT3_ITEM_CHUNK_MIN : share);
+    const uint32_t claimers = gridDim.x * (RT3_CTA_THREADS / 32) * 2u;
+    if (left >= (unsigned long long) RT3_ITEM_CHUNK * claimers) { return RT3_ITEM_CHUNK; } /* the common case: no division */
+    const uint32_t share = (uint32_t) left / claimers;                                      /* left < 256 * claimers < 2^32 */
+    return share <= RT3_ITEM_CHUNK_MIN ? RT3_ITEM_CHUNK_MIN : share;
 }
 
 /* Warp-cooperative claim of one path item per requesting lane. Items are
@@ -543,7 +546,7 @@ __device__ __forceinline__ bool claim_item(bool want, rt3_chunk& c, const rt3_kp
         if (c.cur == c.end) {
             unsigned long long v = 0, size = 0;
             if (lane == 0) {
-                size = chunk_size(*(volatile unsigned long long*) next_item, P);
+                size = chunk_size(c.start, P);
                 v = atomicAdd(next_item, size);
             }
             v = __shfl_sync(0xffffffffu, v, 0);

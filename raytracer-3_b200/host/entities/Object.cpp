@@ -7,13 +7,17 @@
  * colour = colour * |n . (0,0,-1)|. Unlike the reference's loader it also
  * tolerates comments, blank lines, other record types and `f a/b/c` tokens
  * (the reference aborts on those, Object.cpp:100-102), and reads the file
- * once per call.
+ * ONCE per entity: create_object parses it to announce the sizes (reference
+ * Object.cpp:81-122) and keeps the records for the pre-render that follows,
+ * instead of parsing the file a second time there (reference Object.cpp:136-178).
  */
 #include <cerrno>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <limits>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include <CppDebugger.hpp>
@@ -43,6 +47,12 @@ namespace {
         return true;
     }
 
+    /* Records parsed by create_object, waiting for the entity's pre-render (entities are plain structs of the reference's layout, so
+     * the hand-over lives beside them). An entity that is deleted without ever being pre-rendered leaves its records here until
+     * the address is reused by the next create_object, which replaces them. */
+    std::mutex g_parsed_mutex;
+    std::unordered_map<const void*, std::vector<ObjRecord>> g_parsed;
+
     std::vector<ObjRecord> read_records(const std::string& path) {
         std::ifstream in(path);
         if (!in.is_open()) { DLOG(fatal, "Could not open file: " + std::string(std::strerror(errno))); }
@@ -66,15 +76,25 @@ ECS::Object* ECS::create_object(const std::string& file_path, const glm::vec3& c
     obj->scale = scale;
     obj->color = color;
     try {
-        for (const ObjRecord& rec : read_records(file_path)) {
+        std::vector<ObjRecord> records = read_records(file_path);
+        for (const ObjRecord& rec : records) {
             if (rec.kind == 'f') { ++obj->pre_render_faces; } else { ++obj->pre_render_vertices; }
         }
+        std::lock_guard<std::mutex> lock(g_parsed_mutex);
+        g_parsed[obj] = std::move(records);
     } catch (...) { delete obj; throw; }
     return obj;
 }
 
 void ECS::cpu_pre_render_object(Tools::Array<GFace>& faces_buffer, Tools::Array<glm::vec4>& vertex_buffer, Object* obj) {
-    const std::vector<ObjRecord> records = read_records(obj->file_path);
+    std::vector<ObjRecord> records;
+    bool parsed = false;
+    {
+        std::lock_guard<std::mutex> lock(g_parsed_mutex);
+        std::unordered_map<const void*, std::vector<ObjRecord>>::iterator it = g_parsed.find(obj);
+        if (it != g_parsed.end()) { records = std::move(it->second); g_parsed.erase(it); parsed = true; }
+    }
+    if (!parsed) { records = read_records(obj->file_path); } /* a second pre-render of the same entity */
     faces_buffer.resize(obj->pre_render_faces);
     vertex_buffer.resize(obj->pre_render_vertices);
     size_t n_faces = 0, n_vertices = 0;
