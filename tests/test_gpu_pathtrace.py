@@ -193,3 +193,32 @@ def test_radiance_aov_is_the_frame_before_gamma_and_pack(gpu_ctx):
     got = gpu_ctx.read_radiance(w, h)
     assert np.array_equal(got[mine], rgb[mine]) and not got[~mine].any()
     assert np.array_equal(part[mine], frame[mine])
+
+
+def test_accumulate_rejects_what_would_blend_different_renders(gpu_ctx):
+    """RT3_FLAG_ACCUMULATE only continues the render whose sums the accumulators hold: same scene upload, frame, partition, seed,
+    depth, and a sample range that starts where the accumulated one ended (round-1 advice: these were not checked)."""
+    w, h = 64, 36
+    scene, cam = scenes.rtiow_four_spheres(w, h)
+    gpu_ctx.upload(scene)
+    base = dict(mode=abi.MODE_PATHTRACE, max_depth=8, seed=5)
+    first = abi.make_params(w, h, spp=2, tile_rows=4, part_index=0, part_count=2, **base)
+
+    def cont(**kw):
+        args = dict(spp=2, first_sample=2, flags=abi.FLAG_ACCUMULATE, tile_rows=4, part_index=0, part_count=2, **base)
+        args.update(kw)
+        return abi.make_params(w, h, **args)
+
+    for bad, what in ((cont(part_index=1), "partition"), (cont(tile_rows=2), "partition"), (cont(first_sample=3), "first_sample"),
+                      (cont(first_sample=0), "first_sample"), (cont(seed=6), "seed"), (cont(max_depth=9), "seed, max_depth"),
+                      (cont(flags=abi.FLAG_ACCUMULATE | abi.FLAG_NO_JITTER), "sampling flags")):
+        gpu_ctx.render(cam, first)
+        with pytest.raises(abi.Rt3Error, match=what):
+            gpu_ctx.render(cam, bad)
+    gpu_ctx.render(cam, first)
+    gpu_ctx.render(cam, cont())                                   # the right continuation is accepted ...
+    gpu_ctx.render(cam, cont(first_sample=4, flags=abi.FLAG_ACCUMULATE | abi.FLAG_BVH))   # ... also through the hierarchy (same sums)
+    gpu_ctx.upload(scene)                                          # a new upload invalidates the accumulators
+    with pytest.raises(abi.Rt3Error, match="previous path-traced render"):
+        gpu_ctx.render(cam, cont(first_sample=6))
+    assert gpu_ctx.stats().accel_stack_overflows == 0
