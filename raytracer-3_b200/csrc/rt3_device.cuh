@@ -281,34 +281,61 @@ __device__ __forceinline__ void sweep_chunk(const float4* __restrict__ xy, const
         nz[r] = 0u;
     }
     uint32_t waddr = smem_u32(masks) + threadIdx.x * 4u; /* this thread's word 0 of ray 0 */
-    for (uint32_t done = 0; done < n_pairs; done += WORD_PAIRS, waddr += RT3_CTA_THREADS * 4u) {
-        uint32_t m[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) { m[r] = 0u; }
-        const uint32_t base = first_pair + done;
-        if (n_pairs - done >= WORD_PAIRS) {
-RT3_PRAGMA_UNROLL(RT3_UNROLL_PAIRS)
-            for (int j = 0; j < (int) WORD_PAIRS; j++) {
-                slab_pair<R>(CONST_BANK ? c_pair_xy[base + j] : xy[base + j], CONST_BANK ? c_pair_w[base + j] : w[base + j], u1, u2, nou2, m);
-            }
-        } else {
-            /* last, partial word of the scene */
-            const uint32_t left = n_pairs - done;
-            for (uint32_t g = 0; g < left; g += PAD_PAIRS) {
-#pragma unroll
-                for (int j = 0; j < (int) PAD_PAIRS; j++) {
-                    slab_pair<R>(CONST_BANK ? c_pair_xy[base + g + j] : xy[base + g + j], CONST_BANK ? c_pair_w[base + g + j] : w[base + g + j], u1, u2, nou2, m);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < R; r++) { m[r] <<= 32u - 2u * left; }
-        }
+    /* One mask word per ray out: the word goes to shared memory, its "not empty" bit into nz: nz = 2 nz + (m != 0), as the carry of
+     * m + 0xFFFFFFFF added into nz + nz -- two integer adds per ray (IADD3 with carry out, IADD3.X) where the compiler's own
+     * rendering of the C expression takes four. */
+    auto emit = [&](const uint32_t (&m)[R]) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(waddr + (uint32_t) (r * RT3_CHUNK_WORDS * RT3_CTA_THREADS * 4)), "r"(m[r]) : "memory");
-            nz[r] = (nz[r] << 1) + (m[r] < 1u ? m[r] : 1u);
+            asm("{ .reg .u32 t; add.cc.u32 t, %1, 0xFFFFFFFF; addc.u32 %0, %0, %0; }" : "+r"(nz[r]) : "r"(m[r])); /* nz = 2 nz + (m != 0) */
         }
+        waddr += RT3_CTA_THREADS * 4u;
+    };
+    /* full words first (no partial-word test inside the loop), then the last, partial word of the scene */
+    const uint32_t n_full = n_pairs / WORD_PAIRS;
+    uint32_t base = first_pair;
+    for (uint32_t wd = 0; wd < n_full; wd++, base += WORD_PAIRS) {
+        uint32_t m[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) { m[r] = 0u; }
+        if (CONST_BANK) {
+RT3_PRAGMA_UNROLL(RT3_UNROLL_PAIRS)
+            for (int j = 0; j < (int) WORD_PAIRS; j++) { slab_pair<R>(c_pair_xy[base + j], c_pair_w[base + j], u1, u2, nou2, m); }
+        } else {
+            /* shared-memory tiles: the -R^2 of two pairs in one 16-byte load (a word starts at an even pair of a 16-byte aligned tile);
+             * the constant bank gains nothing from this, ptxas feeds FFMA2 from LDCU.64 only */
+RT3_PRAGMA_UNROLL(RT3_UNROLL_PAIRS / 2)
+            for (int j = 0; j < (int) WORD_PAIRS; j += 2) {
+                const float4 W = *reinterpret_cast<const float4*>(w + base + j);
+                slab_pair<R>(xy[base + j], make_float2(W.x, W.y), u1, u2, nou2, m);
+                slab_pair<R>(xy[base + j + 1], make_float2(W.z, W.w), u1, u2, nou2, m);
+            }
+        }
+        emit(m);
     }
+    const uint32_t left = n_pairs - n_full * WORD_PAIRS;
+    if (left) {
+        uint32_t m[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) { m[r] = 0u; }
+        for (uint32_t g = 0; g < left; g += PAD_PAIRS) {
+#pragma unroll
+            for (int j = 0; j < (int) PAD_PAIRS; j++) {
+                slab_pair<R>(CONST_BANK ? c_pair_xy[base + g + j] : xy[base + g + j], CONST_BANK ? c_pair_w[base + g + j] : w[base + g + j], u1, u2, nou2, m);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) { m[r] <<= 32u - 2u * left; }
+        emit(m);
+    }
+}
+
+/* Index of the most significant set bit (x != 0): SASS FLO, without the 31 - x that __clz adds. */
+__device__ __forceinline__ uint32_t highest_bit(uint32_t x) {
+    uint32_t b;
+    asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(x));
+    return b;
 }
 
 /* Exact tests of one ray's level-1 survivors of a chunk, in ascending primitive
@@ -320,20 +347,20 @@ RT3_PRAGMA_UNROLL(RT3_UNROLL_PAIRS)
 template <bool PATH_MODE, bool SPHERES_ONLY>
 __device__ __forceinline__ void drain_chunk(const rt3_scene_view& S, uint32_t first_prim, uint32_t n_words, const rt3_ray_filter& f, rt3_vec3 o,
                                             rt3_vec3 d, const uint32_t* __restrict__ masks, uint32_t nz, rt3_hit& best) {
-    uint32_t m = 0u, word_prim = 0u;
+    uint32_t m = 0u, word_last = 0u; /* word_last: id of the word's LAST primitive (bit 0); bit b of a word is primitive word_last - b */
     const uint32_t maddr = smem_u32(masks);
     for (;;) {
         if (m == 0u) {
             if (nz == 0u) { break; }
-            const uint32_t b = 31u - (uint32_t) __clz((int) nz); /* highest bit = first non-empty word */
+            const uint32_t b = highest_bit(nz); /* highest bit = first non-empty word */
             nz ^= 1u << b;
             const uint32_t wd = n_words - 1u - b;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(maddr + wd * (RT3_CTA_THREADS * 4u)));
-            word_prim = first_prim + wd * RT3_WORD_PRIMS;
+            word_last = first_prim + wd * RT3_WORD_PRIMS + (RT3_WORD_PRIMS - 1u);
         }
-        const uint32_t k = (uint32_t) __clz((int) m);
-        m ^= 0x80000000u >> k;
-        const uint32_t prim = word_prim + k;
+        const uint32_t k = highest_bit(m);   /* bit 31 - j belongs to the word's j-th primitive: the highest bit is the lowest id */
+        m ^= 1u << k;
+        const uint32_t prim = word_last - k;
         if (SPHERES_ONLY || prim >= S.n_faces) {
             const float4 sp = __ldg(&S.spheres[SPHERES_ONLY ? prim : prim - S.n_faces]);
             if (PATH_MODE) { exact_sphere_path<true>(prim, sp, o, d, best); }
