@@ -331,13 +331,6 @@ RT3_PRAGMA_UNROLL(RT3_UNROLL_PAIRS / 2)
     }
 }
 
-/* Index of the most significant set bit (x != 0): SASS FLO, without the 31 - x that __clz adds. */
-__device__ __forceinline__ uint32_t highest_bit(uint32_t x) {
-    uint32_t b;
-    asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(x));
-    return b;
-}
-
 /* Exact tests of one ray's level-1 survivors of a chunk, in ascending primitive
  * order (words ascending, bits from the top), so the strict `t < best` rule
  * keeps the lowest index on ties exactly like the reference loop
@@ -347,20 +340,22 @@ __device__ __forceinline__ uint32_t highest_bit(uint32_t x) {
 template <bool PATH_MODE, bool SPHERES_ONLY>
 __device__ __forceinline__ void drain_chunk(const rt3_scene_view& S, uint32_t first_prim, uint32_t n_words, const rt3_ray_filter& f, rt3_vec3 o,
                                             rt3_vec3 d, const uint32_t* __restrict__ masks, uint32_t nz, rt3_hit& best) {
-    uint32_t m = 0u, word_last = 0u; /* word_last: id of the word's LAST primitive (bit 0); bit b of a word is primitive word_last - b */
+    uint32_t m = 0u, word_prim = 0u;
     const uint32_t maddr = smem_u32(masks);
+    /* (The bit walk is written with __clz. An inline-asm `bfind` would save the two 31 - x, but an asm statement here makes ptxas read
+     * the records of the sweep next to it with per-thread LDC instead of uniform LDCU -- tests/test_sass_evidence.py caught it.) */
     for (;;) {
         if (m == 0u) {
             if (nz == 0u) { break; }
-            const uint32_t b = highest_bit(nz); /* highest bit = first non-empty word */
+            const uint32_t b = 31u - (uint32_t) __clz((int) nz); /* highest bit = first non-empty word */
             nz ^= 1u << b;
             const uint32_t wd = n_words - 1u - b;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(maddr + wd * (RT3_CTA_THREADS * 4u)));
-            word_last = first_prim + wd * RT3_WORD_PRIMS + (RT3_WORD_PRIMS - 1u);
+            word_prim = first_prim + wd * RT3_WORD_PRIMS;
         }
-        const uint32_t k = highest_bit(m);   /* bit 31 - j belongs to the word's j-th primitive: the highest bit is the lowest id */
-        m ^= 1u << k;
-        const uint32_t prim = word_last - k;
+        const uint32_t k = (uint32_t) __clz((int) m);
+        m ^= 0x80000000u >> k;
+        const uint32_t prim = word_prim + k;
         if (SPHERES_ONLY || prim >= S.n_faces) {
             const float4 sp = __ldg(&S.spheres[SPHERES_ONLY ? prim : prim - S.n_faces]);
             if (PATH_MODE) { exact_sphere_path<true>(prim, sp, o, d, best); }
