@@ -99,7 +99,7 @@ struct rt3_ctx {
     bool has_scene = false;
     rt3_scene_view view{};
     uint64_t scene_id = 0; /* identifies the uploaded scene as owner of the constant-bank records */
-    DeviceBuffer<float4> pair_xy, filt3, face_n, face_p1, face_p2, face_p3, spheres, prim_color, materials;
+    DeviceBuffer<float4> pair_xy, filt3, face_rec, spheres, prim_color, materials;
     DeviceBuffer<float2> pair_w;
     DeviceBuffer<uint32_t> prim_material, prim_entity;
 
@@ -540,8 +540,7 @@ int build_scene_on_device(rt3_ctx* ctx, const rt3_scene& d) {
     const uint32_t np_pad = (np + RT3_PAD_PRIMS - 1) / RT3_PAD_PRIMS * RT3_PAD_PRIMS;
     int rc;
     auto at_least_one = [](size_t n) { return n ? n : (size_t) 1; };
-    if ((rc = ctx->face_n.reserve(at_least_one(nf))) != RT3_OK || (rc = ctx->face_p1.reserve(at_least_one(nf))) != RT3_OK ||
-        (rc = ctx->face_p2.reserve(at_least_one(nf))) != RT3_OK || (rc = ctx->face_p3.reserve(at_least_one(nf))) != RT3_OK ||
+    if ((rc = ctx->face_rec.reserve(at_least_one(4 * (size_t) nf))) != RT3_OK ||
         (rc = ctx->spheres.reserve(at_least_one(ns))) != RT3_OK || (rc = ctx->prim_color.reserve(at_least_one(np))) != RT3_OK ||
         (rc = ctx->prim_material.reserve(at_least_one(np))) != RT3_OK || (rc = ctx->prim_entity.reserve(at_least_one(np))) != RT3_OK ||
         (rc = ctx->prim_lo.reserve(at_least_one(np))) != RT3_OK || (rc = ctx->prim_hi.reserve(at_least_one(np))) != RT3_OK ||
@@ -567,7 +566,7 @@ int build_scene_on_device(rt3_ctx* ctx, const rt3_scene& d) {
     build_init_kernel<<<1, 1, 0, stream>>>(info.ptr);
     RT3_CUDA(cudaGetLastError());
     rt3_build_out out;
-    out.face_n = ctx->face_n.ptr; out.face_p1 = ctx->face_p1.ptr; out.face_p2 = ctx->face_p2.ptr; out.face_p3 = ctx->face_p3.ptr;
+    out.face_rec = ctx->face_rec.ptr;
     out.spheres = ctx->spheres.ptr; out.prim_color = ctx->prim_color.ptr; out.prim_lo = ctx->prim_lo.ptr; out.prim_hi = ctx->prim_hi.ptr;
     out.prim_material = ctx->prim_material.ptr; out.prim_entity = ctx->prim_entity.ptr; out.bounds = bounds.ptr; out.r2_keys = keys_in.ptr;
     if (nf) {
@@ -626,7 +625,7 @@ int build_scene_on_device(rt3_ctx* ctx, const rt3_scene& d) {
     ctx->scene_id = g_next_scene_id.fetch_add(1);
     v.n_faces = nf; v.n_spheres = ns; v.n_prims = np; v.n_prims_padded = np_pad;
     v.pair_xy = ctx->pair_xy.ptr; v.pair_w = ctx->pair_w.ptr; v.filt3 = ctx->filt3.ptr;
-    v.face_n = ctx->face_n.ptr; v.face_p1 = ctx->face_p1.ptr; v.face_p2 = ctx->face_p2.ptr; v.face_p3 = ctx->face_p3.ptr;
+    v.face_rec = ctx->face_rec.ptr;
     v.spheres = ctx->spheres.ptr; v.prim_color = ctx->prim_color.ptr;
     v.prim_material = ctx->prim_material.ptr; v.prim_entity = ctx->prim_entity.ptr; v.materials = ctx->materials.ptr;
     ctx->has_scene = true;
@@ -676,7 +675,7 @@ int rt3_destroy(rt3_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
     ctx->prim_lo.release(); ctx->prim_hi.release(); ctx->bvh_nodes.release();
-    ctx->pair_xy.release(); ctx->pair_w.release(); ctx->filt3.release(); ctx->face_n.release(); ctx->face_p1.release(); ctx->face_p2.release(); ctx->face_p3.release();
+    ctx->pair_xy.release(); ctx->pair_w.release(); ctx->filt3.release(); ctx->face_rec.release();
     ctx->spheres.release(); ctx->prim_color.release(); ctx->materials.release(); ctx->prim_material.release(); ctx->prim_entity.release();
     ctx->frame.release(); ctx->aov_prim.release(); ctx->aov_entity.release(); ctx->aov_t.release(); ctx->accum.release(); ctx->counters.release();
     if (ctx->ev_begin) { cudaEventDestroy(ctx->ev_begin); }

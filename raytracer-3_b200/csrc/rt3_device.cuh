@@ -101,10 +101,8 @@ struct rt3_scene_view {
     const float4* pair_xy;   /* per primitive PAIR (2j, 2j+1): (p1a, p1b, p2a, p2b) */
     const float2* pair_w;    /* per primitive pair: (wa, wb) */
     const float4* filt3;     /* per primitive: (p1, p2, p3, w), level 2 */
-    const float4* face_n;    /* per face: (nx, ny, nz, dot3(n, p1)) */
-    const float4* face_p1;   /* per face: p1.xyz */
-    const float4* face_p2;
-    const float4* face_p3;
+    const float4* face_rec;  /* per face one 64-byte record, 4 float4: (nx, ny, nz, dot3(n, p1)), p1.xyz, p2.xyz, p3.xyz -- everything the exact
+                              * test reads lies in two 32-byte sectors of one line (four separate arrays cost four lines per test) */
     const float4* spheres;   /* per sphere: (cx, cy, cz, r) */
     const float4* prim_color;     /* per primitive: flat colour / albedo */
     const uint32_t* prim_material; /* per primitive: index into materials, or RT3_NO_HIT for Lambertian(prim_color) */
@@ -186,11 +184,12 @@ __device__ __forceinline__ bool closer(float t, uint32_t prim, const rt3_hit& be
  * the reference (`t < 0` rejected); the bounce loop passes 0.001. */
 template <bool ORDERED>
 __device__ __forceinline__ void exact_face(const rt3_scene_view& S, uint32_t i, rt3_vec3 o, rt3_vec3 d, float tmin, rt3_hit& best) {
-    float4 fn = __ldg(&S.face_n[i]);
+    const float4* rec = S.face_rec + 4 * (size_t) i;
+    float4 fn = __ldg(&rec[0]);
     rt3_vec3 n = v3(fn.x, fn.y, fn.z);
     float nd = dot3(d, n);
     if (nd == 0) { return; }
-    float4 a1 = __ldg(&S.face_p1[i]), a2 = __ldg(&S.face_p2[i]), a3 = __ldg(&S.face_p3[i]);
+    float4 a1 = __ldg(&rec[1]), a2 = __ldg(&rec[2]), a3 = __ldg(&rec[3]);
     rt3_vec3 p1 = v3(a1.x, a1.y, a1.z), p2 = v3(a2.x, a2.y, a2.z), p3 = v3(a3.x, a3.y, a3.z);
     float pd = fn.w; /* dot3(n, p1), evaluated once at upload in the same order */
     float t = (pd - dot3(n, o)) / dot3(n, d);

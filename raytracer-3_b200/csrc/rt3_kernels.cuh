@@ -633,7 +633,7 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
         rt3_vec3 hp = s.o + best.t * dr;
         rt3_vec3 outward;
         if (prim < S.n_faces) {
-            float4 fn = __ldg(&S.face_n[prim]);
+            float4 fn = __ldg(&S.face_rec[4 * (size_t) prim]);
             outward = v3(fn.x, fn.y, fn.z);
         } else {
             float4 sp = __ldg(&S.spheres[prim - S.n_faces]);
@@ -722,7 +722,7 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
  * (the hit the last sweep found), then gives every free slot of the warp the next (pixel, sample) item,
  * so that all lanes sweep live rays, and (2) sweeps the scene for all slots. */
 #ifndef RT3_ACCEL_CTAS_PER_SM
-#define RT3_ACCEL_CTAS_PER_SM RT3_CTAS_PER_SM
+#define RT3_ACCEL_CTAS_PER_SM 6 /* register cap 85: the traversal kernels need 77-79 and keep six CTAs per SM (without the cap ptxas drifts to 87 and five) */
 #endif
 template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL, int BIN = 0>
 __global__ void __launch_bounds__(RT3_CTA_THREADS, ACCEL ? RT3_ACCEL_CTAS_PER_SM : RT3_CTAS_PER_SM)

@@ -8,7 +8,7 @@
  * where they lie in HBM, so that a scene tessellated on the device (rt3_scene.cuh) never visits the host,
  * and a host scene costs one copy per input array and nothing per primitive on the CPU.
  *
- *   faces_kernel / spheres_kernel : one thread per primitive -> exact-test arrays (face_n with the plane offset in
+ *   faces_kernel / spheres_kernel : one thread per primitive -> exact-test arrays (face records with the plane offset in
  *                                   the reference's operation order, p1..p3, spheres), colour / material / entity,
  *                                   bounding sphere (double), box, validation (first error in input order wins)
  *   (CUB radix sort of the R^2 keys)  -> median and minimum of the bounding radii
@@ -103,7 +103,7 @@ __device__ __forceinline__ void triangle_bound_dev(const double a[3], const doub
 }
 
 struct rt3_build_out {
-    float4 *face_n, *face_p1, *face_p2, *face_p3, *spheres, *prim_color, *prim_lo, *prim_hi;
+    float4 *face_rec, *spheres, *prim_color, *prim_lo, *prim_hi;
     uint32_t *prim_material, *prim_entity;
     rt3_bound* bounds;
     float* r2_keys; /* (float) R^2, +inf for primitives that can never be hit: sorted for the median */
@@ -131,10 +131,11 @@ __global__ void build_faces_kernel(uint32_t n_faces, uint32_t n_vertices, const 
     const float4 a = vertices[idx.x], b = vertices[idx.y], c = vertices[idx.z];
     /* plane offset dot3(n, p1) in the reference's order (SequentialRenderer.cpp:32-33,67); this unit is built without contraction */
     const float pd = (nx * a.x + ny * a.y) + nz * a.z;
-    o.face_n[i] = make_float4(nx, ny, nz, pd);
-    o.face_p1[i] = make_float4(a.x, a.y, a.z, 0.f);
-    o.face_p2[i] = make_float4(b.x, b.y, b.z, 0.f);
-    o.face_p3[i] = make_float4(c.x, c.y, c.z, 0.f);
+    float4* rec = o.face_rec + 4 * (size_t) i;
+    rec[0] = make_float4(nx, ny, nz, pd);
+    rec[1] = make_float4(a.x, a.y, a.z, 0.f);
+    rec[2] = make_float4(b.x, b.y, b.z, 0.f);
+    rec[3] = make_float4(c.x, c.y, c.z, 0.f);
     const double da[3] = { a.x, a.y, a.z }, db[3] = { b.x, b.y, b.z }, dc[3] = { c.x, c.y, c.z };
     double centre[3], radius;
     triangle_bound_dev(da, db, dc, centre, &radius);
