@@ -318,6 +318,23 @@ int claim_constant_bank(rt3_ctx* ctx, cudaStream_t stream, std::unique_lock<std:
 int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params, const rt3_kparams& kp_in, uint32_t* device_frame,
                    uint32_t* prim, uint32_t* ent, float* t, cudaStream_t stream) {
     rt3_kparams kp = kp_in;
+    if (params->mode == RT3_MODE_PATHTRACE && (params->flags & RT3_FLAG_ACCUMULATE)) {
+        /* checked before anything of the previous render (its statistics, its events) is touched */
+        const rt3_kparams& prev = ctx->accum_kp;
+        if (!ctx->accum_valid || ctx->accum_width != kp.width || ctx->accum_height != kp.height || !ctx->accum.ptr) {
+            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE needs a previous path-traced render of the same %ux%u frame and scene on this context", kp.width, kp.height);
+        }
+        if (prev.tile_rows != kp.tile_rows || prev.part_index != kp.part_index || prev.part_count != kp.part_count) {
+            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE: partition (tile_rows %u, part %u of %u) differs from the accumulated render's (%u, %u of %u)",
+                        kp.tile_rows, kp.part_index, kp.part_count, prev.tile_rows, prev.part_index, prev.part_count);
+        }
+        if (prev.seed != kp.seed || prev.max_depth != kp.max_depth || ((prev.flags ^ kp.flags) & ~(RT3_FLAG_ACCUMULATE | RT3_FLAG_BVH | RT3_FLAG_NO_GAMMA))) {
+            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE: seed, max_depth and sampling flags must be those of the accumulated render");
+        }
+        if (kp.first_sample != prev.first_sample + prev.spp) {
+            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE: first_sample must continue the accumulated range (expected %u, got %u)", prev.first_sample + prev.spp, kp.first_sample);
+        }
+    }
     bool resident = false;
     size_t smem = render_smem_bytes(ctx->view, params->mode == RT3_MODE_PATHTRACE, &resident);
     const bool accel = (params->flags & RT3_FLAG_BVH) != 0;
@@ -361,22 +378,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     }
     size_t n_acc = (size_t) kp.width * kp.height * 3;
     const bool accumulate = (params->flags & RT3_FLAG_ACCUMULATE) != 0;
-    if (accumulate) {
-        const rt3_kparams& prev = ctx->accum_kp;
-        if (!ctx->accum_valid || ctx->accum_width != kp.width || ctx->accum_height != kp.height || !ctx->accum.ptr) {
-            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE needs a previous path-traced render of the same %ux%u frame and scene on this context", kp.width, kp.height);
-        }
-        if (prev.tile_rows != kp.tile_rows || prev.part_index != kp.part_index || prev.part_count != kp.part_count) {
-            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE: partition (tile_rows %u, part %u of %u) differs from the accumulated render's (%u, %u of %u)",
-                        kp.tile_rows, kp.part_index, kp.part_count, prev.tile_rows, prev.part_index, prev.part_count);
-        }
-        if (prev.seed != kp.seed || prev.max_depth != kp.max_depth || ((prev.flags ^ kp.flags) & ~(RT3_FLAG_ACCUMULATE | RT3_FLAG_BVH | RT3_FLAG_NO_GAMMA))) {
-            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE: seed, max_depth and sampling flags must be those of the accumulated render");
-        }
-        if (kp.first_sample != prev.first_sample + prev.spp) {
-            return fail(RT3_ERR_INVALID, "RT3_FLAG_ACCUMULATE: first_sample must continue the accumulated range (expected %u, got %u)", prev.first_sample + prev.spp, kp.first_sample);
-        }
-    } else {
+    if (!accumulate) {
         ctx->accum_valid = false;
         rc = ctx->accum.reserve(n_acc);
         if (rc != RT3_OK) { return rc; }
