@@ -242,6 +242,7 @@ __device__ __forceinline__ void bvh_closest_hit(const rt3_scene_view& S, const r
         /* one node record: both child boxes against the ray; returns the subtree to enter next, stacks the farther one */
         auto visit = [&](int32_t node) -> int32_t {
             visits++;
+            RT3_ASSERT(node >= 0 && (uint32_t) node + 2u <= B.tree[0].n_prims + B.tree[1].n_prims); /* n - 1 nodes per tree */
             const float4 n0 = __ldg(&B.nodes[4 * node + 0]), n1 = __ldg(&B.nodes[4 * node + 1]), n2 = __ldg(&B.nodes[4 * node + 2]),
                          n3 = __ldg(&B.nodes[4 * node + 3]);
             const float limit = best.t * RT3_BVH_ROBUST;
@@ -264,6 +265,7 @@ __device__ __forceinline__ void bvh_closest_hit(const rt3_scene_view& S, const r
         };
         auto test = [&](int32_t leaf) {
             const uint32_t prim = (uint32_t) ~leaf;
+            RT3_ASSERT(prim < S.n_prims);
             tests++;
             if (prim < S.n_faces) {
                 exact_face<false>(S, prim, o, d, PATH_MODE ? RT3_TMIN : 0.0f, best);

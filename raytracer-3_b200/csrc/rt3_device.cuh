@@ -17,6 +17,15 @@
 #include "rt3cuda.h"
 #include "rt3_rng.h"
 
+/* -DRT3_DEBUG_ASSERTS: device-side index checks at every data-dependent array access of the render kernels (compute-sanitizer is
+ * closed on the B200 pool, so the bounds are checked by the code itself: profiles/sanitize_probe.py runs this build). */
+#ifdef RT3_DEBUG_ASSERTS
+#include <assert.h>
+#define RT3_ASSERT(cond) assert(cond)
+#else
+#define RT3_ASSERT(cond) ((void) 0)
+#endif
+
 #define RT3_NO_HIT 0xFFFFFFFFu
 #define RT3_TMIN 0.001f
 #define RT3_ACC_SCALE 16777216.0f
@@ -184,6 +193,7 @@ __device__ __forceinline__ bool closer(float t, uint32_t prim, const rt3_hit& be
  * the reference (`t < 0` rejected); the bounce loop passes 0.001. */
 template <bool ORDERED>
 __device__ __forceinline__ void exact_face(const rt3_scene_view& S, uint32_t i, rt3_vec3 o, rt3_vec3 d, float tmin, rt3_hit& best) {
+    RT3_ASSERT(i < S.n_faces);
     const float4* rec = S.face_rec + 4 * (size_t) i;
     float4 fn = __ldg(&rec[0]);
     rt3_vec3 n = v3(fn.x, fn.y, fn.z);
@@ -342,12 +352,14 @@ __device__ __forceinline__ void drain_chunk(const rt3_scene_view& S, uint32_t fi
             const uint32_t b = 31u - (uint32_t) __clz((int) nz); /* highest bit = first non-empty word */
             nz ^= 1u << b;
             const uint32_t wd = n_words - 1u - b;
+            RT3_ASSERT(b < n_words && n_words <= RT3_CHUNK_WORDS);
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(maddr + wd * (RT3_CTA_THREADS * 4u)));
             word_prim = first_prim + wd * RT3_WORD_PRIMS;
         }
         const uint32_t k = (uint32_t) __clz((int) m);
         m ^= 0x80000000u >> k;
         const uint32_t prim = word_prim + k;
+        RT3_ASSERT(prim < S.n_prims); /* padding records never survive level 1 */
         if (SPHERES_ONLY || prim >= S.n_faces) {
             const float4 sp = __ldg(&S.spheres[SPHERES_ONLY ? prim : prim - S.n_faces]);
             if (PATH_MODE) { exact_sphere_path<true>(prim, sp, o, d, best); }

@@ -341,8 +341,12 @@ __device__ __forceinline__ bool traverse_slots_binned(const rt3_scene_view& S, c
 #pragma unroll
     for (int r = 0; r < RT3_RAYS; r++) {
         const uint32_t id = (uint32_t) r * RT3_CTA_THREADS + threadIdx.x;
-        if ((heavy[r] >> lane) & 1u) { bin->order[heavy_before + (r ? (uint32_t) __popc(heavy[0]) : 0u) + (uint32_t) __popc(heavy[r] & lane_lt)] = (uint16_t) id; }
-        if ((light[r] >> lane) & 1u) { bin->order[n_heavy + light_before + (r ? (uint32_t) __popc(light[0]) : 0u) + (uint32_t) __popc(light[r] & lane_lt)] = (uint16_t) id; }
+        const uint32_t at_heavy = heavy_before + (r ? (uint32_t) __popc(heavy[0]) : 0u) + (uint32_t) __popc(heavy[r] & lane_lt);
+        const uint32_t at_light = n_heavy + light_before + (r ? (uint32_t) __popc(light[0]) : 0u) + (uint32_t) __popc(light[r] & lane_lt);
+        RT3_ASSERT(!((heavy[r] >> lane) & 1u) || at_heavy < n_heavy);
+        RT3_ASSERT(!((light[r] >> lane) & 1u) || (at_light >= n_heavy && at_light < n_live));
+        if ((heavy[r] >> lane) & 1u) { bin->order[at_heavy] = (uint16_t) id; }
+        if ((light[r] >> lane) & 1u) { bin->order[at_light] = (uint16_t) id; }
     }
     __syncthreads();
     for (;;) {
@@ -353,6 +357,7 @@ __device__ __forceinline__ bool traverse_slots_binned(const rt3_scene_view& S, c
         const uint32_t idx = pass * 32u + lane;
         if (idx < n_live) {
             const uint32_t id = bin->order[idx], r = id / RT3_CTA_THREADS, t = id - r * RT3_CTA_THREADS;
+            RT3_ASSERT(r < RT3_RAYS && slot_word_at(sm, r, RT3_F_BOUNCE, t) != RT3_NO_HIT);
             rt3_hit best;
             bvh_closest_hit<true>(S, B, slot_vec_at(sm, r, RT3_F_OX, t), slot_vec_at(sm, r, RT3_F_DX, t), best, visits, tests);
             slot_word_at(sm, r, RT3_F_BEST_T, t) = __float_as_uint(best.t); slot_word_at(sm, r, RT3_F_BEST_PRIM, t) = best.prim;
@@ -391,6 +396,7 @@ __device__ __forceinline__ void traverse_slots_warp_sorted(const rt3_scene_view&
         const uint32_t idx = first + lane;
         if (idx < n_live) {
             const uint32_t id = order[idx], r = id / RT3_CTA_THREADS, t = id - r * RT3_CTA_THREADS;
+            RT3_ASSERT(r < RT3_RAYS && (t >> 5) == warp && slot_word_at(sm, r, RT3_F_BOUNCE, t) != RT3_NO_HIT);
             rt3_hit best;
             bvh_closest_hit<true>(S, B, slot_vec_at(sm, r, RT3_F_OX, t), slot_vec_at(sm, r, RT3_F_DX, t), best, visits, tests);
             slot_word_at(sm, r, RT3_F_BEST_T, t) = __float_as_uint(best.t); slot_word_at(sm, r, RT3_F_BEST_PRIM, t) = best.prim;
@@ -630,6 +636,7 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
         done = true;
     } else {
         const uint32_t prim = best.prim;
+        RT3_ASSERT(prim < S.n_prims);
         rt3_vec3 hp = s.o + best.t * dr;
         rt3_vec3 outward;
         if (prim < S.n_faces) {
@@ -709,6 +716,7 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
     }
     if (done) {
         unsigned long long qx = to_fixed(L.x), qy = to_fixed(L.y), qz = to_fixed(L.z);
+        RT3_ASSERT(s.pix < P.width * P.height);
         unsigned long long* acc = accum + 3 * (size_t) s.pix;
         if (qx) { atomicAdd(acc + 0, qx); }
         if (qy) { atomicAdd(acc + 1, qy); }
