@@ -250,6 +250,58 @@ __device__ __forceinline__ void sweep_slots(const rt3_scene_view& S, const rt3_s
     }
 }
 
+/* Any slot of the CTA, not just the calling thread's: */
+__device__ __forceinline__ uint32_t& slot_word_at(const rt3_smem_view& sm, uint32_t r, int field, uint32_t t) {
+    return sm.slots[(r * RT3_SLOT_FIELDS + field) * RT3_CTA_THREADS + t];
+}
+__device__ __forceinline__ rt3_vec3 slot_vec_at(const rt3_smem_view& sm, uint32_t r, int field, uint32_t t) {
+    return v3(__uint_as_float(slot_word_at(sm, r, field, t)), __uint_as_float(slot_word_at(sm, r, field + 1, t)), __uint_as_float(slot_word_at(sm, r, field + 2, t)));
+}
+
+/* The tail of a frame. When the item counter has run dry a warp keeps sweeping for its last few paths, and a sweep costs the same
+ * whether 64 or 3 of its slots hold a ray (level 1 alone is 1 600 warp instructions per slot pair): the last generation of paths
+ * of a frame has members 25-30 segments long, so every frame ends with ~0.5 ms of nearly empty sweeps -- 0.4 % of a one-GPU
+ * frame, 3 % of an eighth of it. With at most RT3_TAIL_RAYS rays left, the warp turns the loop inside out: one ray at a time, the
+ * 32 lanes share the PRIMITIVES (lane l tests l, l + 32, ... with the exact tests, no prefilter) and a shuffle reduction picks the
+ * closest hit, ties to the lower id like everywhere else. Same exact tests, same rule: same result bit for bit. */
+#ifndef RT3_TAIL_RAYS
+#define RT3_TAIL_RAYS 8
+#endif
+/* Slots of this warp that hold a ray (the same number in every lane). */
+__device__ __forceinline__ uint32_t warp_live_slots(const rt3_smem_view& sm) {
+    uint32_t n = 0;
+#pragma unroll
+    for (int r = 0; r < RT3_RAYS; r++) { n += (uint32_t) __popc(__ballot_sync(0xffffffffu, slot_word(sm, r, RT3_F_BOUNCE) != RT3_NO_HIT)); }
+    return n;
+}
+
+__device__ __noinline__ void sweep_slots_by_primitive(const rt3_scene_view& S, const rt3_smem_view& sm) {
+    const uint32_t lane = threadIdx.x & 31u, column0 = threadIdx.x & ~31u;
+#pragma unroll 1
+    for (uint32_t r = 0; r < RT3_RAYS; r++) {
+        uint32_t todo = __ballot_sync(0xffffffffu, slot_word(sm, r, RT3_F_BOUNCE) != RT3_NO_HIT);
+        while (todo) {
+            const uint32_t t = column0 + (uint32_t) __ffs((int) todo) - 1u; /* the owner's column: every lane reads the same words (broadcast) */
+            todo &= todo - 1u;
+            const rt3_vec3 o = slot_vec_at(sm, r, RT3_F_OX, t), d = slot_vec_at(sm, r, RT3_F_DX, t);
+            rt3_hit best;
+            best.t = __int_as_float(0x7f800000); best.prim = RT3_NO_HIT;
+            for (uint32_t prim = lane; prim < S.n_prims; prim += 32u) {
+                if (prim < S.n_faces) { exact_face<false>(S, prim, o, d, RT3_TMIN, best); }
+                else { exact_sphere_path<false>(prim, __ldg(&S.spheres[prim - S.n_faces]), o, d, best); }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                rt3_hit other;
+                other.t = __shfl_xor_sync(0xffffffffu, best.t, off); other.prim = __shfl_xor_sync(0xffffffffu, best.prim, off);
+                if (other.prim != RT3_NO_HIT && closer<false>(other.t, other.prim, best)) { best = other; }
+            }
+            if (lane == 0) { slot_word_at(sm, r, RT3_F_BEST_T, t) = __float_as_uint(best.t); slot_word_at(sm, r, RT3_F_BEST_PRIM, t) = best.prim; }
+        }
+    }
+    __syncwarp();
+}
+
 /* Hierarchy traversal for every live slot (results in the slots' BEST fields). */
 __device__ __forceinline__ void traverse_slots(const rt3_scene_view& S, const rt3_bvh_view& B, const rt3_smem_view& sm, uint32_t& visits, uint32_t& tests) {
 #pragma unroll 1
@@ -280,12 +332,6 @@ struct rt3_bin_scratch {
 };
 static_assert(sizeof(rt3_bin_scratch) <= RT3_BIN_SCRATCH_BYTES, "the sort scratch must fit its reservation");
 
-__device__ __forceinline__ uint32_t& slot_word_at(const rt3_smem_view& sm, uint32_t r, int field, uint32_t t) {
-    return sm.slots[(r * RT3_SLOT_FIELDS + field) * RT3_CTA_THREADS + t];
-}
-__device__ __forceinline__ rt3_vec3 slot_vec_at(const rt3_smem_view& sm, uint32_t r, int field, uint32_t t) {
-    return v3(__uint_as_float(slot_word_at(sm, r, field, t)), __uint_as_float(slot_word_at(sm, r, field + 1, t)), __uint_as_float(slot_word_at(sm, r, field + 2, t)));
-}
 
 /* Does the ray meet the box at all (t >= 0)? Plain slab test; NaNs (a direction component of 0 on a slab plane) count as a hit. */
 __device__ __forceinline__ bool ray_meets_box(rt3_vec3 o, rt3_vec3 d, const float* lo, const float* hi) {
@@ -853,6 +899,7 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
         else { if (!__syncthreads_or(any ? 1 : 0)) { break; } }           /* tiles are CTA-wide */
         if (BIN == 2) { traverse_slots_warp_sorted(S, B, sm, bin, visits, tests); }
         else if (ACCEL) { traverse_slots(S, B, sm, visits, tests); }
+        else if (RESIDENT && chunk.dry && warp_live_slots(sm) <= RT3_TAIL_RAYS) { sweep_slots_by_primitive(S, sm); } /* warp-uniform */
         else { sweep_slots<RESIDENT, SPHERES_ONLY>(S, sm, phase); }
     }
     for (int off = 16; off > 0; off >>= 1) { rays += __shfl_down_sync(0xffffffffu, rays, off); }

@@ -46,9 +46,10 @@ def test_constant_bank_sweep_uses_packed_fma_with_uniform_operands(sass, needles
     ldc64 = sum(op == "LDC.64" for op in ops)
     assert ffma2 >= 96, f"{ffma2} FFMA2"                      # 16 pairs x 2 rays x 3 in the unrolled word (+ the partial-word loop)
     assert ldcu64 >= 48, f"only {ldcu64} LDCU.64 ({ldc64} LDC.64): the records are no longer read through uniform registers"
-    # kernel parameters (camera, pointers) are read with a few per-thread LDC.64 outside the sweep: a dozen in the path tracer, a few
-    # more in the reference-mode kernel with its four rays per thread; a sweep that fell back to LDC would show 48 or more
-    assert ldc64 < 24, f"{ldc64} LDC.64: per-thread constant loads in the sweep"
+    # kernel parameters (camera, pointers) are read with per-thread LDC.64 outside the sweep: a dozen in the path tracer plus as many in
+    # its out-of-line tail routine (sweep_slots_by_primitive), a few more in the reference-mode kernel; a sweep that fell back to LDC
+    # shows 60 or more (and hardly any LDCU.64, which the assertion above catches first)
+    assert ldc64 < 40, f"{ldc64} LDC.64: per-thread constant loads in the sweep"
     assert sum(op.startswith("SHF.L.W") for op in ops) >= 64  # sign bits into the survivor masks
 
 
