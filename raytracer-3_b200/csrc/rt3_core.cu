@@ -395,12 +395,14 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
         /* Measured on C3 (profiles/r02e_variants.jsonl; none / CTA-wide / per warp): 256 spp 365 / 399 / 343 ms, 16 spp 28.7 / 27.8 / 27.3,
          * 4 spp 10.4 / 8.9 / 9.6. The CTA-wide sort pays when a warp's rays come from many pixels (few samples per pixel and call:
          * interactive / progressive passes) and costs 9 % at 256 spp, where a warp's rays share a pixel and the barriers only cost;
-         * the per-warp sort needs no barrier and gains 5-8 % everywhere. */
-        bin = kp.spp <= RT3_BIN_MAX_SPP ? 1 : 2;
-        if (const char* e = getenv("RT3_BINNING")) { bin = atoi(e); } /* 0 none, 1 CTA-wide, 2 per warp: for A/B measurements */
+         * the per-warp sort needs no barrier and gains 5-8 % everywhere; with a third class in front (rays that START inside the root box:
+         * bounces off the mesh) another 2.5-4 % (profiles/r02x_variants.jsonl: 256 spp 333.8 -> 325.3 ms, 16 spp 25.9 -> 24.8). */
+        bin = kp.spp <= RT3_BIN_MAX_SPP ? 1 : 3;
+        if (const char* e = getenv("RT3_BINNING")) { bin = atoi(e); } /* 0 none, 1 CTA-wide, 2 / 3 per warp with two / three classes: for A/B measurements */
     }
     rc = bin == 1 ? launch_pathtrace<true, false, true, 1>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES, stream)
        : bin == 2 ? launch_pathtrace<true, false, true, 2>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES, stream)
+       : bin == 3 ? launch_pathtrace<true, false, true, 3>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES, stream)
        : accel ? launch_pathtrace<true, false, true>(ctx, *cam, kp, smem, stream)
        : resident ? (spheres_only ? launch_pathtrace<true, true, false>(ctx, *cam, kp, smem, stream) : launch_pathtrace<true, false, false>(ctx, *cam, kp, smem, stream))
                   : (spheres_only ? launch_pathtrace<false, true, false>(ctx, *cam, kp, smem, stream) : launch_pathtrace<false, false, false>(ctx, *cam, kp, smem, stream));

@@ -416,24 +416,31 @@ __device__ __forceinline__ bool traverse_slots_binned(const rt3_scene_view& S, c
 
 /* The same idea without leaving the warp (no barriers): a warp sorts its own 64 in-flight rays, heavy first, and walks them in two
  * passes of 32. Gains less than the CTA-wide sort (a warp's heavy rays only meet each other) but costs no synchronisation. */
+template <bool THREE_CLASSES>
 __device__ __forceinline__ void traverse_slots_warp_sorted(const rt3_scene_view& S, const rt3_bvh_view& B, const rt3_smem_view& sm, rt3_bin_scratch* bin,
                                                            uint32_t& visits, uint32_t& tests) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lane_lt = (1u << lane) - 1u;
     static_assert(RT3_RAYS == 2, "the sorted traversal is written for two slots per thread");
     uint16_t* const order = bin->order + warp * (RT3_RAYS * 32u);
-    uint32_t heavy[RT3_RAYS], light[RT3_RAYS];
+    uint32_t inside[RT3_RAYS], heavy[RT3_RAYS], light[RT3_RAYS]; /* THREE_CLASSES: rays that start inside the root box go first, ahead of those that enter it */
 #pragma unroll
     for (int r = 0; r < RT3_RAYS; r++) {
         const bool live = slot_word(sm, r, RT3_F_BOUNCE) != RT3_NO_HIT;
-        const bool meets = live && ray_meets_box(slot_vec(sm, r, RT3_F_OX), slot_vec(sm, r, RT3_F_DX), bin->root_lo, bin->root_hi);
-        heavy[r] = __ballot_sync(0xffffffffu, meets);
+        const rt3_vec3 o = slot_vec(sm, r, RT3_F_OX);
+        const bool meets = live && ray_meets_box(o, slot_vec(sm, r, RT3_F_DX), bin->root_lo, bin->root_hi);
+        const bool in = THREE_CLASSES && meets && o.x >= bin->root_lo[0] && o.x <= bin->root_hi[0] && o.y >= bin->root_lo[1] && o.y <= bin->root_hi[1] &&
+                        o.z >= bin->root_lo[2] && o.z <= bin->root_hi[2];
+        inside[r] = __ballot_sync(0xffffffffu, in);
+        heavy[r] = __ballot_sync(0xffffffffu, meets && !in);
         light[r] = __ballot_sync(0xffffffffu, live && !meets);
     }
-    const uint32_t n_heavy = (uint32_t) (__popc(heavy[0]) + __popc(heavy[1])), n_live = n_heavy + (uint32_t) (__popc(light[0]) + __popc(light[1]));
+    const uint32_t n_inside = (uint32_t) (__popc(inside[0]) + __popc(inside[1])), n_heavy = n_inside + (uint32_t) (__popc(heavy[0]) + __popc(heavy[1])),
+                   n_live = n_heavy + (uint32_t) (__popc(light[0]) + __popc(light[1]));
 #pragma unroll
     for (int r = 0; r < RT3_RAYS; r++) {
         const uint32_t id = (uint32_t) r * RT3_CTA_THREADS + threadIdx.x;
-        if ((heavy[r] >> lane) & 1u) { order[(r ? (uint32_t) __popc(heavy[0]) : 0u) + (uint32_t) __popc(heavy[r] & lane_lt)] = (uint16_t) id; }
+        if ((inside[r] >> lane) & 1u) { order[(r ? (uint32_t) __popc(inside[0]) : 0u) + (uint32_t) __popc(inside[r] & lane_lt)] = (uint16_t) id; }
+        if ((heavy[r] >> lane) & 1u) { order[n_inside + (r ? (uint32_t) __popc(heavy[0]) : 0u) + (uint32_t) __popc(heavy[r] & lane_lt)] = (uint16_t) id; }
         if ((light[r] >> lane) & 1u) { order[n_heavy + (r ? (uint32_t) __popc(light[0]) : 0u) + (uint32_t) __popc(light[r] & lane_lt)] = (uint16_t) id; }
     }
     __syncwarp();
@@ -897,7 +904,8 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
         for (int r = 0; r < R; r++) { any = any || slot_word(sm, r, RT3_F_BOUNCE) != RT3_NO_HIT; }
         if (RESIDENT) { if (!__any_sync(0xffffffffu, any)) { break; } }   /* warps run independently */
         else { if (!__syncthreads_or(any ? 1 : 0)) { break; } }           /* tiles are CTA-wide */
-        if (BIN == 2) { traverse_slots_warp_sorted(S, B, sm, bin, visits, tests); }
+        if (BIN == 2) { traverse_slots_warp_sorted<false>(S, B, sm, bin, visits, tests); }
+        else if (BIN == 3) { traverse_slots_warp_sorted<true>(S, B, sm, bin, visits, tests); }
         else if (ACCEL) { traverse_slots(S, B, sm, visits, tests); }
         else if (RESIDENT && chunk.dry && warp_live_slots(sm) <= RT3_TAIL_RAYS) { sweep_slots_by_primitive(S, sm); } /* warp-uniform */
         else { sweep_slots<RESIDENT, SPHERES_ONLY>(S, sm, phase); }
