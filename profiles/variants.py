@@ -1,6 +1,6 @@
 """Times one build of the library (RT3_CORE_LIB) on BASELINE C2 (sweep and hierarchy) and, with --c3, on C3 through the hierarchy.
 Prints one JSON line with kernel times and a frame checksum (all variants must produce the same frames).
-Usage: RT3_CORE_LIB=<lib.so> python profiles/variants.py <label> [--c3] [--spp N]"""
+Usage: RT3_CORE_LIB=<lib.so> python profiles/variants.py <label> [--c3 [--spp N] | --c2bvh | --c5]"""
 import json
 import os
 import sys
@@ -32,7 +32,17 @@ if "--c3" in sys.argv:
     scene, cam = fullsize.c3_scene(1920, 1080)
     ctx.upload(scene)
     ms, crc, st = timed(cam, abi.make_params(1920, 1080, mode=abi.MODE_PATHTRACE, spp=spp, max_depth=50, seed=1, flags=abi.FLAG_BVH), reps=2)
-    out.update(c3_spp=spp, c3_bvh_kernel_ms=ms, c3_crc=crc, c3_grays_s=round(st.rays / ms / 1e6, 3), c3_visits_per_ray=round(st.accel_node_visits / st.rays, 2))
+    out.update(c3_spp=spp, c3_bvh_kernel_ms=ms, c3_crc=crc, c3_grays_s=round(st.rays / ms / 1e6, 3), c3_visits_per_ray=round(st.accel_node_visits / st.rays, 2), c3_visits=st.accel_node_visits, c3_tests=st.accel_prim_tests)
+elif "--c2bvh" in sys.argv:
+    scene, cam = scenes.rtiow_cover(1200, 800)
+    ctx.upload(scene)
+    ms, crc, st = timed(cam, abi.make_params(1200, 800, mode=abi.MODE_PATHTRACE, spp=500, max_depth=50, seed=1, tile_rows=2, flags=abi.FLAG_BVH), reps=2)
+    out.update(c2_bvh_kernel_ms=ms, c2_crc=crc, c2_grays_s=round(st.rays / ms / 1e6, 3), c2_visits_per_ray=round(st.accel_node_visits / st.rays, 2), c2_visits=st.accel_node_visits, c2_tests=st.accel_prim_tests)
+elif "--c5" in sys.argv:
+    scene, cam = scenes.random_spheres(1000000)
+    ctx.upload(scene)
+    ms, crc, st = timed(cam, abi.make_params(1920, 1080, mode=abi.MODE_PATHTRACE, spp=64, max_depth=1, seed=1, flags=abi.FLAG_BVH | abi.FLAG_NO_JITTER), reps=2)
+    out.update(c5_bvh_kernel_ms=ms, c5_crc=crc, c5_grays_s=round(st.rays / ms / 1e6, 3), c5_visits_per_ray=round(st.accel_node_visits / st.rays, 2), c5_visits=st.accel_node_visits, c5_tests=st.accel_prim_tests)
 else:
     scene, cam = scenes.rtiow_cover(1200, 800)
     ctx.upload(scene)
