@@ -416,7 +416,8 @@ def main():
         achieved = flops / (st.trace_kernel_ms * 1e-3) / 1e12 if st.trace_kernel_ms > 0 else 0.0
         peak = ctx.measure_fma_peak()
         # executed (not credited) FP32 work and DRAM traffic: per-launch ncu counters of this exact workload, from the committed capture
-        kernel_name = "pathtrace_kernel<1,0,1>" if args.bvh else "pathtrace_kernel<1,1,0>"
+        # (resident sphere scenes trace their primary rays against per-chunk candidate lists: the BEAM instantiation, template arguments <1,1,0,0,1>)
+        kernel_name = "pathtrace_kernel<1,0,1>" if args.bvh else ("pathtrace_kernel<1,1,0,0,1>" if st.beam_rays else "pathtrace_kernel<1,1,0>")
         prof, prof_src = profiled_counters(kernel_name, W, H, spp, DEPTH, scene.n_spheres, world)
         share = 1.0
         if not prof and world > 1:
@@ -463,7 +464,9 @@ def main():
                          "traffic_source": (f"dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload, ncu --set full ({prof_src}); "
                                             "the accumulators, the scene is 13 KB") if prof else prof_src,
                          "kernel": "pathtrace_kernel", "kernel_ms": st.trace_kernel_ms,
-                         "algorithmic": f"{FLOP_PER_SPHERE_TEST} FLOP x {st.sphere_tests} ray-sphere tests (rank 0 launch)",
+                         "algorithmic": (f"{FLOP_PER_SPHERE_TEST} FLOP x {st.sphere_tests} ray-sphere tests (rank 0 launch): {st.rays - st.beam_rays} swept ray segments x "
+                                         f"{scene.n_spheres} spheres + {st.beam_tests} candidate tests of the {st.beam_rays} primary rays that were traced against "
+                                         "their chunk's candidate list instead of the whole scene"),
                          "peak_source": "FFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
                          "note": "the path is neither HBM- nor tensor-bound (DRAM ~0 % busy). `achieved` / `frac` CREDIT 17 algorithmic FLOP per ray-sphere test "
                                  "(SURVEY 8d); the conservative prefilter executes 3 FMA per test, so the credited fraction can exceed 1 and does not measure "

@@ -194,6 +194,11 @@ typedef struct rt3_stats {
     /* the most recent scene upload on this context (the reference's prerender, Main.cpp:284) */
     double upload_ms;           /* wall clock of rt3_scene_upload / rt3_scene_upload_device, call to return */
     double upload_device_ms;    /* CUDA-event time of the kernels that derive bounds, boxes, prefilter records and the scene basis */
+    /* pathtrace renders of resident sphere scenes through the sweep: primary rays are traced against a candidate list per chunk of path
+     * items instead of sweeping the scene (same hits, bit for bit); sphere_tests counts what was really tested:
+     * (rays - beam_rays) * n_spheres + beam_tests */
+    uint64_t beam_rays;         /* primary rays traced against a candidate list */
+    uint64_t beam_tests;        /* exact ray-sphere tests those rays ran */
 } rt3_stats;
 
 typedef struct rt3_ctx rt3_ctx;

@@ -48,7 +48,8 @@ else:
     ctx.upload(scene)
     reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 3
     ms, crc, st = timed(cam, abi.make_params(1200, 800, mode=abi.MODE_PATHTRACE, spp=500, max_depth=50, seed=1, tile_rows=2), reps=reps)
-    out.update(c2_sweep_kernel_ms=ms, c2_crc=crc, c2_grays_s=round(st.rays / ms / 1e6, 3))
+    out.update(c2_sweep_kernel_ms=ms, c2_crc=crc, c2_grays_s=round(st.rays / ms / 1e6, 3), beam=os.environ.get("RT3_BEAM", "default"), rays=st.rays,
+               beam_rays=st.beam_rays, beam_tests_per_ray=round(st.beam_tests / max(st.beam_rays, 1), 2))
     if "--eighth" in sys.argv:   # one rank's share of the frame at 8 GPUs: where the tail of the kernel shows
         ms8, _, st8 = timed(cam, abi.make_params(1200, 800, mode=abi.MODE_PATHTRACE, spp=500, max_depth=50, seed=1, tile_rows=1, part_index=3, part_count=8), reps=reps)
         out.update(c2_eighth_kernel_ms=ms8, c2_eighth_ideal_ms=round(ms * st8.rays / st.rays, 3))

@@ -84,6 +84,7 @@ class Stats(C.Structure):
         ("accel_node_visits", C.c_uint64), ("accel_prim_tests", C.c_uint64), ("accel_build_ms", C.c_double),
         ("accel", C.c_uint32), ("accel_stack_overflows", C.c_uint32),
         ("upload_ms", C.c_double), ("upload_device_ms", C.c_double),
+        ("beam_rays", C.c_uint64), ("beam_tests", C.c_uint64),
     ]
 
 

@@ -94,6 +94,7 @@ struct rt3_ctx {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_copy = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     cudaStream_t last_stream = nullptr; /* stream of the most recent render */
     bool stats_pending = false;         /* timings / counters not yet read back */
+    bool stats_beam = false;            /* the most recent render traced its primary rays against candidate lists (counters[2], [3]) */
     bool copy_timed = false;
 
     bool has_scene = false;
@@ -191,10 +192,10 @@ int launch_reference(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
     return RT3_OK;
 }
 
-template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL, int BIN = 0>
+template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL, int BIN = 0, bool BEAM = false>
 int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp, size_t smem, cudaStream_t stream) {
     int per_sm = 0;
-    int rc = configure(pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL, BIN>, smem, &per_sm);
+    int rc = configure(pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL, BIN, BEAM>, smem, &per_sm);
     if (rc != RT3_OK) { return rc; }
     if (ACCEL) {
         /* The traversal reads its node records through L1: ask for the smallest shared-memory carve-out that still
@@ -204,7 +205,7 @@ int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
         const size_t need = (size_t) per_sm * (smem + 1024);
         int percent = sm_bytes > 0 ? (int) ((need * 100 + (size_t) sm_bytes - 1) / (size_t) sm_bytes) : 100;
         if (percent > 100) { percent = 100; }
-        RT3_CUDA(cudaFuncSetAttribute(pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL, BIN>, cudaFuncAttributePreferredSharedMemoryCarveout, percent));
+        RT3_CUDA(cudaFuncSetAttribute(pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL, BIN, BEAM>, cudaFuncAttributePreferredSharedMemoryCarveout, percent));
     }
     if (per_sm < 1) { return fail(RT3_ERR_CUDA, "pathtrace kernel does not fit on an SM (smem %zu)", smem); }
     if (const char* cap = getenv("RT3_MAX_CTAS_PER_SM")) { /* tuning knob: fewer persistent CTAs per SM than fit */
@@ -216,7 +217,7 @@ int launch_pathtrace(rt3_ctx* ctx, const rt3_camera& cam, const rt3_kparams& kp,
     unsigned long long want = (kp.n_items + per_cta - 1) / per_cta;
     unsigned grid = (unsigned) ctx->sm_count * (unsigned) per_sm;
     if (want < grid) { grid = want ? (unsigned) want : 1u; }
-    pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL, BIN><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, ctx->bvh, cam, kp, ctx->accum.ptr, ctx->counters.ptr);
+    pathtrace_kernel<RESIDENT, SPHERES_ONLY, ACCEL, BIN, BEAM><<<grid, RT3_CTA_THREADS, smem, stream>>>(ctx->view, ctx->bvh, cam, kp, ctx->accum.ptr, ctx->counters.ptr);
     RT3_CUDA(cudaGetLastError());
     return RT3_OK;
 }
@@ -345,6 +346,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
         smem = rt3_accel_smem_bytes(params->mode == RT3_MODE_PATHTRACE);
     }
     ctx->stats.accel = accel ? 1u : 0u;
+    ctx->stats_beam = false;
     kp.resident = resident ? 1u : 0u;
     ctx->stats.kernel_launches = 0;
     ctx->stats.rows_rendered = kp.owned_rows;
@@ -400,10 +402,16 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
         bin = kp.spp <= RT3_BIN_MAX_SPP ? 1 : 3;
         if (const char* e = getenv("RT3_BINNING")) { bin = atoi(e); } /* 0 none, 1 CTA-wide, 2 / 3 per warp with two / three classes: for A/B measurements */
     }
+    /* resident sphere scenes: primary rays are traced against a per-chunk candidate list instead of the sweep (rt3_kernels.cuh, "BEAM");
+     * RT3_BEAM=0 switches it off for A/B measurements */
+    bool beam = !accel && resident && spheres_only;
+    if (const char* e = getenv("RT3_BEAM")) { beam = beam && atoi(e) != 0; }
+    ctx->stats_beam = beam;
     rc = bin == 1 ? launch_pathtrace<true, false, true, 1>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES, stream)
        : bin == 2 ? launch_pathtrace<true, false, true, 2>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES, stream)
        : bin == 3 ? launch_pathtrace<true, false, true, 3>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES, stream)
        : accel ? launch_pathtrace<true, false, true>(ctx, *cam, kp, smem, stream)
+       : (resident && spheres_only && beam) ? launch_pathtrace<true, true, false, 0, true>(ctx, *cam, kp, smem + RT3_BEAM_BYTES, stream)
        : resident ? (spheres_only ? launch_pathtrace<true, true, false>(ctx, *cam, kp, smem, stream) : launch_pathtrace<true, false, false>(ctx, *cam, kp, smem, stream))
                   : (spheres_only ? launch_pathtrace<false, true, false>(ctx, *cam, kp, smem, stream) : launch_pathtrace<false, false, false>(ctx, *cam, kp, smem, stream));
     if (rc != RT3_OK) { return rc; }
@@ -494,12 +502,18 @@ int collect_stats(rt3_ctx* ctx) {
     ctx->stats.rays = counters[1];
     ctx->stats.sphere_tests = counters[1] * ctx->view.n_spheres;
     ctx->stats.face_tests = counters[1] * ctx->view.n_faces;
+    ctx->stats.beam_rays = 0; ctx->stats.beam_tests = 0;
+    if (ctx->stats_beam && !ctx->stats.accel) {
+        /* primary rays that were traced against their chunk's candidate list did not sweep the scene: they ran beam_tests exact tests */
+        ctx->stats.beam_rays = counters[2]; ctx->stats.beam_tests = counters[3];
+        ctx->stats.sphere_tests = (counters[1] - counters[2]) * ctx->view.n_spheres + counters[3];
+    }
     if (ctx->stats.accel) {
         /* through the hierarchy only the leaves reached are tested */
         ctx->stats.sphere_tests = 0; ctx->stats.face_tests = 0;
     }
-    ctx->stats.accel_node_visits = counters[2];
-    ctx->stats.accel_prim_tests = counters[3];
+    ctx->stats.accel_node_visits = ctx->stats.accel ? counters[2] : 0;
+    ctx->stats.accel_prim_tests = ctx->stats.accel ? counters[3] : 0;
     ctx->stats.accel_build_ms = ctx->bvh_build_ms;
     ctx->stats.accel_stack_overflows = (uint32_t) std::min<unsigned long long>(counters[4], 0xFFFFFFFFull);
     ctx->stats_pending = false;

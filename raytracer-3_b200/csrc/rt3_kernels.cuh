@@ -577,6 +577,8 @@ struct rt3_chunk {
     unsigned long long cur, end, start;
     uint32_t pixel0, sample0; /* item `start` = (pixel0, sample0) */
     bool dry;                 /* the global counter is exhausted */
+    bool beam_ok;             /* BEAM kernels: the chunk has a candidate list for its primary rays (rt3_beam) ... */
+    uint32_t beam_candidates; /* ... of this many primitives */
 };
 /* (`start` doubles as the warp's last reading of the global counter: the value its previous claim returned.) */
 
@@ -673,6 +675,25 @@ __device__ __forceinline__ void start_path(rt3_path& s, const rt3_cam_view& C, c
     s.bounce = 0;
 }
 
+/* Radiance of a path that left the scene: throughput times the reference's sky (SequentialRenderer.cpp:105-107, unit direction). */
+__device__ __forceinline__ rt3_vec3 shade_miss(rt3_vec3 thr, rt3_vec3 dr, const rt3_kparams& P) {
+    float t = 0.5f * (dr.y + 1.0f);
+    float a = 1.0f - t;
+    rt3_vec3 L = thr * v3(a * 1.0f + t * 0.5f, a * 1.0f + t * 0.7f, a * 1.0f + t * 1.0f);
+    if (P.flags & RT3_FLAG_UNIFORM_SKY) { L = thr; } /* white furnace */
+    return L;
+}
+
+/* Adds a finished path's radiance to its pixel's fixed-point accumulators. */
+__device__ __forceinline__ void add_radiance(unsigned long long* __restrict__ accum, uint32_t pix, rt3_vec3 L, const rt3_kparams& P) {
+    unsigned long long qx = to_fixed(L.x), qy = to_fixed(L.y), qz = to_fixed(L.z);
+    RT3_ASSERT(pix < P.width * P.height);
+    unsigned long long* acc = accum + 3 * (size_t) pix;
+    if (qx) { atomicAdd(acc + 0, qx); }
+    if (qy) { atomicAdd(acc + 1, qy); }
+    if (qz) { atomicAdd(acc + 2, qz); }
+}
+
 /* Shades the closest hit `best` of a live path: miss -> sky * throughput, hit -> scatter
  * (Lambertian, metal, dielectric). A finished path adds its radiance to the
  * pixel's fixed-point accumulators and frees the slot. */
@@ -682,10 +703,7 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
     rt3_vec3 L = v3(0.0f, 0.0f, 0.0f);
     const rt3_vec3 dr = s.d;
     if (best.prim == RT3_NO_HIT) {
-        float t = 0.5f * (dr.y + 1.0f);
-        float a = 1.0f - t;
-        L = s.thr * v3(a * 1.0f + t * 0.5f, a * 1.0f + t * 0.7f, a * 1.0f + t * 1.0f);
-        if (P.flags & RT3_FLAG_UNIFORM_SKY) { L = s.thr; } /* white furnace */
+        L = shade_miss(s.thr, dr, P);
         done = true;
     } else {
         const uint32_t prim = best.prim;
@@ -768,13 +786,162 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
         }
     }
     if (done) {
-        unsigned long long qx = to_fixed(L.x), qy = to_fixed(L.y), qz = to_fixed(L.z);
-        RT3_ASSERT(s.pix < P.width * P.height);
-        unsigned long long* acc = accum + 3 * (size_t) s.pix;
-        if (qx) { atomicAdd(acc + 0, qx); }
-        if (qy) { atomicAdd(acc + 1, qy); }
-        if (qz) { atomicAdd(acc + 2, qz); }
+        add_radiance(accum, s.pix, L, P);
         s.bounce = RT3_NO_HIT;
+    }
+}
+
+/* ---- primary rays through a candidate list (BEAM kernels: resident sphere scenes) -------------------------------------
+ * A third of all ray segments of BASELINE C2 are primary rays, and the primary rays of one pixel are nearly the same ray:
+ * they leave the lens (radius L around the camera origin O) and pass through the pixel's footprint on the focus plane. A
+ * warp claims its path items a chunk at a time, and a chunk of 256 items of a 500-spp frame lies in one or two pixels. So
+ * once per CHUNK the warp tests every primitive against the chunk's BEAM -- everything a primary ray of these pixels can
+ * reach -- and keeps the candidates as a bit mask; the primary ray of each item then runs the exact tests of the
+ * candidates only (a handful), in ascending order like the sweep's drain, and is shaded before the slot sees its first
+ * sweep. A path thus occupies a slot for its bounce segments only: 1.75 instead of 2.75 sweeps per path on C2.
+ *
+ * The beam. Item (x, y, sample) aims at T = llc + u hor + v ver with u in [x, x + 1) / (W - 1), v likewise, from O + off,
+ * |off| <= L' = L (|lens_u| + |lens_v|). With T0 the centre of the chunk's pixel range, D = T0 - O and
+ * delta >= |T - T0|, a point of the ray is P(s) = O + off + s (T - O - off) = Q(s) + (1 - s) off + s (T - T0), where
+ * Q(s) = O + s D is the central ray, hence |P(s) - Q(s)| <= L' + s k with k = L' + delta. The exact sphere test can only
+ * report a sphere whose centre C lies within Re of the ray's line (Re^2 = r^2 + slack (|C|^2 + r^2 + |o|^2): the
+ * conservativeness argument of the level-1 filter, rt3_device.cuh / DESIGN.md 3.1). So if the ray reaches the sphere at
+ * parameter s then |Q(s) - C| <= Re + L' + s k; because |Q(s) - C| >= |s - s*| |D| (s* = the parameter of C's projection on
+ * the central line), s <= s_hi = (max(s*, 0) |D| + Re + L') / (|D| - k), and C is within Re + L' + s_hi k of the central
+ * line. Primitives that fail this test cannot be reported for any item of the chunk; the others are candidates. All of it
+ * is evaluated with generous roundings (the comparison carries 2^-20 |C - O|^2 and 1 + 1e-5): a wrong candidate costs one
+ * exact test, a missing one would be a wrong frame. Chunks that span rows or many pixels, beams with too many
+ * candidates and degenerate cameras fall back to the sweep (ok = 0): their primary rays are traced like every other ray. */
+#define RT3_BEAM_WORDS (RT3_CONST_PRIMS / 32)
+#ifndef RT3_BEAM_MAX_PIXELS
+#define RT3_BEAM_MAX_PIXELS 64u
+#endif
+#ifndef RT3_BEAM_MAX_CANDIDATES
+#define RT3_BEAM_MAX_CANDIDATES 48u
+#endif
+#ifndef RT3_BEAM_BATCHES
+#define RT3_BEAM_BATCHES 4u /* regeneration batches per round at most (the first takes up to 32 of the warp's free slots, the next ones the rest and
+                             * the slots of paths that ended with their primary ray; what is still free after that waits for the next round).
+                             * C2, call AD: 1 batch 128.3 ms, 2: 117.8, 3: 117.2, 4: 116.9 (plain sweep 136.2) */
+#endif
+struct rt3_beam {                      /* one per warp, in shared memory behind the path slots */
+    uint16_t list[64];                 /* candidates of the warp's current chunk, ascending primitive ids (RT3_BEAM_MAX_CANDIDATES <= 64 used) */
+};
+static_assert(RT3_BEAM_MAX_CANDIDATES <= 64u && RT3_CONST_PRIMS <= 0x10000, "candidate ids are 16 bits wide, the list holds 64");
+static_assert(sizeof(rt3_beam) == 128, "one 128-byte line per warp");
+#define RT3_BEAM_BYTES ((RT3_CTA_THREADS / 32) * 128)
+
+/* Approximate square root and reciprocal (one MUFU each, 2^-22 relative): the beam test carries far larger safety factors, and the
+ * IEEE versions would add 3 KB of code to a kernel whose loop has to stay inside the 32 KB instruction cache. */
+__device__ __forceinline__ float beam_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float beam_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+/* The whole warp: candidate list of the chunk `c` has just claimed (spheres only). */
+__device__ __forceinline__ void beam_for_chunk(const rt3_scene_view& S, const rt3_cam_view& C, const rt3_kparams& P, rt3_chunk& c, rt3_beam* beam) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t p_first = c.pixel0, p_last = c.pixel0 + ((uint32_t) (c.end - 1ull - c.start) + c.sample0) / P.spp; /* 32-bit: < spp + chunk */
+    const uint32_t row = p_first / P.width;
+    const uint32_t xa = p_first - row * P.width, xb = p_last - row * P.width;
+    bool ok = p_last / P.width == row && xb - xa < RT3_BEAM_MAX_PIXELS && S.n_faces == 0u && S.n_prims <= (uint32_t) RT3_CONST_PRIMS;
+    const uint32_t y = owned_row_to_global(P, row);
+    /* the (u, v) range of the chunk's pixels, jitter included, and its centre */
+    const float iw = beam_rcp(C.wm1), ih = beam_rcp(C.hm1);
+    const float u0 = (float) xa * iw, u1 = ((float) xb + 1.0f) * iw;
+    const float v0 = (float) (P.height - 1u - y) * ih, v1 = ((float) (P.height - 1u - y) + 1.0f) * ih;
+    const float um = 0.5f * (u0 + u1), vm = 0.5f * (v0 + v1);
+    const rt3_vec3 D = ((C.llc + um * C.hor) + vm * C.ver) - C.origin;
+    const float len_hor = beam_sqrt(dot3(C.hor, C.hor)), len_ver = beam_sqrt(dot3(C.ver, C.ver)), len_o = beam_sqrt(dot3(C.origin, C.origin));
+    const float tiny = 4.76837158203125e-07f * ((len_hor + len_ver) + (beam_sqrt(dot3(C.llc, C.llc)) + len_o)); /* 2^-21: roundings of T and of o + off */
+    const float delta = (0.5f * (u1 - u0) * len_hor + 0.5f * (v1 - v0) * len_ver) * 1.001f + tiny;
+    const float lens = C.lens_radius > 0.0f ? C.lens_radius * (beam_sqrt(dot3(C.lens_u, C.lens_u)) + beam_sqrt(dot3(C.lens_v, C.lens_v))) * 1.001f + tiny : tiny;
+    const float k = lens + delta;
+    const float dd = dot3(D, D), len_d = beam_sqrt(dd);
+    ok = ok && len_d > 4.0f * k && len_d < 1e18f && k < 1e18f; /* false for NaN too */
+    const float inv_dd = beam_rcp(dd), inv_reach = beam_rcp(len_d - k);
+    const float o_max = len_o + lens, o_slack = RT3_FILTER_SLACK * (o_max * o_max);
+    const uint32_t n_words = (S.n_prims + 31u) / 32u;
+    uint32_t n_candidates = 0;
+#pragma unroll 1
+    for (uint32_t w = 0; w < n_words; w++) {
+        const uint32_t prim = w * 32u + lane;
+        bool candidate = false;
+        if (ok && prim < S.n_prims) {
+            const float4 sp = __ldg(&S.spheres[prim]);
+            const rt3_vec3 ctr = v3(sp.x, sp.y, sp.z), co = ctr - C.origin;
+            const float r2 = sp.w * sp.w;
+            const float re = beam_sqrt((r2 + RT3_FILTER_SLACK * (dot3(ctr, ctr) + r2) + o_slack) * 1.0001f);
+            const float proj = dot3(co, D), co2 = dot3(co, co);
+            const float s_star = proj * inv_dd;
+            const float dist2 = co2 - s_star * proj;
+            const float s_hi = (fmaxf(s_star, 0.0f) * len_d + re + lens) * inv_reach;
+            const float reach = (re + lens + s_hi * k) * 1.0001f;
+            candidate = !(dist2 > reach * reach + 1.9073486328125e-06f * co2); /* 2^-19 |C - O|^2 for the roundings; a NaN anywhere keeps the primitive */
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, candidate);
+        const uint32_t at = n_candidates + (uint32_t) __popc(m & ((1u << lane) - 1u));
+        if (candidate && at < RT3_BEAM_MAX_CANDIDATES) { beam->list[at] = (uint16_t) prim; } /* ascending: words in order, lanes in order */
+        n_candidates += (uint32_t) __popc(m);
+    }
+    ok = ok && n_candidates <= RT3_BEAM_MAX_CANDIDATES;
+    /* (no conditional around the votes above and no __syncwarp here: either makes ptxas give up the uniform loads of the sweep, see
+     * tests/test_sass_evidence.py; the caller synchronises the warp before the list is read) */
+    c.beam_ok = ok; c.beam_candidates = n_candidates;
+}
+
+/* claim_item for the BEAM kernels: one path item per requesting lane, all from ONE chunk (so that one candidate mask
+ * serves them); lanes beyond the end of the chunk go empty-handed and ask again. A new chunk gets its beam here. */
+__device__ __forceinline__ bool claim_item_beam(bool want, rt3_chunk& c, const rt3_kparams& P, unsigned long long* next_item, uint32_t& pixel, uint32_t& sample,
+                                                const rt3_scene_view& S, const rt3_cam_view& C, rt3_beam* beam) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    const uint32_t n = (uint32_t) __popc(m), rank = (uint32_t) __popc(m & ((1u << lane) - 1u));
+    bool got = false;
+    if (n != 0u && !c.dry) {
+        if (c.cur == c.end) {
+            unsigned long long v = 0, size = 0;
+            if (lane == 0) {
+                size = chunk_size(c.start, P);
+                v = atomicAdd(next_item, size);
+            }
+            v = __shfl_sync(0xffffffffu, v, 0);
+            size = __shfl_sync(0xffffffffu, size, 0);
+            if (v >= P.n_items) { c.dry = true; }
+            else {
+                c.cur = c.start = v;
+                c.end = v + size < P.n_items ? v + size : P.n_items;
+                unsigned long long p0 = v / P.spp; /* one 64-bit divide per chunk */
+                c.pixel0 = (uint32_t) p0;
+                c.sample0 = (uint32_t) (v - p0 * P.spp);
+                beam_for_chunk(S, C, P, c, beam);
+            }
+        }
+        if (!c.dry) {
+            const unsigned long long avail = c.end - c.cur;
+            const uint32_t take = (unsigned long long) n < avail ? n : (uint32_t) avail;
+            if (want && rank < take) {
+                uint32_t k = (uint32_t) (c.cur - c.start) + rank + c.sample0; /* < spp + chunk */
+                uint32_t dp = k / P.spp;
+                pixel = c.pixel0 + dp;
+                sample = k - dp * P.spp;
+                got = true;
+            }
+            c.cur += (unsigned long long) take;
+        }
+    }
+    return got;
+}
+
+/* Closest hit of a primary ray among the chunk's candidates: the exact tests in ascending primitive order with the strict
+ * `t < best` rule, i.e. what the sweep's drain would report (the list is the warp's, so is the loop). */
+__device__ __forceinline__ void beam_closest_hit(const rt3_scene_view& S, const rt3_beam* beam, uint32_t n_candidates, bool active, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
+    best.t = __int_as_float(0x7f800000);
+    best.prim = RT3_NO_HIT;
+#pragma unroll 1 /* code size: the kernel's loop has to stay inside the instruction cache */
+    for (uint32_t i = 0; i < n_candidates; i++) {
+        const uint32_t prim = beam->list[i];
+        RT3_ASSERT(prim < S.n_prims);
+        const float4 sp = __ldg(&S.spheres[prim]);
+        if (active) { exact_sphere_path<true>(prim, sp, o, d, best); }
     }
 }
 
@@ -782,15 +949,19 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
  * shared memory; a loop iteration (1) takes the slots in turn through one copy of the shading code
  * (the hit the last sweep found), then gives every free slot of the warp the next (pixel, sample) item,
  * so that all lanes sweep live rays, and (2) sweeps the scene for all slots. */
+#ifndef RT3_BEAM_CTAS_PER_SM
+#define RT3_BEAM_CTAS_PER_SM 7 /* register cap 73: the BEAM kernel's regeneration would take 96 on its own; the sweep must keep its seven CTAs per SM */
+#endif
 #ifndef RT3_ACCEL_CTAS_PER_SM
 #define RT3_ACCEL_CTAS_PER_SM 6 /* register cap 85: the traversal kernels need 77-79 and keep six CTAs per SM (without the cap ptxas drifts to 87 and five) */
 #endif
-template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL, int BIN = 0>
-__global__ void __launch_bounds__(RT3_CTA_THREADS, ACCEL ? RT3_ACCEL_CTAS_PER_SM : RT3_CTAS_PER_SM)
+template <bool RESIDENT, bool SPHERES_ONLY, bool ACCEL, int BIN = 0, bool BEAM = false>
+__global__ void __launch_bounds__(RT3_CTA_THREADS, ACCEL ? RT3_ACCEL_CTAS_PER_SM : BEAM ? RT3_BEAM_CTAS_PER_SM : RT3_CTAS_PER_SM)
 pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P, unsigned long long* __restrict__ accum,
                  unsigned long long* __restrict__ counters) {
     constexpr int R = RT3_RAYS;
     static_assert(!BIN || ACCEL, "ray binning belongs to the hierarchy kernels");
+    static_assert(!BEAM || (RESIDENT && SPHERES_ONLY && !ACCEL), "candidate lists for primary rays: resident sphere scenes through the sweep");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const rt3_smem_view sm = smem_view<RESIDENT, ACCEL>(smem_raw);
     scene_prologue<RESIDENT>(sm);
@@ -823,7 +994,114 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
     static_assert(RT3_RAYS * RT3_CHUNK_WORDS >= 8, "the exchange area needs eight mask words per thread");
     rt3_chunk chunk;
     chunk.cur = chunk.end = chunk.start = 0; chunk.pixel0 = chunk.sample0 = 0; chunk.dry = false;
+    /* BEAM: this warp's candidate mask for the primary rays of its current chunk, and what went through it */
+    rt3_beam* const beam = reinterpret_cast<rt3_beam*>(smem_raw + rt3_smem_bytes(RESIDENT, true)) + (threadIdx.x >> 5);
+    uint32_t beam_rays = 0, beam_tests = 0;
+    chunk.beam_ok = false; chunk.beam_candidates = 0u;
 
+    if constexpr (BEAM) {
+        /* The BEAM kernel's round. One loop, one copy of the shading code: its first RT3_RAYS turns shade the slots (the hits the last
+         * sweep found), the following ones are regeneration batches -- up to 32 new paths each, as many as the warp has free slots --
+         * whose primary rays are traced against the candidate list of their chunk and shaded right here, in the lanes that started
+         * them; what reaches a slot is the path's first BOUNCE ray (a path that ends with its primary ray never occupies one), so a
+         * slot's sweeps are all spent on bounce segments. Chunks without a candidate list hand their primary rays to the slots
+         * unshaded, as the other kernels do. */
+        for (;;) {
+            uint32_t my_rank[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) { my_rank[r] = RT3_NO_HIT; }
+            uint32_t n_free = 0, filled = 0;
+#pragma unroll 1
+            for (int turn = 0;; turn++) {
+                const bool slot_turn = turn < R;
+                /* number the warp's free slots. Wanted once, when the slot turns are over -- but a vote under a condition, even this
+                 * warp-uniform one, makes ptxas give up the uniform loads of the sweep (tests/test_sass_evidence.py), so every turn votes
+                 * and only turn R keeps the result */
+                {
+                    uint32_t rank_now[R], free_now = 0;
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const unsigned free_r = __ballot_sync(0xffffffffu, slot_word(sm, r, RT3_F_BOUNCE) == RT3_NO_HIT);
+                        rank_now[r] = ((free_r >> lane) & 1u) ? free_now + (uint32_t) __popc(free_r & lane_lt) : RT3_NO_HIT;
+                        free_now += (uint32_t) __popc(free_r);
+                    }
+                    if (turn == R) {
+                        n_free = free_now;
+#pragma unroll
+                        for (int r = 0; r < R; r++) { my_rank[r] = rank_now[r]; }
+                    }
+                }
+                if (!slot_turn && (filled >= n_free || chunk.dry || turn >= R + RT3_BEAM_BATCHES)) { break; }
+                rt3_path s;
+                s.o = s.d = s.thr = v3(0.0f, 0.0f, 0.0f); s.key = 0u; s.pix = 0u; s.bounce = RT3_NO_HIT;
+                rt3_hit best;
+                best.t = __int_as_float(0x7f800000); best.prim = RT3_NO_HIT;
+                bool have = false, shade = false;
+                /* (votes and __syncwarp stay outside the slot-turn / batch-turn conditionals, with predicates that are false in a slot
+                 * turn: under a condition they cost the sweep its uniform loads, see above) */
+                const uint32_t want_n = slot_turn ? 0u : (n_free - filled < 32u ? n_free - filled : 32u);
+                uint32_t p = 0, sample = 0;
+                const bool got = claim_item_beam(lane < want_n, chunk, P, &counters[0], p, sample, S, C, beam);
+                __syncwarp(); /* a new chunk's candidate list is in shared memory */
+                if (slot_turn) {
+                    s.bounce = slot_word(sm, turn, RT3_F_BOUNCE);
+                    if (s.bounce != RT3_NO_HIT) {
+                        s.o = slot_vec(sm, turn, RT3_F_OX); s.d = slot_vec(sm, turn, RT3_F_DX); s.thr = slot_vec(sm, turn, RT3_F_TX);
+                        s.key = slot_word(sm, turn, RT3_F_KEY); s.pix = slot_word(sm, turn, RT3_F_PIX);
+                        best.t = slot_float(sm, turn, RT3_F_BEST_T); best.prim = slot_word(sm, turn, RT3_F_BEST_PRIM);
+                        have = shade = true;
+                    }
+                } else {
+                    if (got) { start_path(s, C, P, p, sample); have = true; }
+                    if (chunk.beam_ok) { /* warp-uniform */
+                        beam_closest_hit(S, beam, chunk.beam_candidates, got, s.o, s.d, best);
+                        shade = got;
+                        if (got) { beam_rays++; beam_tests += chunk.beam_candidates; }
+                    }
+                }
+                if (shade) { rays++; shade_path(s, best, S, P, accum); }
+                const bool keep = !slot_turn && have && s.bounce != RT3_NO_HIT;
+                const uint32_t keep_mask = __ballot_sync(0xffffffffu, keep);
+                const uint32_t at = (uint32_t) __popc(keep_mask & lane_lt), n_made = (uint32_t) __popc(keep_mask);
+                if (slot_turn) {
+                    if (have) {
+                        slot_word(sm, turn, RT3_F_BOUNCE) = s.bounce;
+                        if (s.bounce != RT3_NO_HIT) { slot_store_vec(sm, turn, RT3_F_OX, s.o); slot_store_vec(sm, turn, RT3_F_DX, s.d); slot_store_vec(sm, turn, RT3_F_TX, s.thr); }
+                    }
+                } else if (keep) {
+                    exchange[0 * RT3_CTA_THREADS + at] = __float_as_uint(s.o.x); exchange[1 * RT3_CTA_THREADS + at] = __float_as_uint(s.o.y);
+                    exchange[2 * RT3_CTA_THREADS + at] = __float_as_uint(s.o.z); exchange[3 * RT3_CTA_THREADS + at] = __float_as_uint(s.d.x);
+                    exchange[4 * RT3_CTA_THREADS + at] = __float_as_uint(s.d.y); exchange[5 * RT3_CTA_THREADS + at] = __float_as_uint(s.d.z);
+                    exchange[6 * RT3_CTA_THREADS + at] = __float_as_uint(s.thr.x); exchange[7 * RT3_CTA_THREADS + at] = __float_as_uint(s.thr.y);
+                    exchange[8 * RT3_CTA_THREADS + at] = __float_as_uint(s.thr.z); exchange[9 * RT3_CTA_THREADS + at] = s.key;
+                    exchange[10 * RT3_CTA_THREADS + at] = s.pix; exchange[11 * RT3_CTA_THREADS + at] = s.bounce;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const uint32_t e = my_rank[r] - filled; /* wraps around for slots that are not free, or filled already */
+                    if (!slot_turn && my_rank[r] != RT3_NO_HIT && e < n_made) {
+#pragma unroll
+                        for (int f = 0; f < 9; f++) { slot_word(sm, r, RT3_F_OX + f) = exchange[f * RT3_CTA_THREADS + e]; }
+                        slot_word(sm, r, RT3_F_KEY) = exchange[9 * RT3_CTA_THREADS + e]; slot_word(sm, r, RT3_F_PIX) = exchange[10 * RT3_CTA_THREADS + e];
+                        slot_word(sm, r, RT3_F_BOUNCE) = exchange[11 * RT3_CTA_THREADS + e];
+                    }
+                }
+                __syncwarp();
+                filled += n_made;
+                if (!slot_turn && !__any_sync(0xffffffffu, got)) { break; } /* the counter ran dry */
+            }
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < R; r++) { any = any || slot_word(sm, r, RT3_F_BOUNCE) != RT3_NO_HIT; }
+            if (!__any_sync(0xffffffffu, any)) {
+                if (chunk.dry) { break; } /* warps run independently */
+                continue;                 /* every path of this round ended with its primary ray (sky): nothing to sweep, on to the next items */
+            }
+            if (chunk.dry && warp_live_slots(sm) <= RT3_TAIL_RAYS) { sweep_slots_by_primitive(S, sm); } /* warp-uniform */
+            else { sweep_slots<RESIDENT, SPHERES_ONLY>(S, sm, phase); }
+        }
+    } else
     for (;;) {
         /* (1a) slot by slot through one copy of the shading code: shade the hit the last sweep found */
 #pragma unroll 1
@@ -913,6 +1191,11 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
     for (int off = 16; off > 0; off >>= 1) { rays += __shfl_down_sync(0xffffffffu, rays, off); }
     if ((threadIdx.x & 31) == 0 && rays) { atomicAdd(&counters[1], rays); }
     if (ACCEL) { count_accel(visits, tests, counters); }
+    if (BEAM) { /* counters[2], [3] (the hierarchy's in ACCEL kernels): primary rays traced against a candidate list, exact tests they ran */
+        unsigned long long br = beam_rays, bt = beam_tests;
+        for (int off = 16; off > 0; off >>= 1) { br += __shfl_down_sync(0xffffffffu, br, off); bt += __shfl_down_sync(0xffffffffu, bt, off); }
+        if ((threadIdx.x & 31) == 0 && br) { atomicAdd(&counters[2], br); atomicAdd(&counters[3], bt); }
+    }
 }
 
 /* Mean over samples, gamma 2, reference packing (SequentialRenderer.cpp:297). */

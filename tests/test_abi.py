@@ -40,7 +40,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(abi.Camera) == 4 * (12 + 1 + 6)
     assert C.sizeof(abi.Params) == 44
     assert C.sizeof(abi.Scene) == 8 + 4 * 8 + 8 + 5 * 8
-    assert C.sizeof(abi.Stats) == 4 * 8 + 3 * 8 + 8 + 3 * 8 + 8 + 2 * 8   # ... + upload_ms, upload_device_ms
+    assert C.sizeof(abi.Stats) == 4 * 8 + 3 * 8 + 8 + 3 * 8 + 8 + 2 * 8 + 2 * 8   # ... + upload_ms, upload_device_ms + beam_rays, beam_tests
 
 
 def py_partition_rows(h, tile, idx, cnt):

@@ -128,7 +128,9 @@ def test_full_size_properties(gpu_ctx):
     a = gpu_ctx.render(cam, p)
     st = gpu_ctx.stats()
     assert w * h * 100 <= st.rays <= w * h * 100 * 50
-    assert st.sphere_tests == st.rays * 4
+    # primary rays are traced against their chunk's candidate list instead of the whole scene: every path has one
+    assert 0 < st.beam_rays <= w * h * 100 and 0 < st.beam_tests <= st.beam_rays * 4   # (chunks of path items that span two rows have none)
+    assert st.sphere_tests == (st.rays - st.beam_rays) * 4 + st.beam_tests
     assert (a & 0xFF).min() == 0xFF                      # alpha byte
     assert np.array_equal(a, gpu_ctx.render(cam, p))      # idempotent
     top = (a[0] >> 8) & 0xFF                              # sky row: blue channel saturated, gradient intact
@@ -222,3 +224,25 @@ def test_accumulate_rejects_what_would_blend_different_renders(gpu_ctx):
     with pytest.raises(abi.Rt3Error, match="previous path-traced render"):
         gpu_ctx.render(cam, cont(first_sample=6))
     assert gpu_ctx.stats().accel_stack_overflows == 0
+
+
+def test_primary_candidate_lists_change_nothing(gpu_ctx, monkeypatch):
+    """Resident sphere scenes trace their primary rays against a per-chunk candidate list (rt3_kernels.cuh, BEAM kernel): the frame is
+    the plain sweep's (RT3_BEAM=0) bit for bit, with thin lens and without, at many and at few samples per pixel (few: a chunk of path
+    items spans many pixels or rows, the candidate list grows or is given up), under a row partition, and the ray count is the same."""
+    for (w, h, spp, scene_fn, kw) in [(192, 128, 40, scenes.rtiow_cover, {}), (192, 128, 3, scenes.rtiow_cover, {}), (160, 90, 64, scenes.rtiow_four_spheres, {}),
+                                      (97, 61, 7, scenes.rtiow_cover, dict(tile_rows=3, part_index=1, part_count=2)), (64, 40, 1, scenes.rtiow_four_spheres, {})]:
+        scene, cam = scene_fn(w, h)
+        gpu_ctx.upload(scene)
+        p = abi.make_params(w, h, mode=abi.MODE_PATHTRACE, spp=spp, max_depth=50, seed=3, **kw)
+        monkeypatch.setenv("RT3_BEAM", "0")
+        plain = gpu_ctx.render(cam, p).copy()
+        st0 = gpu_ctx.stats()
+        assert st0.beam_rays == 0 and st0.sphere_tests == st0.rays * scene.n_spheres
+        monkeypatch.delenv("RT3_BEAM")
+        beam = gpu_ctx.render(cam, p)
+        st1 = gpu_ctx.stats()
+        assert np.array_equal(plain, beam)
+        assert st1.rays == st0.rays and st1.beam_rays <= st1.rays
+        if spp >= 40:
+            assert st1.beam_rays > 0 and st1.beam_tests < st1.beam_rays * scene.n_spheres
