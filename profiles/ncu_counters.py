@@ -31,6 +31,7 @@ def main():
         ap.add_argument("--" + name, type=int, required=True)
     ap.add_argument("--n-gpus", type=int, default=1)
     ap.add_argument("--rays", type=int, default=0, help="ray segments of the captured launch (rt3_stats.rays): lets bench.py scale the counters to a rank's share at N > 1")
+    ap.add_argument("--tests", type=int, default=0, help="ray-primitive tests the captured launch is credited with (rt3_stats.sphere_tests + triangle_tests); 0 = rays x primitives")
     ap.add_argument("--source", required=True, help="the committed summary this capture is described in")
     a = ap.parse_args()
 
@@ -58,7 +59,7 @@ def main():
     row = {
         "kernel": a.kernel, "source": a.source,
         "workload": {"width": a.width, "height": a.height, "spp": a.spp, "max_depth": a.max_depth, "n_prims": a.n_prims, "n_gpus": a.n_gpus},
-        "duration_ms_under_ncu": metric("gpu__time_duration.sum"), "rays_per_launch": a.rays,
+        "duration_ms_under_ncu": metric("gpu__time_duration.sum"), "rays_per_launch": a.rays, "tests_per_launch": a.tests or a.rays * a.n_prims,
         "ffma_thread_inst": metric("smsp__sass_thread_inst_executed_op_ffma_pred_on.sum"),
         "fmul_thread_inst": metric("smsp__sass_thread_inst_executed_op_fmul_pred_on.sum"),
         "fadd_thread_inst": metric("smsp__sass_thread_inst_executed_op_fadd_pred_on.sum"),

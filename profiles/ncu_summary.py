@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, out = sys.argv[1], sys.argv[2]
 surv = json.load(open(sys.argv[3])) if len(sys.argv) > 3 else None
 c = [r for r in json.load(open(os.path.join(ROOT, "profiles", "ncu_counters.json")))["captures"] if r["kernel"].startswith("pathtrace")][-1]
+beam = c["kernel"].endswith(",0,1>")  # the BEAM instantiation: primary rays against per-chunk candidate lists
 rows = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], check=True, capture_output=True, text=True).stdout)))
 hdr, data = rows[1], rows[2:]
 isrc, ie, it, isamp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
@@ -30,13 +31,15 @@ k = l1_hi
 while k < len(data) and not op(data[k]).startswith("WARPSYNC"):
     k += 1
 regions = [("level 1 (slab sweep: FFMA2 / SHF / LDCU, per-word mask stores)", l1_lo, l1_hi), ("drain (survivor walk + exact sphere tests)", l1_hi, k),
-           ("shade / regenerate / ray filters (everything before the sweep)", 0, l1_lo), ("epilogue (slot write-back, loop control, counters)", k, len(data))]
+           ("shade / regenerate" + (" + primary rays vs candidate lists" if beam else "") + " / ray filters (everything before the sweep)", 0, l1_lo), ("epilogue (slot write-back, loop control, counters)", k, len(data))]
 warp_rays = c["rays_per_launch"] / 32
 lines = []
 for name, lo, hi in regions:
     sub = data[lo:hi]
     w, t, s = sum(int(r[ie]) for r in sub), sum(int(r[it]) for r in sub), sum(int(r[isamp]) for r in sub)
-    lines.append(f"  {name:70s} {100 * w / tot:6.2f} % of warp instructions  {w / warp_rays:7.0f} per warp-ray  {t / max(w, 1):5.1f} lanes  {100 * s / tots:6.2f} % of warp-state samples")
+    lines.append(f"  {name:98s} {100 * w / tot:6.2f} % of warp instructions  {w / warp_rays:7.0f} per warp-ray  {t / max(w, 1):5.1f} lanes  {100 * s / tots:6.2f} % of warp-state samples")
+tests = c.get("tests_per_launch") or c["rays_per_launch"] * c["workload"]["n_prims"]
+cred = 17.0 * tests
 fl = 2 * c["ffma_thread_inst"] + 4 * c["ffma2_thread_inst"] + c["fmul_thread_inst"] + c["fadd_thread_inst"]
 ms, peak = c["duration_ms_under_ncu"], 72.3
 txt = f"""ncu --set full --metrics smsp__sass_thread_inst_executed_op_{{ffma,fmul,fadd,fp32}}_pred_on.sum --clock-control none --import-source on
@@ -44,7 +47,7 @@ txt = f"""ncu --set full --metrics smsp__sass_thread_inst_executed_op_{{ffma,fmu
 (BASELINE config C2: cover scene, 484 spheres, 1200x800, 500 spp, depth 50; counters extracted by profiles/ncu_counters.py into
  profiles/ncu_counters.json, which bench.py reads for roofline.executed_* and roofline.traffic; this text by profiles/ncu_summary.py)
 
-kernel: pathtrace_kernel<1,1,0>   grid 1036 x 128 threads, {c['registers_per_thread']} registers, 7 CTAs / SM
+kernel: {c['kernel']}   grid 1036 x 128 threads, {c['registers_per_thread']} registers, 7 CTAs / SM
 gpu__time_duration.sum                         = {ms:.3f} ms
 dram__bytes_read.sum + dram__bytes_write.sum   = {c['dram_bytes_read'] + c['dram_bytes_write']:.0f} B  (the 23.0 MB of accumulators; DRAM idle)
 smsp__issue_active (pct of peak)               = {c['issue_active_pct']} %   (counts the two-cycle FFMA2 once)
@@ -58,7 +61,7 @@ EXECUTED FP32 WORK (thread-level, predicated-on)
   op_fadd  {c['fadd_thread_inst']:.4g}
   op_fp32  {c['fp32_thread_inst']:.4g}  (all fp32 opcodes incl. FFMA2, FSETP, FSEL, FMNMX, MUFU)
   executed = 2 ffma + 4 ffma2 + fmul + fadd = {fl:.4g} FLOP per launch -> {fl / ms / 1e9:.1f} TFLOP/s = {fl / ms / 1e9 / peak:.2f} of the measured FFMA peak ({peak})
-  credited (SURVEY 8d: 17 FLOP x 6.386e11 ray-sphere tests) = 1.0857e13 FLOP -> {1.0857e13 / ms / 1e9:.1f} TFLOP/s = {1.0857e13 / ms / 1e9 / peak:.2f}
+  credited (SURVEY 8d: 17 FLOP x {tests:.4g} ray-sphere tests{" -- swept segments x spheres + the candidate tests of the primary rays, rt3_stats.sphere_tests" if beam else ""}) = {cred:.4g} FLOP -> {cred / ms / 1e9:.1f} TFLOP/s = {cred / ms / 1e9 / peak:.2f}
   => the north star's ">= 60 % of FP32-FMA peak, by ncu counters" is NOT met by this kernel: {c['pipe_fma_cycles_active_pct']} % pipe-active, {fl / ms / 1e9 / peak:.2f} executed.
      The level-1 loop alone is at its formulation's ceiling (3 FFMA2 = 6 issue cycles of the 9 per pair and ray: 67 %); the other half of the kernel is not FMA work.
 
