@@ -196,9 +196,10 @@ typedef struct rt3_stats {
     double upload_device_ms;    /* CUDA-event time of the kernels that derive bounds, boxes, prefilter records and the scene basis */
     /* pathtrace renders of resident sphere scenes through the sweep: primary rays are traced against a candidate list per chunk of path
      * items instead of sweeping the scene (same hits, bit for bit); sphere_tests counts what was really tested:
-     * (rays - beam_rays) * n_spheres + beam_tests */
+     * (rays - beam_rays) * n_spheres + beam_tests. Renders through the hierarchy (RT3_FLAG_BVH) do the same with the candidates a beam's
+     * walk of the trees collected: those primary rays did not traverse (accel_node_visits includes the nodes the beams read) */
     uint64_t beam_rays;         /* primary rays traced against a candidate list */
-    uint64_t beam_tests;        /* exact ray-sphere tests those rays ran */
+    uint64_t beam_tests;        /* exact tests those rays ran (spheres; through the hierarchy: spheres and triangles) */
 } rt3_stats;
 
 typedef struct rt3_ctx rt3_ctx;

@@ -20,6 +20,7 @@ n_scenes = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2026)
 ctx = abi.Context(0)
 bad = 0
+beams = 0
 t0 = time.time()
 for i in range(n_scenes):
     nf = int(rng.choice([0, 0, 3, 40, 500, 3000]))
@@ -65,4 +66,17 @@ for i in range(n_scenes):
             if not (np.array_equal(gpu, cpu) and ctx.stats().rays == rays):
                 bad += 1
                 print(f"scene {i}: path tracing differs (flags={flags}, faces={nf}, spheres={ns}, scale={scale:.3g}): {int((gpu != cpu).sum())} pixels", flush=True)
-print(f"{n_scenes} scenes, {bad} mismatches, {time.time() - t0:.1f} s")
+        # one row at many samples per pixel: a chunk of path items then lies in a few pixels, and the hierarchy kernels trace its primary
+        # rays against the candidates a beam's walk of the trees collected (rt3_kernels.cuh, beam_for_chunk_bvh); sweep kernels of
+        # resident sphere scenes do the same with their own candidate lists
+        y = int(rng.integers(0, h))
+        pb = dict(mode=abi.MODE_PATHTRACE, spp=int(rng.choice([24, 48, 128, 300])), max_depth=6, seed=i, tile_rows=1, part_index=y, part_count=h)
+        cpu, _, rays = ol.oracle_pathtrace(sc, cam, abi.make_params(w, h, **pb))
+        for flags in (0, abi.FLAG_BVH):
+            gpu = ctx.render(cam, abi.make_params(w, h, flags=flags, **pb))
+            st = ctx.stats()
+            beams += st.beam_rays
+            if not (np.array_equal(gpu[y], cpu[y]) and st.rays == rays):
+                bad += 1
+                print(f"scene {i}: path tracing of row {y} at {pb['spp']} spp differs (flags={flags}, faces={nf}, spheres={ns}, scale={scale:.3g}): {int((gpu[y] != cpu[y]).sum())} pixels", flush=True)
+print(f"{n_scenes} scenes, {bad} mismatches, {beams} primary rays through candidate lists, {time.time() - t0:.1f} s")

@@ -53,4 +53,7 @@ else:
     if "--eighth" in sys.argv:   # one rank's share of the frame at 8 GPUs: where the tail of the kernel shows
         ms8, _, st8 = timed(cam, abi.make_params(1200, 800, mode=abi.MODE_PATHTRACE, spp=500, max_depth=50, seed=1, tile_rows=1, part_index=3, part_count=8), reps=reps)
         out.update(c2_eighth_kernel_ms=ms8, c2_eighth_ideal_ms=round(ms * st8.rays / st.rays, 3))
+if "--c3" in sys.argv or "--c2bvh" in sys.argv or "--c5" in sys.argv:   # hierarchy kernels: primary rays through the candidates of a beam's walk (RT3_BEAM_BVH=0: off)
+    out.update(beam_bvh=os.environ.get("RT3_BEAM_BVH", "default"), rays=st.rays, beam_rays=st.beam_rays, beam_tests_per_ray=round(st.beam_tests / max(st.beam_rays, 1), 2),
+               tests_per_ray=round(st.accel_prim_tests / st.rays, 2))
 print(json.dumps(out), flush=True)

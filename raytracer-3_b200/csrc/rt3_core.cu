@@ -94,6 +94,7 @@ struct rt3_ctx {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_copy = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     cudaStream_t last_stream = nullptr; /* stream of the most recent render */
     bool stats_pending = false;         /* timings / counters not yet read back */
+    bool stats_beam_accel = false;      /* ... or, through the hierarchy, against the candidates a beam's walk of the trees collected (counters[5], [6]) */
     bool stats_beam = false;            /* the most recent render traced its primary rays against candidate lists (counters[2], [3]) */
     bool copy_timed = false;
 
@@ -346,7 +347,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
         smem = rt3_accel_smem_bytes(params->mode == RT3_MODE_PATHTRACE);
     }
     ctx->stats.accel = accel ? 1u : 0u;
-    ctx->stats_beam = false;
+    ctx->stats_beam = false; ctx->stats_beam_accel = false;
     kp.resident = resident ? 1u : 0u;
     ctx->stats.kernel_launches = 0;
     ctx->stats.rows_rendered = kp.owned_rows;
@@ -357,7 +358,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     std::unique_lock<std::mutex> bank_lock; /* released when this function returns, i.e. after the launch below */
     if (resident && kp.n_pixels != 0 && (rc = claim_constant_bank(ctx, stream, bank_lock)) != RT3_OK) { return rc; }
     RT3_CUDA(cudaEventRecord(ctx->ev_begin, stream));
-    RT3_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 5 * sizeof(unsigned long long), stream));
+    RT3_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 8 * sizeof(unsigned long long), stream));
     if (kp.n_pixels == 0) {
         RT3_CUDA(cudaEventRecord(ctx->ev_k0, stream));
         RT3_CUDA(cudaEventRecord(ctx->ev_k1, stream));
@@ -407,7 +408,14 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     bool beam = !accel && resident && spheres_only;
     if (const char* e = getenv("RT3_BEAM")) { beam = beam && atoi(e) != 0; }
     ctx->stats_beam = beam;
-    rc = bin == 1 ? launch_pathtrace<true, false, true, 1>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES, stream)
+    /* the same through the hierarchy (the beam walks the trees once per chunk of path items): every hierarchy kernel but the CTA-wide sort
+     * of few-spp calls, whose chunks span too many pixels for a beam anyway; RT3_BEAM_BVH=0 switches it off */
+    bool beam_accel = accel && bin != 1 && bin != 2;
+    if (const char* e = getenv("RT3_BEAM_BVH")) { beam_accel = beam_accel && atoi(e) != 0; }
+    ctx->stats_beam_accel = beam_accel;
+    rc = (beam_accel && bin == 3) ? launch_pathtrace<true, false, true, 3, true>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES + RT3_ABEAM_BYTES, stream)
+       : beam_accel ? launch_pathtrace<true, false, true, 0, true>(ctx, *cam, kp, smem + RT3_ABEAM_BYTES, stream)
+       : bin == 1 ? launch_pathtrace<true, false, true, 1>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES, stream)
        : bin == 2 ? launch_pathtrace<true, false, true, 2>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES, stream)
        : bin == 3 ? launch_pathtrace<true, false, true, 3>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES, stream)
        : accel ? launch_pathtrace<true, false, true>(ctx, *cam, kp, smem, stream)
@@ -489,7 +497,7 @@ int collect_stats(rt3_ctx* ctx) {
     if (!ctx->stats_pending) { return RT3_OK; }
     RT3_CUDA(cudaSetDevice(ctx->device));
     RT3_CUDA(cudaStreamSynchronize(ctx->last_stream));
-    unsigned long long counters[5] = { 0, 0, 0, 0, 0 };
+    unsigned long long counters[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     RT3_CUDA(cudaMemcpy(counters, ctx->counters.ptr, sizeof counters, cudaMemcpyDeviceToHost));
     float ms = 0.0f, ms_k = 0.0f, ms_copy = 0.0f;
     RT3_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
@@ -512,6 +520,7 @@ int collect_stats(rt3_ctx* ctx) {
         /* through the hierarchy only the leaves reached are tested */
         ctx->stats.sphere_tests = 0; ctx->stats.face_tests = 0;
     }
+    if (ctx->stats.accel && ctx->stats_beam_accel) { ctx->stats.beam_rays = counters[5]; ctx->stats.beam_tests = counters[6]; }
     ctx->stats.accel_node_visits = ctx->stats.accel ? counters[2] : 0;
     ctx->stats.accel_prim_tests = ctx->stats.accel ? counters[3] : 0;
     ctx->stats.accel_build_ms = ctx->bvh_build_ms;
@@ -679,7 +688,7 @@ int rt3_create(rt3_ctx** out, int device) {
     if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_copy); }
     if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_k0); }
     if (err == cudaSuccess) { err = cudaEventCreate(&ctx->ev_k1); }
-    if (err == cudaSuccess && ctx->counters.reserve(5) != RT3_OK) { err = cudaErrorMemoryAllocation; }
+    if (err == cudaSuccess && ctx->counters.reserve(8) != RT3_OK) { err = cudaErrorMemoryAllocation; }
     if (err != cudaSuccess) {
         rt3_destroy(ctx);
         return fail(RT3_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(err));

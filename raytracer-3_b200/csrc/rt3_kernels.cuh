@@ -888,10 +888,145 @@ __device__ __forceinline__ void beam_for_chunk(const rt3_scene_view& S, const rt
     c.beam_ok = ok; c.beam_candidates = n_candidates;
 }
 
+/* ---- the same through the hierarchy (ACCEL + BEAM kernels: any scene rendered with RT3_FLAG_BVH) -----------------------
+ * The chunk's beam walks the two trees once, the whole warp at a time and level by level: the lanes take one node of the
+ * current level each, test both child boxes against the beam and append the children that meet it to the next level
+ * (internal nodes) or to the candidate list (leaves). A ray can only be reported a primitive whose (host-widened) box,
+ * grown by ray_margin |o|, it crosses -- that is the hierarchy's own contract, rt3_bvh.cuh -- so a box the beam misses
+ * holds no primitive that any primary ray of the chunk could be reported. The box is tested through its bounding sphere
+ * (centre, half diagonal + sqrt(3) ray_margin o_max) with the inequality of beam_for_chunk above; NaNs and infinities keep
+ * the box. Levels wider than RT3_ABEAM_LEVEL nodes and lists longer than RT3_ABEAM_MAX_CANDIDATES give the chunk up (ok = 0: its primary
+ * rays walk the hierarchy like every other ray). The primary rays then run the exact tests of the candidates with the
+ * hierarchy's tie rule (lower primitive id), whatever the order of the list. */
+#ifndef RT3_ABEAM_MAX_PIXELS
+#define RT3_ABEAM_MAX_PIXELS 16u
+#endif
+#ifndef RT3_ABEAM_MAX_CANDIDATES
+#define RT3_ABEAM_MAX_CANDIDATES 128u    /* a beam does not stop at the first hit: on BASELINE C5 (10^6 spheres, four pixels per chunk) it meets 56 primitives on
+                                          * average and up to 150 (CPU model of the walk); 128 exact tests at full lanes still cost less than 129 node visits at a third */
+#endif
+#define RT3_ABEAM_LEVEL 192u             /* nodes per level of the walk: C5 reaches 100 on average, 153 at most in the same model */
+struct rt3_abeam {                        /* one per warp, in shared memory behind the exchange area */
+    uint32_t list[RT3_ABEAM_MAX_CANDIDATES]; /* candidate primitives of the warp's current chunk (global ids, no particular order) */
+};
+#define RT3_ABEAM_EXCHANGE_BYTES (12 * RT3_CTA_THREADS * 4) /* the hierarchy kernels have no survivor masks to alias the exchange area on */
+#define RT3_ABEAM_BYTES (RT3_ABEAM_EXCHANGE_BYTES + (RT3_CTA_THREADS / 32) * sizeof(rt3_abeam))
+static_assert(2u * RT3_ABEAM_LEVEL == 12u * 32u, "the two levels of the walk live in the warp's 12 x 32 words of the exchange area, which is idle while a chunk is claimed");
+/* word i of level `which` of this warp's walk (`exchange` points at the warp's first column) */
+__device__ __forceinline__ uint32_t& abeam_level(uint32_t* exchange, uint32_t which, uint32_t i) {
+    const uint32_t w = which * RT3_ABEAM_LEVEL + i;
+    return exchange[(w >> 5) * RT3_CTA_THREADS + (w & 31u)];
+}
+
+__device__ __forceinline__ void beam_for_chunk_bvh(const rt3_bvh_view& B, const rt3_cam_view& C, const rt3_kparams& P, rt3_chunk& c, rt3_abeam* ab,
+                                                   uint32_t* exchange, uint32_t& visits) {
+    const uint32_t lane = threadIdx.x & 31u, lane_lt = (1u << lane) - 1u;
+    const uint32_t p_first = c.pixel0, p_last = c.pixel0 + ((uint32_t) (c.end - 1ull - c.start) + c.sample0) / P.spp;
+    const uint32_t row = p_first / P.width;
+    const uint32_t xa = p_first - row * P.width, xb = p_last - row * P.width;
+    bool ok = p_last / P.width == row && xb - xa < RT3_ABEAM_MAX_PIXELS;
+    const uint32_t y = owned_row_to_global(P, row);
+    /* the beam of the chunk's pixels: as in beam_for_chunk */
+    const float iw = beam_rcp(C.wm1), ih = beam_rcp(C.hm1);
+    const float u0 = (float) xa * iw, u1 = ((float) xb + 1.0f) * iw;
+    const float v0 = (float) (P.height - 1u - y) * ih, v1 = ((float) (P.height - 1u - y) + 1.0f) * ih;
+    const float um = 0.5f * (u0 + u1), vm = 0.5f * (v0 + v1);
+    const rt3_vec3 D = ((C.llc + um * C.hor) + vm * C.ver) - C.origin;
+    const float len_hor = beam_sqrt(dot3(C.hor, C.hor)), len_ver = beam_sqrt(dot3(C.ver, C.ver)), len_o = beam_sqrt(dot3(C.origin, C.origin));
+    const float tiny = 4.76837158203125e-07f * ((len_hor + len_ver) + (beam_sqrt(dot3(C.llc, C.llc)) + len_o));
+    const float delta = (0.5f * (u1 - u0) * len_hor + 0.5f * (v1 - v0) * len_ver) * 1.001f + tiny;
+    const float lens = C.lens_radius > 0.0f ? C.lens_radius * (beam_sqrt(dot3(C.lens_u, C.lens_u)) + beam_sqrt(dot3(C.lens_v, C.lens_v))) * 1.001f + tiny : tiny;
+    const float k = lens + delta;
+    const float dd = dot3(D, D), len_d = beam_sqrt(dd);
+    ok = ok && len_d > 4.0f * k && len_d < 1e18f && k < 1e18f; /* false for NaN too */
+    const float inv_dd = beam_rcp(dd), inv_reach = beam_rcp(len_d - k);
+    const float o_max = len_o + lens;
+    uint32_t n_candidates = 0;
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
+        const rt3_bvh_tree T = B.tree[which];
+        if (!ok || T.n_prims == 0u) { continue; } /* warp-uniform, like everything that guards a vote below */
+        if (T.root < 0) { /* a tree of one primitive */
+            if (lane == 0 && n_candidates < RT3_ABEAM_MAX_CANDIDATES) { ab->list[n_candidates] = (uint32_t) ~T.root; }
+            n_candidates++;
+            continue;
+        }
+        const float grow = 1.7320508f * T.ray_margin * o_max * 1.0001f + tiny; /* the per-ray widening of a box, at its corners */
+        uint32_t n_cur = 1u, cur = 0u;
+        if (lane == 0) { abeam_level(exchange, 0u, 0u) = (uint32_t) T.root; }
+        __syncwarp();
+#pragma unroll 1
+        while (n_cur != 0u) {
+            uint32_t n_next = 0u;
+#pragma unroll 1
+            for (uint32_t base = 0; base < n_cur; base += 32u) {
+                bool meets[2] = { false, false };
+                int32_t ref[2] = { 0, 0 };
+                if (base + lane < n_cur) {
+                    const int32_t node = (int32_t) abeam_level(exchange, cur, base + lane);
+                    RT3_ASSERT(node >= 0 && (uint32_t) node + 2u <= B.tree[0].n_prims + B.tree[1].n_prims);
+                    visits++;
+                    const float4 n0 = __ldg(&B.nodes[4 * node + 0]), n1 = __ldg(&B.nodes[4 * node + 1]), n2 = __ldg(&B.nodes[4 * node + 2]),
+                                 n3 = __ldg(&B.nodes[4 * node + 3]);
+                    const float lo[2][3] = { { n0.x, n0.y, n0.z }, { n1.z, n1.w, n2.x } }, hi[2][3] = { { n0.w, n1.x, n1.y }, { n2.y, n2.z, n2.w } };
+                    ref[0] = __float_as_int(n3.x); ref[1] = __float_as_int(n3.y);
+#pragma unroll
+                    for (int ch = 0; ch < 2; ch++) {
+                        const rt3_vec3 ctr = v3(0.5f * lo[ch][0] + 0.5f * hi[ch][0], 0.5f * lo[ch][1] + 0.5f * hi[ch][1], 0.5f * lo[ch][2] + 0.5f * hi[ch][2]);
+                        const rt3_vec3 half = v3(0.5f * hi[ch][0] - 0.5f * lo[ch][0], 0.5f * hi[ch][1] - 0.5f * lo[ch][1], 0.5f * hi[ch][2] - 0.5f * lo[ch][2]);
+                        const float rho = beam_sqrt(dot3(half, half));
+                        /* + 2^-21 (|centre| + rho): the roundings of the centre and of centre - O */
+                        const float re = (rho + grow) * 1.0001f + 4.76837158203125e-07f * (((fabsf(ctr.x) + fabsf(ctr.y)) + fabsf(ctr.z)) + rho);
+                        const rt3_vec3 co = ctr - C.origin;
+                        const float proj = dot3(co, D), co2 = dot3(co, co);
+                        const float s_star = proj * inv_dd;
+                        const float dist2 = co2 - s_star * proj;
+                        const float s_hi = (fmaxf(s_star, 0.0f) * len_d + re + lens) * inv_reach;
+                        const float reach = (re + lens + s_hi * k) * 1.0001f;
+                        meets[ch] = !(dist2 > reach * reach + 1.9073486328125e-06f * co2); /* a NaN anywhere keeps the box */
+                    }
+                }
+#pragma unroll
+                for (int ch = 0; ch < 2; ch++) {
+                    const uint32_t m_in = __ballot_sync(0xffffffffu, meets[ch] && ref[ch] >= 0), m_lf = __ballot_sync(0xffffffffu, meets[ch] && ref[ch] < 0);
+                    const uint32_t at_in = n_next + (uint32_t) __popc(m_in & lane_lt), at_lf = n_candidates + (uint32_t) __popc(m_lf & lane_lt);
+                    if (meets[ch] && ref[ch] >= 0 && at_in < RT3_ABEAM_LEVEL) { abeam_level(exchange, cur ^ 1u, at_in) = (uint32_t) ref[ch]; }
+                    if (meets[ch] && ref[ch] < 0 && at_lf < RT3_ABEAM_MAX_CANDIDATES) { ab->list[at_lf] = (uint32_t) ~ref[ch]; }
+                    n_next += (uint32_t) __popc(m_in); n_candidates += (uint32_t) __popc(m_lf);
+                }
+            }
+            __syncwarp();
+            if (n_next > RT3_ABEAM_LEVEL || n_candidates > RT3_ABEAM_MAX_CANDIDATES) { ok = false; n_next = 0u; }
+            cur ^= 1u; n_cur = n_next;
+        }
+    }
+    ok = ok && n_candidates <= RT3_ABEAM_MAX_CANDIDATES;
+    c.beam_ok = ok; c.beam_candidates = n_candidates;
+}
+
+/* Closest hit of a primary ray among the candidates the beam's walk collected: the leaf tests of bvh_closest_hit (path mode). */
+__device__ __forceinline__ void beam_closest_hit_bvh(const rt3_scene_view& S, const rt3_abeam* ab, uint32_t n_candidates, bool active, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
+    best.t = __int_as_float(0x7f800000);
+    best.prim = RT3_NO_HIT;
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_candidates; i++) {
+        const uint32_t prim = ab->list[i]; /* warp-uniform */
+        RT3_ASSERT(prim < S.n_prims);
+        if (prim < S.n_faces) {
+            if (active) { exact_face<false>(S, prim, o, d, RT3_TMIN, best); }
+        } else {
+            const float4 sp = __ldg(&S.spheres[prim - S.n_faces]);
+            if (active) { exact_sphere_path<false>(prim, sp, o, d, best); }
+        }
+    }
+}
+
 /* claim_item for the BEAM kernels: one path item per requesting lane, all from ONE chunk (so that one candidate mask
  * serves them); lanes beyond the end of the chunk go empty-handed and ask again. A new chunk gets its beam here. */
+template <bool ACCEL>
 __device__ __forceinline__ bool claim_item_beam(bool want, rt3_chunk& c, const rt3_kparams& P, unsigned long long* next_item, uint32_t& pixel, uint32_t& sample,
-                                                const rt3_scene_view& S, const rt3_cam_view& C, rt3_beam* beam) {
+                                                const rt3_scene_view& S, const rt3_cam_view& C, rt3_beam* beam, const rt3_bvh_view& B, rt3_abeam* abeam,
+                                                uint32_t* exchange, uint32_t& visits) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned m = __ballot_sync(0xffffffffu, want);
     const uint32_t n = (uint32_t) __popc(m), rank = (uint32_t) __popc(m & ((1u << lane) - 1u));
@@ -912,7 +1047,8 @@ __device__ __forceinline__ bool claim_item_beam(bool want, rt3_chunk& c, const r
                 unsigned long long p0 = v / P.spp; /* one 64-bit divide per chunk */
                 c.pixel0 = (uint32_t) p0;
                 c.sample0 = (uint32_t) (v - p0 * P.spp);
-                beam_for_chunk(S, C, P, c, beam);
+                if constexpr (ACCEL) { beam_for_chunk_bvh(B, C, P, c, abeam, exchange, visits); }
+                else { beam_for_chunk(S, C, P, c, beam); }
             }
         }
         if (!c.dry) {
@@ -961,7 +1097,8 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
                  unsigned long long* __restrict__ counters) {
     constexpr int R = RT3_RAYS;
     static_assert(!BIN || ACCEL, "ray binning belongs to the hierarchy kernels");
-    static_assert(!BEAM || (RESIDENT && SPHERES_ONLY && !ACCEL), "candidate lists for primary rays: resident sphere scenes through the sweep");
+    static_assert(!BEAM || (RESIDENT && (ACCEL ? (!SPHERES_ONLY && BIN != 1) : SPHERES_ONLY)),
+                  "candidate lists for primary rays: resident sphere scenes through the sweep, or any scene through the hierarchy (not the CTA-wide sort)");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const rt3_smem_view sm = smem_view<RESIDENT, ACCEL>(smem_raw);
     scene_prologue<RESIDENT>(sm);
@@ -990,12 +1127,14 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
     uint32_t visits = 0, tests = 0;
     const uint32_t lane = threadIdx.x & 31u;
     const unsigned lane_lt = (1u << lane) - 1u;
-    uint32_t* const exchange = sm.masks + (threadIdx.x & ~31u); /* [field][this warp's 32 columns] */
+    /* [field][this warp's 32 columns]; ACCEL + BEAM: behind the slots (and the sort scratch) */
+    uint32_t* const exchange = (ACCEL ? reinterpret_cast<uint32_t*>(smem_raw + RT3_SLOT_BYTES + (BIN ? RT3_BIN_SCRATCH_BYTES : 0)) : sm.masks) + (threadIdx.x & ~31u);
     static_assert(RT3_RAYS * RT3_CHUNK_WORDS >= 8, "the exchange area needs eight mask words per thread");
     rt3_chunk chunk;
     chunk.cur = chunk.end = chunk.start = 0; chunk.pixel0 = chunk.sample0 = 0; chunk.dry = false;
     /* BEAM: this warp's candidate mask for the primary rays of its current chunk, and what went through it */
     rt3_beam* const beam = reinterpret_cast<rt3_beam*>(smem_raw + rt3_smem_bytes(RESIDENT, true)) + (threadIdx.x >> 5);
+    rt3_abeam* const abeam = reinterpret_cast<rt3_abeam*>(smem_raw + RT3_SLOT_BYTES + (BIN ? RT3_BIN_SCRATCH_BYTES : 0) + RT3_ABEAM_EXCHANGE_BYTES) + (threadIdx.x >> 5); /* ACCEL */
     uint32_t beam_rays = 0, beam_tests = 0;
     chunk.beam_ok = false; chunk.beam_candidates = 0u;
 
@@ -1041,7 +1180,7 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
                  * turn: under a condition they cost the sweep its uniform loads, see above) */
                 const uint32_t want_n = slot_turn ? 0u : (n_free - filled < 32u ? n_free - filled : 32u);
                 uint32_t p = 0, sample = 0;
-                const bool got = claim_item_beam(lane < want_n, chunk, P, &counters[0], p, sample, S, C, beam);
+                const bool got = claim_item_beam<ACCEL>(lane < want_n, chunk, P, &counters[0], p, sample, S, C, beam, B, abeam, exchange, visits);
                 __syncwarp(); /* a new chunk's candidate list is in shared memory */
                 if (slot_turn) {
                     s.bounce = slot_word(sm, turn, RT3_F_BOUNCE);
@@ -1054,7 +1193,8 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
                 } else {
                     if (got) { start_path(s, C, P, p, sample); have = true; }
                     if (chunk.beam_ok) { /* warp-uniform */
-                        beam_closest_hit(S, beam, chunk.beam_candidates, got, s.o, s.d, best);
+                        if constexpr (ACCEL) { beam_closest_hit_bvh(S, abeam, chunk.beam_candidates, got, s.o, s.d, best); }
+                        else { beam_closest_hit(S, beam, chunk.beam_candidates, got, s.o, s.d, best); }
                         shade = got;
                         if (got) { beam_rays++; beam_tests += chunk.beam_candidates; }
                     }
@@ -1098,8 +1238,14 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
                 if (chunk.dry) { break; } /* warps run independently */
                 continue;                 /* every path of this round ended with its primary ray (sky): nothing to sweep, on to the next items */
             }
-            if (chunk.dry && warp_live_slots(sm) <= RT3_TAIL_RAYS) { sweep_slots_by_primitive(S, sm); } /* warp-uniform */
-            else { sweep_slots<RESIDENT, SPHERES_ONLY>(S, sm, phase); }
+            if constexpr (ACCEL) {
+                if (BIN == 2) { traverse_slots_warp_sorted<false>(S, B, sm, bin, visits, tests); }
+                else if (BIN == 3) { traverse_slots_warp_sorted<true>(S, B, sm, bin, visits, tests); }
+                else { traverse_slots(S, B, sm, visits, tests); }
+            } else {
+                if (chunk.dry && warp_live_slots(sm) <= RT3_TAIL_RAYS) { sweep_slots_by_primitive(S, sm); } /* warp-uniform */
+                else { sweep_slots<RESIDENT, SPHERES_ONLY>(S, sm, phase); }
+            }
         }
     } else
     for (;;) {
@@ -1191,10 +1337,10 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
     for (int off = 16; off > 0; off >>= 1) { rays += __shfl_down_sync(0xffffffffu, rays, off); }
     if ((threadIdx.x & 31) == 0 && rays) { atomicAdd(&counters[1], rays); }
     if (ACCEL) { count_accel(visits, tests, counters); }
-    if (BEAM) { /* counters[2], [3] (the hierarchy's in ACCEL kernels): primary rays traced against a candidate list, exact tests they ran */
+    if (BEAM) { /* counters[2], [3] ([5], [6] in ACCEL kernels, where the hierarchy has those): primary rays traced against a candidate list, exact tests they ran */
         unsigned long long br = beam_rays, bt = beam_tests;
         for (int off = 16; off > 0; off >>= 1) { br += __shfl_down_sync(0xffffffffu, br, off); bt += __shfl_down_sync(0xffffffffu, bt, off); }
-        if ((threadIdx.x & 31) == 0 && br) { atomicAdd(&counters[2], br); atomicAdd(&counters[3], bt); }
+        if ((threadIdx.x & 31) == 0 && br) { atomicAdd(&counters[ACCEL ? 5 : 2], br); atomicAdd(&counters[ACCEL ? 6 : 3], bt); }
     }
 }
 

@@ -344,6 +344,7 @@ void CudaRenderer::render_samples(Camera& camera, uint32_t first_sample, bool ac
         if (i == 0) { total = st; continue; }
         total.rays += st.rays; total.sphere_tests += st.sphere_tests; total.face_tests += st.face_tests;
         total.accel_node_visits += st.accel_node_visits; total.accel_prim_tests += st.accel_prim_tests;
+        total.beam_rays += st.beam_rays; total.beam_tests += st.beam_tests;
         total.rows_rendered += st.rows_rendered; total.kernel_launches += st.kernel_launches;
         if (st.device_ms > total.device_ms) { total.device_ms = st.device_ms; }
         if (st.trace_kernel_ms > total.trace_kernel_ms) { total.trace_kernel_ms = st.trace_kernel_ms; }

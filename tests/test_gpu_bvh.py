@@ -118,6 +118,42 @@ def test_mesh_path_tracing_through_the_hierarchy(gpu_ctx):
     assert np.array_equal(tree, brute)
 
 
+def test_primary_candidate_lists_through_the_hierarchy(gpu_ctx, monkeypatch):
+    """Hierarchy kernels trace the primary rays of a chunk of path items against the candidates a beam's walk of the trees collected
+    (rt3_kernels.cuh, beam_for_chunk_bvh): the frame is the plain traversal's (RT3_BEAM_BVH=0) and the oracle's bit for bit -- sphere
+    scenes with thin lens and without, the un-jittered sphere cloud of C5, a mesh with spheres (sorted traversal), a row partition --
+    and at many samples per pixel most primary rays go that way."""
+    g, mesh = load_golden("default_400x225")
+    cases = [(scenes.rtiow_cover(96, 64), 96, 64, dict(spp=64, max_depth=50, seed=3), True, True),
+             (scenes.rtiow_four_spheres(64, 36), 64, 36, dict(spp=300, max_depth=50, seed=5), True, True),
+             (scenes.random_spheres(20000, width=96, height=54), 96, 54, dict(spp=256, max_depth=1, seed=1, flags=abi.FLAG_NO_JITTER), True, False),
+             ((mesh, abi.reference_camera(96, 54)), 96, 54, dict(spp=48, max_depth=8, seed=11), False, False),
+             (scenes.rtiow_cover(97, 61), 97, 61, dict(spp=40, max_depth=50, seed=7, tile_rows=3, part_index=1, part_count=2), False, False),
+             (scenes.rtiow_cover(64, 40), 64, 40, dict(spp=2, max_depth=50, seed=9), True, False)]
+    seen = 0
+    for (scene, cam), w, h, kw, with_oracle, expect_beams in cases:
+        flags = kw.pop("flags", 0)
+        gpu_ctx.upload(scene)
+        p = abi.make_params(w, h, mode=abi.MODE_PATHTRACE, flags=flags | abi.FLAG_BVH, **kw)
+        monkeypatch.setenv("RT3_BEAM_BVH", "0")
+        plain = gpu_ctx.render(cam, p).copy()
+        st0 = gpu_ctx.stats()
+        assert st0.beam_rays == 0
+        monkeypatch.delenv("RT3_BEAM_BVH")
+        beam = gpu_ctx.render(cam, p).copy()
+        st1 = gpu_ctx.stats()
+        assert np.array_equal(plain, beam), f"{int((plain != beam).sum())} pixels differ ({w}x{h}, {kw})"
+        assert st1.rays == st0.rays and st1.accel == 1 and st1.accel_stack_overflows == 0
+        seen += st1.beam_rays
+        if expect_beams:
+            assert st1.beam_rays > 0.5 * w * h * kw["spp"], "most primary rays should find a candidate list"
+            assert st1.accel_node_visits < st0.accel_node_visits
+        if with_oracle:
+            cpu, _, rays = ol.oracle_pathtrace(scene, cam, abi.make_params(w, h, mode=abi.MODE_PATHTRACE, flags=flags, **kw))
+            assert rays == st1.rays and np.array_equal(beam, cpu)
+    assert seen > 0
+
+
 def test_rebuild_after_new_upload(gpu_ctx):
     w, h = 64, 36
     cam = abi.reference_camera(w, h)
