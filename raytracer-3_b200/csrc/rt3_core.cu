@@ -408,10 +408,12 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     bool beam = !accel && resident && spheres_only;
     if (const char* e = getenv("RT3_BEAM")) { beam = beam && atoi(e) != 0; }
     ctx->stats_beam = beam;
-    /* the same through the hierarchy (the beam walks the trees once per chunk of path items): every hierarchy kernel but the CTA-wide sort
-     * of few-spp calls, whose chunks span too many pixels for a beam anyway; RT3_BEAM_BVH=0 switches it off */
-    bool beam_accel = accel && bin != 1 && bin != 2;
-    if (const char* e = getenv("RT3_BEAM_BVH")) { beam_accel = beam_accel && atoi(e) != 0; }
+    /* the same through the hierarchy (the beam walks the trees once per chunk of path items): the unsorted hierarchy kernel, i.e. sphere scenes and
+     * small meshes. Measured (call AG, profiles/r02ag_variants.jsonl): C5 45.7 -> 27.5 ms, C2 through the hierarchy 129.4 -> 117.4 ms; under the sorted
+     * traversal of large meshes it gains nothing (C3 325.1 -> 327.8 ms: the primary rays of such a scene are its cheap rays, and the warp-wide
+     * regeneration the beams need is the slower one there), so that kernel takes it only on request: RT3_BEAM_BVH=1 (0: never) */
+    bool beam_accel = accel && bin == 0;
+    if (const char* e = getenv("RT3_BEAM_BVH")) { beam_accel = accel && (bin == 0 || bin == 3) && atoi(e) != 0; }
     ctx->stats_beam_accel = beam_accel;
     rc = (beam_accel && bin == 3) ? launch_pathtrace<true, false, true, 3, true>(ctx, *cam, kp, smem + RT3_BIN_SCRATCH_BYTES + RT3_ABEAM_BYTES, stream)
        : beam_accel ? launch_pathtrace<true, false, true, 0, true>(ctx, *cam, kp, smem + RT3_ABEAM_BYTES, stream)

@@ -902,11 +902,11 @@ __device__ __forceinline__ void beam_for_chunk(const rt3_scene_view& S, const rt
 #define RT3_ABEAM_MAX_PIXELS 16u
 #endif
 #ifndef RT3_ABEAM_MAX_CANDIDATES
-#define RT3_ABEAM_MAX_CANDIDATES 128u    /* a beam does not stop at the first hit: on BASELINE C5 (10^6 spheres, four pixels per chunk) it meets 56 primitives on
+#define RT3_ABEAM_MAX_CANDIDATES 192u    /* a beam does not stop at the first hit: on BASELINE C5 (10^6 spheres, four pixels per chunk) it meets 56 primitives on
                                           * average and up to 150 (CPU model of the walk); 128 exact tests at full lanes still cost less than 129 node visits at a third */
 #endif
 #define RT3_ABEAM_LEVEL 192u             /* nodes per level of the walk: C5 reaches 100 on average, 153 at most in the same model */
-struct rt3_abeam {                        /* one per warp, in shared memory behind the exchange area */
+struct __align__(16) rt3_abeam {          /* one per warp, in shared memory behind the exchange area */
     uint32_t list[RT3_ABEAM_MAX_CANDIDATES]; /* candidate primitives of the warp's current chunk (global ids, no particular order) */
 };
 #define RT3_ABEAM_EXCHANGE_BYTES (12 * RT3_CTA_THREADS * 4) /* the hierarchy kernels have no survivor masks to alias the exchange area on */
@@ -1004,20 +1004,48 @@ __device__ __forceinline__ void beam_for_chunk_bvh(const rt3_bvh_view& B, const 
     c.beam_ok = ok; c.beam_candidates = n_candidates;
 }
 
-/* Closest hit of a primary ray among the candidates the beam's walk collected: the leaf tests of bvh_closest_hit (path mode). */
+/* Closest hit of a primary ray among the candidates the beam's walk collected: the leaf tests of bvh_closest_hit (path mode). Four
+ * candidates at a time when they are all spheres -- their records are loaded together, so that a lane waits for one load instead of four
+ * in a row (the tests of one ray depend on each other through `best` only) -- and one by one otherwise. */
+#ifndef RT3_ABEAM_GROUP
+#define RT3_ABEAM_GROUP 1
+#endif
 __device__ __forceinline__ void beam_closest_hit_bvh(const rt3_scene_view& S, const rt3_abeam* ab, uint32_t n_candidates, bool active, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
     best.t = __int_as_float(0x7f800000);
     best.prim = RT3_NO_HIT;
 #pragma unroll 1
-    for (uint32_t i = 0; i < n_candidates; i++) {
-        const uint32_t prim = ab->list[i]; /* warp-uniform */
-        RT3_ASSERT(prim < S.n_prims);
-        if (prim < S.n_faces) {
-            if (active) { exact_face<false>(S, prim, o, d, RT3_TMIN, best); }
-        } else {
-            const float4 sp = __ldg(&S.spheres[prim - S.n_faces]);
-            if (active) { exact_sphere_path<false>(prim, sp, o, d, best); }
+    for (uint32_t i = 0; i < n_candidates;) { /* i stays a multiple of four up to the last group */
+        const uint32_t g = n_candidates - i < 4u ? n_candidates - i : 4u;
+        bool done = false;
+#if RT3_ABEAM_GROUP
+        if (g == 4u) {
+            const uint4 p = *reinterpret_cast<const uint4*>(&ab->list[i]); /* warp-uniform */
+            RT3_ASSERT(p.x < S.n_prims && p.y < S.n_prims && p.z < S.n_prims && p.w < S.n_prims);
+            if (min(min(p.x, p.y), min(p.z, p.w)) >= S.n_faces) {
+                const float4 s0 = __ldg(&S.spheres[p.x - S.n_faces]), s1 = __ldg(&S.spheres[p.y - S.n_faces]), s2 = __ldg(&S.spheres[p.z - S.n_faces]),
+                             s3 = __ldg(&S.spheres[p.w - S.n_faces]);
+                if (active) {
+                    exact_sphere_path<false>(p.x, s0, o, d, best); exact_sphere_path<false>(p.y, s1, o, d, best);
+                    exact_sphere_path<false>(p.z, s2, o, d, best); exact_sphere_path<false>(p.w, s3, o, d, best);
+                }
+                done = true;
+            }
         }
+#endif
+        if (!done) {
+#pragma unroll 1
+            for (uint32_t j = 0; j < g; j++) {
+                const uint32_t prim = ab->list[i + j]; /* warp-uniform */
+                RT3_ASSERT(prim < S.n_prims);
+                if (prim < S.n_faces) {
+                    if (active) { exact_face<false>(S, prim, o, d, RT3_TMIN, best); }
+                } else {
+                    const float4 sp = __ldg(&S.spheres[prim - S.n_faces]);
+                    if (active) { exact_sphere_path<false>(prim, sp, o, d, best); }
+                }
+            }
+        }
+        i += g;
     }
 }
 
