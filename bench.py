@@ -388,7 +388,9 @@ def main():
         sb = ctx.stats()
         hierarchy = {"value": sb.rays / (sb.device_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": sb.device_ms, "build_ms": sb.accel_build_ms,
                      "node_visits_per_ray": sb.accel_node_visits / max(sb.rays, 1), "prim_tests_per_ray": sb.accel_prim_tests / max(sb.rays, 1),
-                     "note": "same workload through the device-built BVH (identical frame); informational, the metric is the brute-force sweep"}
+                     "beam_rays": sb.beam_rays, "beam_tests_per_ray": sb.beam_tests / max(sb.beam_rays, 1),
+                     "note": "same workload through the device-built BVH (identical frame; primary rays against the candidates of a beam's walk of the trees, "
+                             "every other ray segment by traversal); informational, the metric is the brute-force sweep"}
 
     # ---- BASELINE configs[3] (C4: the same scene at 3840x2160, 1024 spp -- the configuration named for 2/4/8 GPUs), as an extra
     #      key of the same line: device-timed like `value`, same split and frame end, assembled frame checked (N>1) ----

@@ -246,6 +246,24 @@ __device__ __forceinline__ void exact_sphere_path(uint32_t prim, float4 sp, rt3_
     if (disc >= 0.0f && t >= RT3_TMIN && closer<ORDERED>(t, prim, best)) { best.prim = prim; best.t = t; }
 }
 
+/* The same test for callers whose lanes test the SAME sphere at the same time (the candidate lists of a chunk's primary rays,
+ * rt3_kernels.cuh): there most candidates are missed by every lane of the warp, and a branch on the discriminant skips the
+ * square root and the root selection for all of them -- 13 instructions instead of 37 per missed candidate. Same arithmetic,
+ * same result. */
+template <bool ORDERED>
+__device__ __forceinline__ void exact_sphere_path_coherent(uint32_t prim, float4 sp, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
+    rt3_vec3 oc = o - v3(sp.x, sp.y, sp.z);
+    float h = __fmaf_rn(oc.x, d.x, __fmaf_rn(oc.y, d.y, oc.z * d.z));
+    float c = __fmaf_rn(oc.x, oc.x, __fmaf_rn(oc.y, oc.y, __fmaf_rn(oc.z, oc.z, -(sp.w * sp.w))));
+    float disc = __fmaf_rn(h, h, -c);
+    if (disc >= 0.0f) {
+        float sq = sqrtf(disc);
+        const float t1 = -h - sq, t2 = -h + sq;
+        const float t = t1 >= RT3_TMIN ? t1 : t2;
+        if (t >= RT3_TMIN && closer<ORDERED>(t, prim, best)) { best.prim = prim; best.t = t; }
+    }
+}
+
 /* Records of scenes up to RT3_CONST_PRIMS live in the constant bank: the sweep
  * reads them through uniform registers (SASS LDCU), so the packed FMAs take the
  * primitive operand from the uniform datapath and only the ray's constants and

@@ -819,6 +819,9 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
 #ifndef RT3_BEAM_MAX_CANDIDATES
 #define RT3_BEAM_MAX_CANDIDATES 48u
 #endif
+#ifndef RT3_BEAM_EARLY_OUT
+#define RT3_BEAM_EARLY_OUT 1 /* exact_sphere_path_coherent in the candidate tests of the sweep's BEAM kernel */
+#endif
 #ifndef RT3_BEAM_BATCHES
 #define RT3_BEAM_BATCHES 4u /* regeneration batches per round at most (the first takes up to 32 of the warp's free slots, the next ones the rest and
                              * the slots of paths that ended with their primary ray; what is still free after that waits for the next round).
@@ -1010,6 +1013,14 @@ __device__ __forceinline__ void beam_for_chunk_bvh(const rt3_bvh_view& B, const 
 #ifndef RT3_ABEAM_GROUP
 #define RT3_ABEAM_GROUP 1
 #endif
+#ifndef RT3_ABEAM_EARLY_OUT
+#define RT3_ABEAM_EARLY_OUT 1 /* the lanes test the same sphere: leave at the discriminant when it is negative (exact_sphere_path_coherent) */
+#endif
+#if RT3_ABEAM_EARLY_OUT
+#define RT3_ABEAM_SPHERE_TEST exact_sphere_path_coherent<false>
+#else
+#define RT3_ABEAM_SPHERE_TEST exact_sphere_path<false>
+#endif
 __device__ __forceinline__ void beam_closest_hit_bvh(const rt3_scene_view& S, const rt3_abeam* ab, uint32_t n_candidates, bool active, rt3_vec3 o, rt3_vec3 d, rt3_hit& best) {
     best.t = __int_as_float(0x7f800000);
     best.prim = RT3_NO_HIT;
@@ -1025,8 +1036,8 @@ __device__ __forceinline__ void beam_closest_hit_bvh(const rt3_scene_view& S, co
                 const float4 s0 = __ldg(&S.spheres[p.x - S.n_faces]), s1 = __ldg(&S.spheres[p.y - S.n_faces]), s2 = __ldg(&S.spheres[p.z - S.n_faces]),
                              s3 = __ldg(&S.spheres[p.w - S.n_faces]);
                 if (active) {
-                    exact_sphere_path<false>(p.x, s0, o, d, best); exact_sphere_path<false>(p.y, s1, o, d, best);
-                    exact_sphere_path<false>(p.z, s2, o, d, best); exact_sphere_path<false>(p.w, s3, o, d, best);
+                    RT3_ABEAM_SPHERE_TEST(p.x, s0, o, d, best); RT3_ABEAM_SPHERE_TEST(p.y, s1, o, d, best);
+                    RT3_ABEAM_SPHERE_TEST(p.z, s2, o, d, best); RT3_ABEAM_SPHERE_TEST(p.w, s3, o, d, best);
                 }
                 done = true;
             }
@@ -1041,7 +1052,7 @@ __device__ __forceinline__ void beam_closest_hit_bvh(const rt3_scene_view& S, co
                     if (active) { exact_face<false>(S, prim, o, d, RT3_TMIN, best); }
                 } else {
                     const float4 sp = __ldg(&S.spheres[prim - S.n_faces]);
-                    if (active) { exact_sphere_path<false>(prim, sp, o, d, best); }
+                    if (active) { RT3_ABEAM_SPHERE_TEST(prim, sp, o, d, best); }
                 }
             }
         }
@@ -1105,7 +1116,11 @@ __device__ __forceinline__ void beam_closest_hit(const rt3_scene_view& S, const 
         const uint32_t prim = beam->list[i];
         RT3_ASSERT(prim < S.n_prims);
         const float4 sp = __ldg(&S.spheres[prim]);
+#if RT3_BEAM_EARLY_OUT
+        if (active) { exact_sphere_path_coherent<true>(prim, sp, o, d, best); }
+#else
         if (active) { exact_sphere_path<true>(prim, sp, o, d, best); }
+#endif
     }
 }
 
