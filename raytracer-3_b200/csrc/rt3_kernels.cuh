@@ -908,6 +908,9 @@ __device__ __forceinline__ void beam_for_chunk(const rt3_scene_view& S, const rt
 #define RT3_ABEAM_MAX_CANDIDATES 192u    /* a beam does not stop at the first hit: on BASELINE C5 (10^6 spheres, four pixels per chunk) it meets 56 primitives on
                                           * average and up to 150 (CPU model of the walk); 128 exact tests at full lanes still cost less than 129 node visits at a third */
 #endif
+#ifndef RT3_ABEAM_BATCHES
+#define RT3_ABEAM_BATCHES 16u            /* regeneration batches per round at most: a scene of depth 1 (C5) never fills a slot, and every round pays RT3_RAYS idle slot turns */
+#endif
 #define RT3_ABEAM_LEVEL 192u             /* nodes per level of the walk: C5 reaches 100 on average, 153 at most in the same model */
 struct __align__(16) rt3_abeam {          /* one per warp, in shared memory behind the exchange area */
     uint32_t list[RT3_ABEAM_MAX_CANDIDATES]; /* candidate primitives of the warp's current chunk (global ids, no particular order) */
@@ -1213,7 +1216,7 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
                         for (int r = 0; r < R; r++) { my_rank[r] = rank_now[r]; }
                     }
                 }
-                if (!slot_turn && (filled >= n_free || chunk.dry || turn >= R + RT3_BEAM_BATCHES)) { break; }
+                if (!slot_turn && (filled >= n_free || chunk.dry || turn >= R + (int) (ACCEL ? RT3_ABEAM_BATCHES : RT3_BEAM_BATCHES))) { break; }
                 rt3_path s;
                 s.o = s.d = s.thr = v3(0.0f, 0.0f, 0.0f); s.key = 0u; s.pix = 0u; s.bounce = RT3_NO_HIT;
                 rt3_hit best;
