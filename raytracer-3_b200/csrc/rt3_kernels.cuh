@@ -819,6 +819,11 @@ __device__ __forceinline__ void shade_path(rt3_path& s, const rt3_hit& best, con
 #ifndef RT3_BEAM_MAX_CANDIDATES
 #define RT3_BEAM_MAX_CANDIDATES 48u
 #endif
+#ifndef RT3_BEAM_MIN_BATCH
+#define RT3_BEAM_MIN_BATCH 8u /* a further regeneration batch of a round runs only for at least this many free slots (a batch turn costs the warp about as much
+                               * as sweeping nine slots); what stays free is filled by the first batch of the next round. C2, call AK
+                               * (profiles/r02ak_variants.jsonl): 1: 116.12 ms, 4: 116.02, 8: 115.66, 16: 116.60 */
+#endif
 #ifndef RT3_BEAM_EARLY_OUT
 #define RT3_BEAM_EARLY_OUT 1 /* exact_sphere_path_coherent in the candidate tests of the sweep's BEAM kernel */
 #endif
@@ -1216,7 +1221,7 @@ pathtrace_kernel(rt3_scene_view S, rt3_bvh_view B, rt3_camera cam, rt3_kparams P
                         for (int r = 0; r < R; r++) { my_rank[r] = rank_now[r]; }
                     }
                 }
-                if (!slot_turn && (filled >= n_free || chunk.dry || turn >= R + (int) (ACCEL ? RT3_ABEAM_BATCHES : RT3_BEAM_BATCHES))) { break; }
+                if (!slot_turn && (filled + (turn > R ? RT3_BEAM_MIN_BATCH : 1u) > n_free || chunk.dry || turn >= R + (int) (ACCEL ? RT3_ABEAM_BATCHES : RT3_BEAM_BATCHES))) { break; }
                 rt3_path s;
                 s.o = s.d = s.thr = v3(0.0f, 0.0f, 0.0f); s.key = 0u; s.pix = 0u; s.bounce = RT3_NO_HIT;
                 rt3_hit best;
