@@ -65,3 +65,31 @@ def test_streamed_sweep_stages_tiles_with_bulk_copies(sass, needles):
 def test_accumulation_is_a_64_bit_reduction(sass, needle):
     ops = kernel(sass, needle)
     assert any(op.startswith("RED") and "64" in op for op in ops)
+
+
+@pytest.fixture(scope="module")
+def resources(built):
+    """{mangled kernel name: (registers, spill-free?)} from cuobjdump -res-usage."""
+    text = subprocess.run(["cuobjdump", "-res-usage", abi.CORE_LIB_PATH], check=True, capture_output=True, text=True).stdout
+    out = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", text):
+        out[m.group(1)] = (int(m.group(2)), int(m.group(3)), int(m.group(5)))
+    return out
+
+
+# (instantiation, register cap that keeps the resident CTAs the launch bounds ask for, largest stack frame: the traversal's 128 x 8-byte
+# stack + the path state, or the tail routine's frame in the sweep kernels)
+@pytest.mark.parametrize("needle,max_regs,max_stack", [
+    ("pathtrace_kernelILb1ELb1ELb0ELi0ELb0", 73, 256),    # sweep, resident spheres: 7 CTAs of 128 threads per SM
+    ("pathtrace_kernelILb1ELb1ELb0ELi0ELb1", 73, 256),    # ... with the primary rays through candidate lists (the headline kernel)
+    ("pathtrace_kernelILb1ELb0ELb1ELi0ELb0", 85, 1200),   # hierarchy, 6 CTAs per SM
+    ("pathtrace_kernelILb1ELb0ELb1ELi3ELb0", 85, 1200),   # ... sorted traversal
+    ("pathtrace_kernelILb1ELb0ELb1ELi0ELb1", 85, 1200),   # ... with the beams (sphere scenes, small meshes)
+    ("pathtrace_kernelILb1ELb0ELb1ELi3ELb1", 85, 1200),   # ... sorted traversal with the beams (RT3_BEAM_BVH=1)
+])
+def test_render_kernels_keep_their_occupancy(resources, needle, max_regs, max_stack):
+    names = [n for n in resources if needle in n]
+    assert len(names) == 1, names
+    regs, stack, local = resources[names[0]]
+    assert regs <= max_regs, f"{regs} registers: fewer resident CTAs per SM than the kernel was tuned for"
+    assert stack <= max_stack and local == 0, f"stack {stack} B, local {local} B: the kernel spills"
