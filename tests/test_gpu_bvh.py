@@ -122,7 +122,10 @@ def test_primary_candidate_lists_through_the_hierarchy(gpu_ctx, monkeypatch):
     """Hierarchy kernels trace the primary rays of a chunk of path items against the candidates a beam's walk of the trees collected
     (rt3_kernels.cuh, beam_for_chunk_bvh): the frame is the plain traversal's (RT3_BEAM_BVH=0) and the oracle's bit for bit -- sphere
     scenes with thin lens and without, the un-jittered sphere cloud of C5, a mesh with spheres (sorted traversal), a row partition --
-    and at many samples per pixel most primary rays go that way."""
+    and at many samples per pixel most primary rays go that way. (Since call AH the sorted traversal of large meshes takes beams only on request,
+    RT3_BEAM_BVH=1, because they gain nothing there; for the mesh case below the two renders are therefore the same kernel by default. That
+    instantiation was compared with the plain traversal and, on the C3 bands, with the oracle when it was the default: call AG,
+    profiles/r02ag_parity.txt, r02ag_variants.jsonl.)"""
     g, mesh = load_golden("default_400x225")
     cases = [(scenes.rtiow_cover(96, 64), 96, 64, dict(spp=64, max_depth=50, seed=3), True, True),
              (scenes.rtiow_four_spheres(64, 36), 64, 36, dict(spp=300, max_depth=50, seed=5), True, True),
