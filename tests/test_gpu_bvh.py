@@ -123,9 +123,8 @@ def test_primary_candidate_lists_through_the_hierarchy(gpu_ctx, monkeypatch):
     (rt3_kernels.cuh, beam_for_chunk_bvh): the frame is the plain traversal's (RT3_BEAM_BVH=0) and the oracle's bit for bit -- sphere
     scenes with thin lens and without, the un-jittered sphere cloud of C5, a mesh with spheres (sorted traversal), a row partition --
     and at many samples per pixel most primary rays go that way. (Since call AH the sorted traversal of large meshes takes beams only on request,
-    RT3_BEAM_BVH=1, because they gain nothing there; for the mesh case below the two renders are therefore the same kernel by default. That
-    instantiation was compared with the plain traversal and, on the C3 bands, with the oracle when it was the default: call AG,
-    profiles/r02ag_parity.txt, r02ag_variants.jsonl.)"""
+    RT3_BEAM_BVH=1, because they gain nothing there: the mesh case below asks for them; profiles/beam_bvh_sorted_check.py is the same comparison
+    as a script, call AO.)"""
     g, mesh = load_golden("default_400x225")
     cases = [(scenes.rtiow_cover(96, 64), 96, 64, dict(spp=64, max_depth=50, seed=3), True, True),
              (scenes.rtiow_four_spheres(64, 36), 64, 36, dict(spp=300, max_depth=50, seed=5), True, True),
@@ -143,8 +142,13 @@ def test_primary_candidate_lists_through_the_hierarchy(gpu_ctx, monkeypatch):
         st0 = gpu_ctx.stats()
         assert st0.beam_rays == 0
         monkeypatch.delenv("RT3_BEAM_BVH")
+        if scene is mesh:
+            monkeypatch.setenv("RT3_BEAM_BVH", "1")  # the sorted traversal takes beams only on request
         beam = gpu_ctx.render(cam, p).copy()
         st1 = gpu_ctx.stats()
+        monkeypatch.delenv("RT3_BEAM_BVH", raising=False)
+        if scene is mesh:
+            assert st1.beam_rays > 0
         assert np.array_equal(plain, beam), f"{int((plain != beam).sum())} pixels differ ({w}x{h}, {kw})"
         assert st1.rays == st0.rays and st1.accel == 1 and st1.accel_stack_overflows == 0
         seen += st1.beam_rays
