@@ -409,7 +409,7 @@ int enqueue_render(rt3_ctx* ctx, const rt3_camera* cam, const rt3_params* params
     if (const char* e = getenv("RT3_BEAM")) { beam = beam && atoi(e) != 0; }
     ctx->stats_beam = beam;
     /* the same through the hierarchy (the beam walks the trees once per chunk of path items): the unsorted hierarchy kernel, i.e. sphere scenes and
-     * small meshes. Measured (call AG, profiles/r02ag_variants.jsonl): C5 45.7 -> 27.5 ms, C2 through the hierarchy 129.4 -> 117.4 ms; under the sorted
+     * small meshes. Measured (call AG, profiles/r02ag_variants.jsonl): C5 45.7 -> 27.5 ms (17.0 after calls AH, AI), C2 through the hierarchy 129.4 -> 117.4 ms; under the sorted
      * traversal of large meshes it gains nothing (C3 325.1 -> 327.8 ms: the primary rays of such a scene are its cheap rays, and the warp-wide
      * regeneration the beams need is the slower one there), so that kernel takes it only on request: RT3_BEAM_BVH=1 (0: never) */
     bool beam_accel = accel && bin == 0;
